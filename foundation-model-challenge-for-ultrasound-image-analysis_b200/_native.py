@@ -1,0 +1,95 @@
+"""Shared plumbing for the two native modules (Swin encoder core, FPN decoder).
+
+Both keep their parameters as ``nn.Parameter`` *views* into one flat fp32 buffer whose layout is
+dictated by the C++ executors (``mtus_*_param_info``): the state-dict keys stay those of timm / smp
+(the reference checkpoints with ``model.state_dict()``, code/train.py:695), while the kernels see one
+contiguous parameter block and write one contiguous gradient block (one NCCL call per stage).
+"""
+
+import ctypes as C
+from typing import List, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def precision_to_dtype(precision: str):
+    if precision in ("bf16", "bfloat16"):
+        return _lib.BF16, torch.bfloat16
+    if precision in ("fp32", "float32"):
+        return _lib.F32, torch.float32
+    raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+
+
+def enumerate_params(info_fn, cfg) -> List[Tuple[str, int, Tuple[int, ...]]]:
+    out = []
+    name = C.create_string_buffer(128)
+    off, rank, shape = C.c_int64(), C.c_int(), (C.c_int64 * 4)()
+    idx = 0
+    while info_fn(C.byref(cfg), idx, name, C.byref(off), C.byref(rank), shape) == 0:
+        out.append((name.value.decode(), int(off.value), tuple(int(shape[i]) for i in range(rank.value))))
+        idx += 1
+    return out
+
+
+class FlatParamModule(nn.Module):
+    """nn.Module whose parameters are views of ``self._flat`` (fp32) at executor-defined offsets."""
+
+    def _init_flat(self, infos, total: int):
+        self._infos = infos
+        self._n_flat = int(total)
+        self._flat = torch.zeros(self._n_flat, dtype=torch.float32)
+        self._params_by_name = {}
+        for name, off, shape in infos:
+            parts = name.split(".")
+            mod = self
+            for p in parts[:-1]:
+                if not hasattr(mod, p):
+                    mod.add_module(p, nn.Module())
+                mod = getattr(mod, p)
+            numel = 1
+            for s in shape:
+                numel *= s
+            param = nn.Parameter(self._flat[off:off + numel].view(shape))
+            mod.register_parameter(parts[-1], param)
+            self._params_by_name[name] = (param, off, numel, shape)
+
+    def _apply(self, fn, recurse=True):
+        super()._apply(fn, recurse)
+        self._reflatten()
+        return self
+
+    def _reflatten(self):
+        first = next(iter(self._params_by_name.values()))[0]
+        flat = torch.zeros(self._n_flat, dtype=torch.float32, device=first.device)
+        with torch.no_grad():
+            for name, (param, off, numel, shape) in self._params_by_name.items():
+                view = flat[off:off + numel].view(shape)
+                view.copy_(param.data)
+                param.data = view
+        self._flat = flat
+
+    def flat_params(self) -> torch.Tensor:
+        """The flat fp32 parameter buffer; re-flattens if somebody re-pointed a parameter."""
+        base = self._flat.data_ptr()
+        for param, off, numel, shape in self._params_by_name.values():
+            if param.data_ptr() != base + 4 * off or param.dtype != torch.float32:
+                self._reflatten()
+                break
+        return self._flat
+
+    def ordered_params(self):
+        return [v[0] for v in self._params_by_name.values()]
+
+    def grad_views(self, flat_grad: torch.Tensor, needs):
+        out = []
+        for (param, off, numel, shape), need in zip(self._params_by_name.values(), needs):
+            out.append(flat_grad[off:off + numel].view(shape) if need else None)
+        return out
+
+
+def is_channels_last_view(t: torch.Tensor) -> bool:
+    """True when a [B,C,H,W] tensor is laid out NHWC in memory (dense)."""
+    return t.dim() == 4 and t.permute(0, 2, 3, 1).is_contiguous()

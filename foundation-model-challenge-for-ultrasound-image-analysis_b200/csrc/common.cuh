@@ -1,0 +1,157 @@
+// Shared device helpers for the MTUS-Net B200 hot path (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/mtus_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+#define MTUS_CHECK_ARG(cond) do { if (!(cond)) return MTUS_ERR_BAD_ARG; } while (0)
+#define MTUS_LAUNCH_STATUS() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; } while (0)
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- 8-wide vector load/store, fp32 compute -------------------------------------------------
+template <typename T> struct IO;
+
+template <> struct IO<float> {
+  static __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  static __device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  }
+  static __device__ __forceinline__ void store4(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  static __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+
+template <> struct IO<bf16> {
+  static __device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+    uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+  static __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+    uint4 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = r;
+  }
+  static __device__ __forceinline__ void load4(const bf16* p, float (&v)[4]) {
+    uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+    float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  static __device__ __forceinline__ void store4(bf16* p, const float (&v)[4]) {
+    uint2 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+    h[0] = __floats2bfloat162_rn(v[0], v[1]);
+    h[1] = __floats2bfloat162_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = r;
+  }
+  static __device__ __forceinline__ float ld(const bf16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ void st(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// exact-erf GELU (timm Mlp uses nn.GELU()) and its derivative
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// ---- fused GEMM epilogue (shared by the SIMT fp32 GEMM and the tcgen05 bf16 GEMM) -----------
+struct EpiParams {
+  const float* bias;       // [N] fp32 or null
+  int act;                 // 0 none | 1 GELU fwd (pre-activation also written to aux) | 2 GELU bwd (acc *= gelu'(aux))
+  void* aux;               // [M, ld_aux] in the activation dtype
+  int64_t ld_aux;
+  const void* res;         // residual in the activation dtype, or null
+  int64_t ld_res;
+  int res_mode;            // 1 same row | 2 nearest-x2 gather: row (b,y,x) of [B,H,W] reads row (b,y/2,x/2) of [B,H/2,W/2]
+  int H, W;
+  const float* rowscale;   // per-sample scale (drop-path mask / keep) or null
+  int rows_per_sample;
+  void* out;               // [M, ld_out]
+  int64_t ld_out;
+  int out_f32;             // 1: out is fp32 regardless of the activation dtype
+  int atomic;              // 1: atomicAdd into the fp32 out (split-K wgrad)
+};
+
+// Applies the epilogue to 4 consecutive columns (n0..n0+3) of row m.  nvalid = columns in range.
+template <typename T>
+__device__ __forceinline__ void epilogue4(const EpiParams& ep, int64_t m, int n0, int nvalid, float (&v)[4]) {
+  if (ep.bias) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (j < nvalid) v[j] += __ldg(ep.bias + n0 + j);
+  }
+  if (ep.act == 1) {
+    T* a = reinterpret_cast<T*>(ep.aux) + m * ep.ld_aux + n0;
+    if (nvalid == 4) IO<T>::store4(a, v); else for (int j = 0; j < nvalid; ++j) IO<T>::st(a + j, v[j]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = gelu_f(v[j]);
+  } else if (ep.act == 2) {
+    const T* a = reinterpret_cast<const T*>(ep.aux) + m * ep.ld_aux + n0;
+    float h[4] = {0.f, 0.f, 0.f, 0.f};
+    if (nvalid == 4) IO<T>::load4(a, h); else for (int j = 0; j < nvalid; ++j) h[j] = IO<T>::ld(a + j);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] *= gelu_grad_f(h[j]);
+  }
+  if (ep.rowscale) {
+    const float s = __ldg(ep.rowscale + m / ep.rows_per_sample);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] *= s;
+  }
+  if (ep.res) {
+    int64_t rm = m;
+    if (ep.res_mode == 2) {
+      const int64_t hw = (int64_t)ep.H * ep.W;
+      const int64_t b = m / hw;
+      const int rem = (int)(m - b * hw);
+      const int y = rem / ep.W, x = rem - y * ep.W;
+      rm = (b * (ep.H >> 1) + (y >> 1)) * (ep.W >> 1) + (x >> 1);
+    }
+    const T* r = reinterpret_cast<const T*>(ep.res) + rm * ep.ld_res + n0;
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    if (nvalid == 4) IO<T>::load4(r, t); else for (int j = 0; j < nvalid; ++j) t[j] = IO<T>::ld(r + j);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] += t[j];
+  }
+  if (ep.out_f32) {
+    float* o = reinterpret_cast<float*>(ep.out) + m * ep.ld_out + n0;
+    if (ep.atomic) { for (int j = 0; j < nvalid; ++j) atomicAdd(o + j, v[j]); }
+    else if (nvalid == 4) IO<float>::store4(o, v);
+    else for (int j = 0; j < nvalid; ++j) o[j] = v[j];
+  } else {
+    T* o = reinterpret_cast<T*>(ep.out) + m * ep.ld_out + n0;
+    if (nvalid == 4) IO<T>::store4(o, v); else for (int j = 0; j < nvalid; ++j) IO<T>::st(o + j, v[j]);
+  }
+}

@@ -1,0 +1,280 @@
+// LayerNorm forward / backward (bandwidth-bound; HBM roofline), with an optional fused
+// PatchMerging 2x2 gather on the input side.
+//
+// Replaces: timm LayerNorm call sites in SwinTransformerBlock.norm1/norm2, PatchEmbed.norm and
+// PatchMerging.norm (reached from /root/reference/code/models/encoders.py:104); the gather mode
+// replaces PatchMerging's reshape/permute/flatten copy.
+//
+// Layout: rows of C contiguous elements (NHWC tokens).  One warp (WPR=1) or four warps (WPR=4)
+// per row; each lane owns NV 8-element vectors (16 B for bf16, 32 B for fp32), statistics in
+// fp32 via a two-pass (mean, then centred variance) over registers, warp-shuffle reductions.
+// Algorithmic bytes: fwd 2*rows*C*s (+8 B/row stats), bwd 3*rows*C*s (+ dres: 4*rows*C*s).
+#include "common.cuh"
+
+struct MergeGeom { int B, H, W, C, Ho, Wo; };  // input [B,H,W,C] -> rows (b,i,j) of 4C columns
+
+template <typename T, int MODE>
+__device__ __forceinline__ const T* ln_src(const T* x, int64_t row, int col, int C, const MergeGeom& g, bool& valid) {
+  if (MODE == 0) { valid = true; return x + row * C + col; }
+  const int q = col / g.C, cc = col - q * g.C;          // q: 0 h0w0 | 1 h1w0 | 2 h0w1 | 3 h1w1
+  const int j = (int)(row % g.Wo); const int64_t t = row / g.Wo;
+  const int i = (int)(t % g.Ho); const int64_t b = t / g.Ho;
+  const int y = 2 * i + (q & 1), xx = 2 * j + (q >> 1);
+  valid = (y < g.H) && (xx < g.W);
+  return x + ((b * g.H + y) * (int64_t)g.W + xx) * g.C + cc;
+}
+
+template <typename T, int NV, int WPR, int MODE>
+__global__ void __launch_bounds__(128) ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, T* __restrict__ y,
+                                                     float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                     int64_t rows, int C, float eps, MergeGeom g) {
+  __shared__ float red[2][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rpb = 4 / WPR;                                    // rows per block-iteration
+  const int sub = (WPR == 1) ? 0 : warp;                      // which quarter of the row this warp owns
+  const float invC = 1.0f / (float)C;
+  for (int64_t row0 = (int64_t)blockIdx.x * rpb; row0 < rows; row0 += (int64_t)gridDim.x * rpb) {
+    const int64_t row = row0 + ((WPR == 1) ? warp : 0);
+    const bool active = row < rows;
+    float v[NV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = ((sub * NV + i) * 32 + lane) * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[i][k] = 0.f;
+      if (active && col < C) {
+        bool valid; const T* p = ln_src<T, MODE>(x, row, col, C, g, valid);
+        if (valid) IO<T>::load8(p, v[i]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += v[i][k];
+      }
+    }
+    s = warp_sum(s);
+    if (WPR > 1) {
+      if (lane == 0) red[0][warp] = s;
+      __syncthreads();
+      s = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+    }
+    const float mean = s * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = ((sub * NV + i) * 32 + lane) * 8;
+      if (active && col < C) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float d = v[i][k] - mean; q += d * d; }
+      }
+    }
+    q = warp_sum(q);
+    if (WPR > 1) {
+      if (lane == 0) red[1][warp] = q;
+      __syncthreads();
+      q = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+    }
+    const float rstd = rsqrtf(q * invC + eps);
+    if (active) {
+      if (lane == 0 && sub == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int col = ((sub * NV + i) * 32 + lane) * 8;
+        if (col < C) {
+          float gm[8], bt[8], o[8];
+          IO<float>::load8(gamma + col, gm);
+          IO<float>::load8(beta + col, bt);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = (v[i][k] - mean) * rstd * gm[k] + bt[k];
+          IO<T>::store8(y + row * C + col, o);
+        }
+      }
+    }
+    if (WPR > 1) __syncthreads();
+  }
+}
+
+template <typename T, int NV, int WPR, int MODE>
+__global__ void __launch_bounds__(128) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                     const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                                                     const float* __restrict__ rstd_in, const T* dres,
+                                                     T* dx, float* __restrict__ dgamma,
+                                                     float* __restrict__ dbeta, int64_t rows, int C, MergeGeom g) {
+  __shared__ float red[2][4];
+  extern __shared__ float acc_smem[];                         // WPR==1: [2][4 warps][C] partial dgamma/dbeta
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rpb = 4 / WPR;
+  const int sub = (WPR == 1) ? 0 : warp;
+  const float invC = 1.0f / (float)C;
+  float adg[NV][8], adb[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { adg[i][k] = 0.f; adb[i][k] = 0.f; }
+
+  for (int64_t row0 = (int64_t)blockIdx.x * rpb; row0 < rows; row0 += (int64_t)gridDim.x * rpb) {
+    const int64_t row = row0 + ((WPR == 1) ? warp : 0);
+    const bool active = row < rows;
+    const float mean = active ? mean_in[row] : 0.f, rstd = active ? rstd_in[row] : 0.f;
+    float xh[NV][8], gy[NV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = ((sub * NV + i) * 32 + lane) * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { xh[i][k] = 0.f; gy[i][k] = 0.f; }
+      if (active && col < C) {
+        float xv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dv[8], gm[8];
+        bool valid; const T* p = ln_src<T, MODE>(x, row, col, C, g, valid);
+        if (valid) IO<T>::load8(p, xv);
+        IO<T>::load8(dy + row * C + col, dv);
+        IO<float>::load8(gamma + col, gm);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          xh[i][k] = (xv[k] - mean) * rstd;
+          gy[i][k] = dv[k] * gm[k];
+          s1 += gy[i][k];
+          s2 += gy[i][k] * xh[i][k];
+          adg[i][k] += dv[k] * xh[i][k];
+          adb[i][k] += dv[k];
+        }
+      }
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (WPR > 1) {
+      if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
+      __syncthreads();
+      s1 = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+      s2 = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+    }
+    s1 *= invC; s2 *= invC;
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int col = ((sub * NV + i) * 32 + lane) * 8;
+        if (col < C) {
+          float o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = rstd * (gy[i][k] - s1 - xh[i][k] * s2);
+          bool valid; const T* p = ln_src<T, MODE>(x, row, col, C, g, valid);
+          if (valid) {
+            const int64_t off = p - x;
+            if (dres) {
+              float r[8]; IO<T>::load8(dres + off, r);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) o[k] += r[k];
+            }
+            IO<T>::store8(dx + off, o);
+          }
+        }
+      }
+    }
+    if (WPR > 1) __syncthreads();
+  }
+  // parameter gradients: reduce over the block, then one atomicAdd per column per block
+  if (WPR == 1) {
+    float* sg = acc_smem; float* sb = acc_smem + 4 * C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 8;
+      if (col < C) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sg[warp * C + col + k] = adg[i][k]; sb[warp * C + col + k] = adb[i][k]; }
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      atomicAdd(dgamma + c, sg[c] + sg[C + c] + sg[2 * C + c] + sg[3 * C + c]);
+      atomicAdd(dbeta + c, sb[c] + sb[C + c] + sb[2 * C + c] + sb[3 * C + c]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = ((sub * NV + i) * 32 + lane) * 8;
+      if (col < C) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { atomicAdd(dgamma + col + k, adg[i][k]); atomicAdd(dbeta + col + k, adb[i][k]); }
+      }
+    }
+  }
+}
+
+// ---- dispatch -------------------------------------------------------------------------------
+template <typename T, int MODE>
+static int ln_launch(bool fwd, const void* a0, const void* a1, const float* gamma, const float* beta_or_mean,
+                     const float* rstd_in, const void* dres, void* out, float* o1, float* o2, int64_t rows, int C,
+                     float eps, MergeGeom g, cudaStream_t st) {
+  if (rows == 0) return MTUS_OK;
+  MTUS_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 4096);
+  const int nvec = C / 8;                                      // 8-wide vectors per row
+#define LN_CASE(NV_, WPR_)                                                                                   \
+  {                                                                                                          \
+    const int rpb = 4 / WPR_;                                                                                \
+    int64_t blocks = (rows + rpb - 1) / rpb;                                                                 \
+    if (fwd) {                                                                                               \
+      if (blocks > 148 * 16) blocks = 148 * 16;                                                              \
+      ln_fwd_kernel<T, NV_, WPR_, MODE><<<(int)blocks, 128, 0, st>>>((const T*)a0, gamma, beta_or_mean,      \
+                                                                    (T*)out, o1, o2, rows, C, eps, g);       \
+    } else {                                                                                                 \
+      if (blocks > 148 * 4) blocks = 148 * 4;                                                                \
+      const size_t sm = (WPR_ == 1) ? (size_t)8 * C * sizeof(float) : 0;                                     \
+      ln_bwd_kernel<T, NV_, WPR_, MODE><<<(int)blocks, 128, sm, st>>>((const T*)a0, (const T*)a1, gamma,     \
+                                                                     beta_or_mean, rstd_in, (const T*)dres, \
+                                                                     (T*)out, o1, o2, rows, C, g);           \
+    }                                                                                                        \
+  }
+  if (nvec <= 32) LN_CASE(1, 1)
+  else if (nvec <= 64) LN_CASE(2, 1)
+  else if (nvec <= 96) LN_CASE(3, 1)
+  else if (nvec <= 128) LN_CASE(1, 4)
+  else if (nvec <= 256) LN_CASE(2, 4)
+  else if (nvec <= 384) LN_CASE(3, 4)
+  else LN_CASE(4, 4)
+#undef LN_CASE
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}
+
+extern "C" int mtus_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                                  float* rstd, int64_t rows, int C, float eps, int dtype, void* stream) {
+  MTUS_CHECK_ARG(x && gamma && beta && y && mean && rstd && rows >= 0);
+  MergeGeom g{};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MTUS_F32) return ln_launch<float, 0>(true, x, nullptr, gamma, beta, nullptr, nullptr, y, mean, rstd, rows, C, eps, g, st);
+  if (dtype == MTUS_BF16) return ln_launch<bf16, 0>(true, x, nullptr, gamma, beta, nullptr, nullptr, y, mean, rstd, rows, C, eps, g, st);
+  return MTUS_ERR_UNSUPPORTED;
+}
+
+extern "C" int mtus_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
+                                  const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
+                                  int64_t rows, int C, int dtype, void* stream) {
+  MTUS_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && rows >= 0);
+  MergeGeom g{};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MTUS_F32) return ln_launch<float, 0>(false, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, C, 0.f, g, st);
+  if (dtype == MTUS_BF16) return ln_launch<bf16, 0>(false, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, C, 0.f, g, st);
+  return MTUS_ERR_UNSUPPORTED;
+}
+
+extern "C" int mtus_patch_merge_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                                       float* rstd, int B, int H, int W, int C, float eps, int dtype, void* stream) {
+  MTUS_CHECK_ARG(x && gamma && beta && y && mean && rstd && B >= 0 && H > 0 && W > 0 && C % 8 == 0);
+  MergeGeom g{B, H, W, C, (H + 1) / 2, (W + 1) / 2};
+  const int64_t rows = (int64_t)B * g.Ho * g.Wo;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MTUS_F32) return ln_launch<float, 1>(true, x, nullptr, gamma, beta, nullptr, nullptr, y, mean, rstd, rows, 4 * C, eps, g, st);
+  if (dtype == MTUS_BF16) return ln_launch<bf16, 1>(true, x, nullptr, gamma, beta, nullptr, nullptr, y, mean, rstd, rows, 4 * C, eps, g, st);
+  return MTUS_ERR_UNSUPPORTED;
+}
+
+// dx is written at the (un-gathered) [B,H,W,C] positions; dres (same layout as x) is added if given.
+extern "C" int mtus_patch_merge_ln_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
+                                       const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
+                                       int B, int H, int W, int C, int dtype, void* stream) {
+  MTUS_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && B >= 0 && H > 0 && W > 0 && C % 8 == 0);
+  MergeGeom g{B, H, W, C, (H + 1) / 2, (W + 1) / 2};
+  const int64_t rows = (int64_t)B * g.Ho * g.Wo;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MTUS_F32) return ln_launch<float, 1>(false, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, 4 * C, 0.f, g, st);
+  if (dtype == MTUS_BF16) return ln_launch<bf16, 1>(false, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, 4 * C, 0.f, g, st);
+  return MTUS_ERR_UNSUPPORTED;
+}

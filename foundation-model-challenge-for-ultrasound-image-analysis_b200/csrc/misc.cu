@@ -1,0 +1,230 @@
+// Bandwidth-bound helpers: casts, column sums (bias gradients), per-sample row scaling (drop-path),
+// NHWC<->NCHW transposes (the reference's permute(0,3,1,2).contiguous(), code/models/encoders.py:106)
+// and the PatchEmbed im2col (timm PatchEmbed.proj as a K=48 GEMM).  All are coalesced, 16-byte
+// vectorised, grid-stride kernels; HBM roofline, algorithmic bytes = one read + one write of the tensor.
+#include "common.cuh"
+
+extern "C" int mtus_version(void) { return 100; }
+
+extern "C" const char* mtus_status_string(int s) {
+  if (s == MTUS_OK) return "ok";
+  if (s == MTUS_ERR_BAD_ARG) return "bad argument (shape / alignment / null pointer)";
+  if (s == MTUS_ERR_UNSUPPORTED) return "unsupported configuration";
+  if (s == MTUS_ERR_DRIVER) return "CUDA driver entry point / tensor-map encoding failed";
+  if (s > 0) return cudaGetErrorString((cudaError_t)s);
+  return "unknown";
+}
+
+static inline int grid_for(int64_t work_items, int threads, int max_blocks = 148 * 16) {
+  int64_t b = (work_items + threads - 1) / threads;
+  if (b > max_blocks) b = max_blocks;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+__global__ void cast_kernel(const float* __restrict__ s, bf16* __restrict__ d, int64_t n8, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    float v[8];
+    IO<float>::load8(s + i * 8, v);
+    IO<bf16>::store8(d + i * 8, v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n - n8 * 8)) {
+    const int64_t i = n8 * 8 + threadIdx.x;
+    d[i] = __float2bfloat16_rn(s[i]);
+  }
+}
+
+extern "C" int mtus_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  MTUS_CHECK_ARG(src && dst && n >= 0);
+  MTUS_CHECK_ARG(((uintptr_t)src & 31) == 0 && ((uintptr_t)dst & 15) == 0);
+  if (n == 0) return MTUS_OK;
+  cast_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n / 8, n);
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}
+
+// out[c] += sum_r x[r, c]
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t rows, int C,
+                                                     int64_t rows_per_chunk) {
+  __shared__ float red[8][32][9];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + tx) * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+  const int64_t r1 = min(rows, r0 + rows_per_chunk);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < C) {
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      float v[8];
+      IO<T>::load8(x + r * C + col, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[ty][tx][k] = acc[k];
+  __syncthreads();
+  if (ty == 0 && col < C) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += red[j][tx][k];
+      atomicAdd(out + col + k, s);
+    }
+  }
+}
+
+extern "C" int mtus_colsum(const void* x, float* out, int64_t rows, int C, int dtype, void* stream) {
+  MTUS_CHECK_ARG(x && out && rows >= 0 && C % 8 == 0);
+  if (rows == 0) return MTUS_OK;
+  const int gx = ceil_div(C, 256);
+  int64_t chunks = (148 * 4 + gx - 1) / gx;
+  const int64_t max_chunks = (rows + 63) / 64;
+  if (chunks > max_chunks) chunks = max_chunks;
+  const int64_t rpc = (rows + chunks - 1) / chunks;
+  dim3 grid(gx, (unsigned)((rows + rpc - 1) / rpc));
+  if (dtype == MTUS_F32) colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, out, rows, C, rpc);
+  else if (dtype == MTUS_BF16) colsum_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, out, rows, C, rpc);
+  else return MTUS_ERR_UNSUPPORTED;
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}
+
+template <typename T>
+__global__ void scale_rows_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ s, int rps,
+                                  int64_t n8, int C8) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const int64_t row = i / C8;
+    const float f = __ldg(s + row / rps);
+    float v[8];
+    IO<T>::load8(x + i * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] *= f;
+    IO<T>::store8(y + i * 8, v);
+  }
+}
+
+extern "C" int mtus_scale_rows(const void* x, void* y, const float* rowscale, int rows_per_sample, int64_t rows, int C,
+                               int dtype, void* stream) {
+  MTUS_CHECK_ARG(x && y && rowscale && rows_per_sample > 0 && C % 8 == 0);
+  const int64_t n8 = rows * (C / 8);
+  if (n8 == 0) return MTUS_OK;
+  if (dtype == MTUS_F32) scale_rows_kernel<float><<<grid_for(n8, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, rowscale, rows_per_sample, n8, C / 8);
+  else if (dtype == MTUS_BF16) scale_rows_kernel<bf16><<<grid_for(n8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, rowscale, rows_per_sample, n8, C / 8);
+  else return MTUS_ERR_UNSUPPORTED;
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}
+
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, int64_t n8) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    float u[8], v[8];
+    IO<T>::load8(a + i * 8, u);
+    IO<T>::load8(b + i * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) u[k] += v[k];
+    IO<T>::store8(y + i * 8, u);
+  }
+}
+
+extern "C" int mtus_add(const void* a, const void* b, void* y, int64_t n, int dtype, void* stream) {
+  MTUS_CHECK_ARG(a && b && y && n % 8 == 0);
+  if (n == 0) return MTUS_OK;
+  if (dtype == MTUS_F32) add_kernel<float><<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const float*)a, (const float*)b, (float*)y, n / 8);
+  else if (dtype == MTUS_BF16) add_kernel<bf16><<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, (bf16*)y, n / 8);
+  else return MTUS_ERR_UNSUPPORTED;
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}
+
+// ---- [B, HW, C] <-> [B, C, HW] via 32x32 shared-memory tiles (coalesced both sides) ----------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) transpose_kernel(const TI* __restrict__ x, TO* __restrict__ y, int R, int Cc) {
+  // per batch: in [R][Cc] -> out [Cc][R]
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const TI* xb = x + (int64_t)b * R * Cc;
+  TO* yb = y + (int64_t)b * R * Cc;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + i * 8, c = c0 + tx;
+    if (r < R && c < Cc) tile[ty + i * 8][tx] = IO<TI>::ld(xb + (int64_t)r * Cc + c);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + i * 8, r = r0 + tx;
+    if (r < R && c < Cc) IO<TO>::st(yb + (int64_t)c * R + r, tile[tx][ty + i * 8]);
+  }
+}
+
+template <typename TI, typename TO>
+static int transpose_launch(const void* x, void* y, int B, int R, int Cc, cudaStream_t st) {
+  if (B == 0) return MTUS_OK;
+  dim3 grid(ceil_div(Cc, 32), ceil_div(R, 32), B);
+  transpose_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)x, (TO*)y, R, Cc);
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}
+
+extern "C" int mtus_nhwc_to_nchw(const void* x, void* y, int B, int HW, int C, int dtype, int out_f32, void* stream) {
+  MTUS_CHECK_ARG(x && y && B >= 0 && HW > 0 && C > 0 && B <= 65535);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MTUS_F32) return transpose_launch<float, float>(x, y, B, HW, C, st);
+  if (dtype == MTUS_BF16) return out_f32 ? transpose_launch<bf16, float>(x, y, B, HW, C, st) : transpose_launch<bf16, bf16>(x, y, B, HW, C, st);
+  return MTUS_ERR_UNSUPPORTED;
+}
+
+extern "C" int mtus_nchw_to_nhwc(const void* x, void* y, int B, int HW, int C, int dtype, int in_f32, void* stream) {
+  MTUS_CHECK_ARG(x && y && B >= 0 && HW > 0 && C > 0 && B <= 65535);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MTUS_F32) return transpose_launch<float, float>(x, y, B, C, HW, st);
+  if (dtype == MTUS_BF16) return in_f32 ? transpose_launch<float, bf16>(x, y, B, C, HW, st) : transpose_launch<bf16, bf16>(x, y, B, C, HW, st);
+  return MTUS_ERR_UNSUPPORTED;
+}
+
+// ---- PatchEmbed im2col: x [B,3,H,W] -> cols [B*(H/4)*(W/4), 64], k = c*16 + ky*4 + kx, k >= 48 zero ----
+template <typename TI, typename TO>
+__global__ void patch_im2col_kernel(const TI* __restrict__ x, TO* __restrict__ cols, int B, int H, int W) {
+  const int Ho = H / 4, Wo = W / 4;
+  const int64_t total = (int64_t)B * Ho * Wo * 8;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int k8 = (int)(i & 7);
+    const int64_t m = i >> 3;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (k8 < 6) {
+      const int ox = (int)(m % Wo); const int64_t t = m / Wo; const int oy = (int)(t % Ho); const int64_t b = t / Ho;
+      const int c = k8 >> 1, ky0 = (k8 & 1) * 2;
+      const TI* p = x + ((b * 3 + c) * H + (oy * 4 + ky0)) * (int64_t)W + ox * 4;
+      float a[4], q[4];
+      IO<TI>::load4(p, a);
+      IO<TI>::load4(p + W, q);
+      v[0] = a[0]; v[1] = a[1]; v[2] = a[2]; v[3] = a[3]; v[4] = q[0]; v[5] = q[1]; v[6] = q[2]; v[7] = q[3];
+    }
+    IO<TO>::store8(cols + i * 8, v);
+  }
+}
+
+extern "C" int mtus_patch_embed_im2col(const void* x, void* cols, int B, int H, int W, int x_is_f32, int dtype,
+                                       void* stream) {
+  MTUS_CHECK_ARG(x && cols && B >= 0 && H % 4 == 0 && W % 4 == 0);
+  if (B == 0) return MTUS_OK;
+  const int64_t total = (int64_t)B * (H / 4) * (W / 4) * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = grid_for(total, 256);
+  if (dtype == MTUS_F32) patch_im2col_kernel<float, float><<<g, 256, 0, st>>>((const float*)x, (float*)cols, B, H, W);
+  else if (dtype == MTUS_BF16) {
+    if (x_is_f32) patch_im2col_kernel<float, bf16><<<g, 256, 0, st>>>((const float*)x, (bf16*)cols, B, H, W);
+    else patch_im2col_kernel<bf16, bf16><<<g, 256, 0, st>>>((const bf16*)x, (bf16*)cols, B, H, W);
+  } else return MTUS_ERR_UNSUPPORTED;
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}

@@ -1,0 +1,377 @@
+// Whole-encoder executor: one C-ABI call runs the Swin Transformer forward (or a range of stages of
+// the backward) as a fixed schedule of the kernels in this library on the caller's stream.
+//
+// This is the native runtime that replaces the Python module tree of timm's SwinTransformer /
+// FeatureListNet (patch_embed -> layers_0..3 -> 4 NHWC features) and the reference wrapper's
+// NHWC->NCHW permute (/root/reference/code/models/encoders.py:103-106).  No Python, no allocation
+// and no synchronisation happen between kernels, so the whole step is CUDA-graph capturable.
+//
+// Memory: parameters live in ONE flat fp32 buffer (timm state-dict order, each tensor 8-element
+// aligned) with a bf16 shadow for the GEMM operands; gradients mirror that layout, so every stage's
+// gradient is one contiguous slice that can be all-reduced while earlier stages still run backward.
+// Activations saved for backward live in one caller-provided workspace laid out by plan().
+#include "common.cuh"
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct PInfo { std::string name; int64_t off; int rank; int64_t shape[4]; int64_t numel; };
+
+struct BlockP { int64_t n1w, n1b, table, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b, fc2w, fc2b; };
+struct StageP { int64_t mg_nw, mg_nb, mg_red; std::vector<BlockP> blk; int64_t begin, end; };
+struct BlockA { size_t mean1, rstd1, ln1, qkv, attn, xmid, mean2, rstd2, ln2, h, a, xout; };
+struct StageA { size_t mg_ln, mg_mean, mg_rstd, xin; std::vector<BlockA> blk; };
+
+struct Plan {
+  int B, S, C0, window, dtype, backend, training;
+  float eps;
+  int depths[4], heads[4];
+  int C[4], res[4], win[4], shift[4];
+  int64_t M[4];
+  size_t es;  // activation element size
+  // params
+  int64_t pe_w, pe_b, pe_nw, pe_nb;
+  StageP sp[4];
+  int64_t n_params;
+  std::vector<PInfo> pinfo;
+  // activations
+  size_t cols, pe_pre, pe_mean, pe_rstd, x0;
+  StageA sa[4];
+  size_t G, dLN, dQKV, dH, tmpS;
+  size_t ws_bytes;
+};
+
+struct Arena {
+  size_t off = 0;
+  size_t take(size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; }
+};
+
+int64_t add_param(Plan& p, const std::string& name, std::initializer_list<int64_t> shape) {
+  PInfo pi; pi.name = name; pi.rank = (int)shape.size(); pi.numel = 1;
+  int i = 0;
+  for (int64_t s : shape) { pi.shape[i++] = s; pi.numel *= s; }
+  pi.off = p.n_params;
+  p.n_params += (pi.numel + 7) & ~(int64_t)7;
+  p.pinfo.push_back(pi);
+  return pi.off;
+}
+
+bool build_plan(const mtus_swin_config* c, Plan& p) {
+  if (!c || c->batch < 0 || c->img_size <= 0 || c->img_size % 4 || c->embed_dim <= 0 || c->embed_dim % 32) return false;
+  if (c->dtype != MTUS_F32 && c->dtype != MTUS_BF16) return false;
+  if (c->window <= 0 || c->window > 16) return false;
+  p.B = c->batch; p.S = c->img_size; p.C0 = c->embed_dim; p.window = c->window; p.dtype = c->dtype;
+  p.backend = c->backend; p.training = c->training; p.eps = c->ln_eps > 0 ? c->ln_eps : 1e-5f;
+  p.es = (c->dtype == MTUS_BF16) ? 2 : 4;
+  int r = c->img_size / 4;
+  for (int i = 0; i < 4; ++i) {
+    if (c->depths[i] <= 0 || c->heads[i] <= 0) return false;
+    p.depths[i] = c->depths[i]; p.heads[i] = c->heads[i];
+    p.C[i] = c->embed_dim << i;
+    if (p.C[i] != p.heads[i] * 32) return false;       // head_dim 32 (every Swin variant)
+    if (i > 0) r = (r + 1) / 2;
+    p.res[i] = r;
+    p.win[i] = r <= c->window ? r : c->window;          // timm _calc_window_shift
+    p.shift[i] = r <= p.win[i] ? 0 : c->window / 2;
+    p.M[i] = (int64_t)p.B * r * r;
+  }
+  // ---- parameters (timm FeatureListNet state-dict order) ----
+  p.n_params = 0; p.pinfo.clear();
+  p.pe_w = add_param(p, "patch_embed.proj.weight", {p.C0, 3, 4, 4});
+  p.pe_b = add_param(p, "patch_embed.proj.bias", {p.C0});
+  p.pe_nw = add_param(p, "patch_embed.norm.weight", {p.C0});
+  p.pe_nb = add_param(p, "patch_embed.norm.bias", {p.C0});
+  for (int i = 0; i < 4; ++i) {
+    StageP& s = p.sp[i];
+    s.begin = p.n_params;
+    const std::string L = "layers_" + std::to_string(i) + ".";
+    if (i > 0) {
+      s.mg_nw = add_param(p, L + "downsample.norm.weight", {4 * p.C[i - 1]});
+      s.mg_nb = add_param(p, L + "downsample.norm.bias", {4 * p.C[i - 1]});
+      s.mg_red = add_param(p, L + "downsample.reduction.weight", {p.C[i], 4 * p.C[i - 1]});
+    }
+    s.blk.resize(p.depths[i]);
+    const int64_t Cc = p.C[i], ntab = (int64_t)(2 * p.win[i] - 1) * (2 * p.win[i] - 1);
+    for (int j = 0; j < p.depths[i]; ++j) {
+      BlockP& b = s.blk[j];
+      const std::string Bn = L + "blocks." + std::to_string(j) + ".";
+      b.n1w = add_param(p, Bn + "norm1.weight", {Cc});
+      b.n1b = add_param(p, Bn + "norm1.bias", {Cc});
+      b.table = add_param(p, Bn + "attn.relative_position_bias_table", {ntab, p.heads[i]});
+      b.qkvw = add_param(p, Bn + "attn.qkv.weight", {3 * Cc, Cc});
+      b.qkvb = add_param(p, Bn + "attn.qkv.bias", {3 * Cc});
+      b.projw = add_param(p, Bn + "attn.proj.weight", {Cc, Cc});
+      b.projb = add_param(p, Bn + "attn.proj.bias", {Cc});
+      b.n2w = add_param(p, Bn + "norm2.weight", {Cc});
+      b.n2b = add_param(p, Bn + "norm2.bias", {Cc});
+      b.fc1w = add_param(p, Bn + "mlp.fc1.weight", {4 * Cc, Cc});
+      b.fc1b = add_param(p, Bn + "mlp.fc1.bias", {4 * Cc});
+      b.fc2w = add_param(p, Bn + "mlp.fc2.weight", {Cc, 4 * Cc});
+      b.fc2b = add_param(p, Bn + "mlp.fc2.bias", {Cc});
+    }
+    s.end = p.n_params;
+  }
+  // ---- activations ----
+  Arena a;
+  const size_t es = p.es;
+  p.cols = a.take((size_t)p.M[0] * 64 * es);
+  p.pe_pre = a.take((size_t)p.M[0] * p.C0 * es);
+  p.pe_mean = a.take((size_t)p.M[0] * 4);
+  p.pe_rstd = a.take((size_t)p.M[0] * 4);
+  p.x0 = a.take((size_t)p.M[0] * p.C0 * es);
+  for (int i = 0; i < 4; ++i) {
+    StageA& s = p.sa[i];
+    const size_t MC = (size_t)p.M[i] * p.C[i] * es;
+    size_t xin = p.x0;
+    if (i > 0) {
+      s.mg_ln = a.take(MC * 2);                          // [M_i, 4 C_{i-1}] = [M_i, 2 C_i]
+      s.mg_mean = a.take((size_t)p.M[i] * 4);
+      s.mg_rstd = a.take((size_t)p.M[i] * 4);
+      xin = a.take(MC);
+    }
+    s.xin = xin;
+    s.blk.resize(p.depths[i]);
+    // inference: per-stage buffers are recycled (three rotating residual-stream buffers)
+    size_t sh_mean1 = 0, sh_rstd1 = 0, sh_ln1 = 0, sh_qkv = 0, sh_attn = 0, sh_mean2 = 0, sh_rstd2 = 0, sh_ln2 = 0, sh_h = 0, sh_a = 0, rot[3] = {0, 0, 0};
+    if (!p.training) {
+      sh_mean1 = a.take((size_t)p.M[i] * 4); sh_rstd1 = a.take((size_t)p.M[i] * 4); sh_ln1 = a.take(MC); sh_qkv = a.take(3 * MC);
+      sh_attn = a.take(MC); sh_mean2 = a.take((size_t)p.M[i] * 4); sh_rstd2 = a.take((size_t)p.M[i] * 4); sh_ln2 = a.take(MC);
+      sh_h = a.take(4 * MC); sh_a = sh_h;               // GELU output overwrites its input in inference
+      rot[0] = xin; rot[1] = a.take(MC); rot[2] = a.take(MC);
+    }
+    for (int j = 0; j < p.depths[i]; ++j) {
+      BlockA& b = s.blk[j];
+      if (p.training) {
+        b.mean1 = a.take((size_t)p.M[i] * 4); b.rstd1 = a.take((size_t)p.M[i] * 4); b.ln1 = a.take(MC); b.qkv = a.take(3 * MC);
+        b.attn = a.take(MC); b.xmid = a.take(MC); b.mean2 = a.take((size_t)p.M[i] * 4); b.rstd2 = a.take((size_t)p.M[i] * 4);
+        b.ln2 = a.take(MC); b.h = a.take(4 * MC); b.a = a.take(4 * MC); b.xout = a.take(MC);
+      } else {
+        b.mean1 = sh_mean1; b.rstd1 = sh_rstd1; b.ln1 = sh_ln1; b.qkv = sh_qkv; b.attn = sh_attn; b.mean2 = sh_mean2; b.rstd2 = sh_rstd2;
+        b.ln2 = sh_ln2; b.h = sh_h; b.a = sh_a;
+        b.xmid = rot[(2 * j + 1) % 3]; b.xout = rot[(2 * j + 2) % 3];   // x_in of block j is rot[(2j) % 3]
+      }
+    }
+  }
+  if (p.training) {
+    const size_t MC0 = (size_t)p.M[0] * p.C0 * es;      // M_i*C_i is largest at stage 0
+    p.G = a.take(MC0); p.dLN = a.take(MC0); p.tmpS = a.take(MC0); p.dQKV = a.take(3 * MC0); p.dH = a.take(4 * MC0);
+  } else p.G = p.dLN = p.tmpS = p.dQKV = p.dH = 0;
+  p.ws_bytes = a.off;
+  return true;
+}
+
+size_t block_xin(const Plan& p, int i, int j) {
+  if (j == 0) return p.sa[i].xin;
+  return p.sa[i].blk[j - 1].xout;
+}
+
+#define RUN(expr) do { int rc__ = (expr); if (rc__ != MTUS_OK) { fprintf(stderr, "mtus swin_exec: %s -> %d (%s) at %s:%d\n", #expr, rc__, mtus_status_string(rc__), __FILE__, __LINE__); return rc__; } } while (0)
+
+}  // namespace
+
+extern "C" int64_t mtus_swin_param_count(const mtus_swin_config* cfg) {
+  Plan p;
+  if (!build_plan(cfg, p)) return -1;
+  return p.n_params;
+}
+
+extern "C" int64_t mtus_swin_workspace_bytes(const mtus_swin_config* cfg) {
+  Plan p;
+  if (!build_plan(cfg, p)) return -1;
+  return (int64_t)p.ws_bytes;
+}
+
+extern "C" int64_t mtus_swin_feature_offset(const mtus_swin_config* cfg, int stage) {
+  Plan p;
+  if (!build_plan(cfg, p) || stage < 0 || stage > 3) return -1;
+  return (int64_t)p.sa[stage].blk.back().xout;
+}
+
+extern "C" int mtus_swin_param_info(const mtus_swin_config* cfg, int idx, char* name, int64_t* offset, int* rank,
+                                    int64_t* shape) {
+  Plan p;
+  if (!build_plan(cfg, p) || idx < 0 || idx >= (int)p.pinfo.size()) return -1;
+  const PInfo& pi = p.pinfo[idx];
+  if (name) { strncpy(name, pi.name.c_str(), 127); name[127] = 0; }
+  if (offset) *offset = pi.off;
+  if (rank) *rank = pi.rank;
+  if (shape) for (int i = 0; i < pi.rank; ++i) shape[i] = pi.shape[i];
+  return 0;
+}
+
+extern "C" int64_t mtus_swin_param_offset(const mtus_swin_config* cfg, const char* name, int64_t* numel) {
+  Plan p;
+  if (!build_plan(cfg, p) || !name) return -1;
+  for (const PInfo& pi : p.pinfo)
+    if (pi.name == name) { if (numel) *numel = pi.numel; return pi.off; }
+  return -1;
+}
+
+extern "C" int mtus_swin_forward(const mtus_swin_config* cfg, const void* x, int x_is_f32, const float* params,
+                                 const void* params_lp, const float* droppath, void* workspace, void* const* feats,
+                                 int feats_layout, int feats_f32, void* stream) {
+  Plan p;
+  if (!build_plan(cfg, p)) return MTUS_ERR_BAD_ARG;
+  MTUS_CHECK_ARG(x && params && workspace && feats);
+  MTUS_CHECK_ARG(p.dtype == MTUS_F32 || params_lp);
+  if (p.B == 0) return MTUS_OK;
+  char* ws = reinterpret_cast<char*>(workspace);
+  const int dt = p.dtype, be = p.backend;
+  // GEMM weights: bf16 shadow in bf16 mode, the fp32 master otherwise
+  auto W = [&](int64_t off) -> const void* {
+    return dt == MTUS_BF16 ? (const void*)(reinterpret_cast<const bf16*>(params_lp) + off) : (const void*)(params + off);
+  };
+  auto F = [&](int64_t off) { return params + off; };
+  auto A = [&](size_t off) -> void* { return ws + off; };
+  auto FA = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+
+  // ---- patch embed: im2col -> GEMM(K=48, +bias) -> LayerNorm ----
+  const int r0 = p.res[0];
+  RUN(mtus_patch_embed_im2col(x, A(p.cols), p.B, p.S, p.S, x_is_f32 || dt == MTUS_F32, dt, stream));
+  {
+    mtus_gemm_desc d; memset(&d, 0, sizeof(d));
+    d.a = A(p.cols); d.lda = 64; d.b = W(p.pe_w); d.ldb = 48;
+    d.M = (int)p.M[0]; d.N = p.C0; d.K = 48; d.bias = F(p.pe_b);
+    d.out = A(p.pe_pre); d.ld_out = p.C0; d.dtype = dt; d.backend = be;
+    RUN(mtus_gemm(&d, stream));
+  }
+  RUN(mtus_layernorm_fwd(A(p.pe_pre), F(p.pe_nw), F(p.pe_nb), A(p.x0), FA(p.pe_mean), FA(p.pe_rstd), p.M[0], p.C0, p.eps, dt, stream));
+  (void)r0;
+
+  int gblk = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int Cc = p.C[i], res = p.res[i];
+    const int64_t M = p.M[i];
+    const int rps = res * res;
+    if (i > 0) {
+      const StageA& s = p.sa[i];
+      const size_t prev_out = p.sa[i - 1].blk.back().xout;
+      RUN(mtus_patch_merge_ln_fwd(A(prev_out), F(p.sp[i].mg_nw), F(p.sp[i].mg_nb), A(s.mg_ln), FA(s.mg_mean), FA(s.mg_rstd), p.B,
+                                  p.res[i - 1], p.res[i - 1], p.C[i - 1], p.eps, dt, stream));
+      RUN(mtus_linear_fwd(A(s.mg_ln), W(p.sp[i].mg_red), nullptr, A(p.sa[i].xin), nullptr, nullptr, nullptr, 1, M, Cc,
+                          4 * p.C[i - 1], dt, be, stream));
+    }
+    for (int j = 0; j < p.depths[i]; ++j, ++gblk) {
+      const BlockP& bp = p.sp[i].blk[j];
+      const BlockA& ba = p.sa[i].blk[j];
+      const size_t xin = block_xin(p, i, j);
+      const int shift = (j % 2) ? p.shift[i] : 0;
+      const float* dp1 = droppath ? droppath + (size_t)(2 * gblk) * p.B : nullptr;
+      const float* dp2 = droppath ? droppath + (size_t)(2 * gblk + 1) * p.B : nullptr;
+      RUN(mtus_layernorm_fwd(A(xin), F(bp.n1w), F(bp.n1b), A(ba.ln1), FA(ba.mean1), FA(ba.rstd1), M, Cc, p.eps, dt, stream));
+      RUN(mtus_linear_fwd(A(ba.ln1), W(bp.qkvw), F(bp.qkvb), A(ba.qkv), nullptr, nullptr, nullptr, 1, M, 3 * Cc, Cc, dt, be, stream));
+      RUN(mtus_window_attn_fwd(A(ba.qkv), F(bp.table), F(bp.qkvb), A(ba.attn), p.B, res, res, Cc, p.heads[i], p.win[i], p.win[i],
+                               shift, shift, dt, stream));
+      RUN(mtus_linear_fwd(A(ba.attn), W(bp.projw), F(bp.projb), A(ba.xmid), nullptr, A(xin), dp1, rps, M, Cc, Cc, dt, be, stream));
+      RUN(mtus_layernorm_fwd(A(ba.xmid), F(bp.n2w), F(bp.n2b), A(ba.ln2), FA(ba.mean2), FA(ba.rstd2), M, Cc, p.eps, dt, stream));
+      // fc1 + GELU: pre-activation -> h (saved for backward), activation -> a
+      RUN(mtus_linear_fwd(A(ba.ln2), W(bp.fc1w), F(bp.fc1b), A(ba.a), A(ba.h), nullptr, nullptr, 1, M, 4 * Cc, Cc, dt, be, stream));
+      RUN(mtus_linear_fwd(A(ba.a), W(bp.fc2w), F(bp.fc2b), A(ba.xout), nullptr, A(ba.xmid), dp2, rps, M, Cc, 4 * Cc, dt, be, stream));
+    }
+    if (feats[i]) {
+      if (feats_layout == 0) RUN(mtus_nhwc_to_nchw(A(p.sa[i].blk.back().xout), feats[i], p.B, res * res, Cc, dt, feats_f32, stream));
+      else {
+        MTUS_CHECK_ARG(!(feats_f32 && dt != MTUS_F32));
+        cudaError_t e = cudaMemcpyAsync(feats[i], A(p.sa[i].blk.back().xout), (size_t)M * Cc * p.es, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+        if (e != cudaSuccess) return (int)e;
+      }
+    }
+  }
+  return MTUS_OK;
+}
+
+extern "C" int mtus_swin_backward(const mtus_swin_config* cfg, const float* params, const void* params_lp,
+                                  const float* droppath, void* workspace, const void* const* dfeats, int dfeats_layout,
+                                  int dfeats_f32, float* grads, int stage_hi, int stage_lo, void* stream) {
+  Plan p;
+  if (!build_plan(cfg, p)) return MTUS_ERR_BAD_ARG;
+  MTUS_CHECK_ARG(params && workspace && dfeats && grads && p.training);
+  MTUS_CHECK_ARG(p.dtype == MTUS_F32 || params_lp);
+  MTUS_CHECK_ARG(stage_hi <= 4 && stage_lo >= 0 && stage_lo < stage_hi);
+  if (p.B == 0) return MTUS_OK;
+  char* ws = reinterpret_cast<char*>(workspace);
+  const int dt = p.dtype, be = p.backend;
+  cudaStream_t st = (cudaStream_t)stream;
+  auto W = [&](int64_t off) -> const void* {
+    return dt == MTUS_BF16 ? (const void*)(reinterpret_cast<const bf16*>(params_lp) + off) : (const void*)(params + off);
+  };
+  auto F = [&](int64_t off) { return params + off; };
+  auto GR = [&](int64_t off) { return grads + off; };
+  auto A = [&](size_t off) -> void* { return ws + off; };
+  auto FA = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  void* G = A(p.G); void* dLN = A(p.dLN); void* tmpS = A(p.tmpS); void* dQKV = A(p.dQKV); void* dH = A(p.dH);
+
+  int gblk_end = 0;
+  for (int i = 0; i < stage_hi; ++i) gblk_end += p.depths[i];
+
+  for (int i = stage_hi - 1; i >= stage_lo; --i) {
+    const int Cc = p.C[i], res = p.res[i];
+    const int64_t M = p.M[i];
+    const int rps = res * res;
+    if (i == 3) {  // top of the chain: G = NHWC(dfeat3) or zero
+      if (dfeats[3] && dfeats_layout == 0) RUN(mtus_nchw_to_nhwc(dfeats[3], G, p.B, res * res, Cc, dt, dfeats_f32, stream));
+      else if (dfeats[3]) {
+        MTUS_CHECK_ARG(!(dfeats_f32 && dt != MTUS_F32));
+        cudaError_t e = cudaMemcpyAsync(G, dfeats[3], (size_t)M * Cc * p.es, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return (int)e;
+      } else { cudaError_t e = cudaMemsetAsync(G, 0, (size_t)M * Cc * p.es, st); if (e != cudaSuccess) return (int)e; }
+    }
+    int gblk = gblk_end - 1;
+    for (int j = p.depths[i] - 1; j >= 0; --j, --gblk) {
+      const BlockP& bp = p.sp[i].blk[j];
+      const BlockA& ba = p.sa[i].blk[j];
+      const size_t xin = block_xin(p, i, j);
+      const int shift = (j % 2) ? p.shift[i] : 0;
+      const float* dp1 = droppath ? droppath + (size_t)(2 * gblk) * p.B : nullptr;
+      const float* dp2 = droppath ? droppath + (size_t)(2 * gblk + 1) * p.B : nullptr;
+      // ---- MLP branch ----
+      const void* dy2 = G;
+      if (dp2) { RUN(mtus_scale_rows(G, tmpS, dp2, rps, M, Cc, dt, stream)); dy2 = tmpS; }
+      RUN(mtus_linear_wgrad(dy2, A(ba.a), GR(bp.fc2w), GR(bp.fc2b), M, Cc, 4 * Cc, dt, be, stream));
+      RUN(mtus_linear_dgrad(dy2, W(bp.fc2w), dH, A(ba.h), nullptr, 1, M, Cc, 4 * Cc, dt, be, stream));
+      RUN(mtus_linear_wgrad(dH, A(ba.ln2), GR(bp.fc1w), GR(bp.fc1b), M, 4 * Cc, Cc, dt, be, stream));
+      RUN(mtus_linear_dgrad(dH, W(bp.fc1w), dLN, nullptr, nullptr, 1, M, 4 * Cc, Cc, dt, be, stream));
+      RUN(mtus_layernorm_bwd(dLN, A(ba.xmid), F(bp.n2w), FA(ba.mean2), FA(ba.rstd2), G, G, GR(bp.n2w), GR(bp.n2b), M, Cc, dt, stream));
+      // ---- attention branch ----
+      const void* dy1 = G;
+      if (dp1) { RUN(mtus_scale_rows(G, tmpS, dp1, rps, M, Cc, dt, stream)); dy1 = tmpS; }
+      RUN(mtus_linear_wgrad(dy1, A(ba.attn), GR(bp.projw), GR(bp.projb), M, Cc, Cc, dt, be, stream));
+      RUN(mtus_linear_dgrad(dy1, W(bp.projw), dLN, nullptr, nullptr, 1, M, Cc, Cc, dt, be, stream));
+      RUN(mtus_window_attn_bwd(dLN, A(ba.qkv), A(ba.attn), F(bp.table), F(bp.qkvb), dQKV, GR(bp.table), GR(bp.qkvb), p.B, res, res, Cc,
+                               p.heads[i], p.win[i], p.win[i], shift, shift, dt, stream));
+      RUN(mtus_linear_wgrad(dQKV, A(ba.ln1), GR(bp.qkvw), GR(bp.qkvb), M, 3 * Cc, Cc, dt, be, stream));
+      RUN(mtus_linear_dgrad(dQKV, W(bp.qkvw), dLN, nullptr, nullptr, 1, M, 3 * Cc, Cc, dt, be, stream));
+      RUN(mtus_layernorm_bwd(dLN, A(xin), F(bp.n1w), FA(ba.mean1), FA(ba.rstd1), G, G, GR(bp.n1w), GR(bp.n1b), M, Cc, dt, stream));
+    }
+    gblk_end -= p.depths[i];
+    if (i > 0) {
+      // ---- patch merging backward: reduction wgrad/dgrad, then LN backward scattered to [B,H,W,C_{i-1}] ----
+      const StageA& s = p.sa[i];
+      const int Cp = p.C[i - 1], rp = p.res[i - 1];
+      RUN(mtus_linear_wgrad(G, A(s.mg_ln), GR(p.sp[i].mg_red), nullptr, M, Cc, 4 * Cp, dt, be, stream));
+      RUN(mtus_linear_dgrad(G, W(p.sp[i].mg_red), dH, nullptr, nullptr, 1, M, Cc, 4 * Cp, dt, be, stream));
+      const void* dres = nullptr;
+      if (dfeats[i - 1] && dfeats_layout == 0) { RUN(mtus_nchw_to_nhwc(dfeats[i - 1], tmpS, p.B, rp * rp, Cp, dt, dfeats_f32, stream)); dres = tmpS; }
+      else if (dfeats[i - 1]) { MTUS_CHECK_ARG(!(dfeats_f32 && dt != MTUS_F32)); dres = dfeats[i - 1]; }
+      RUN(mtus_patch_merge_ln_bwd(dH, A(p.sa[i - 1].blk.back().xout), F(p.sp[i].mg_nw), FA(s.mg_mean), FA(s.mg_rstd), dres, G,
+                                  GR(p.sp[i].mg_nw), GR(p.sp[i].mg_nb), p.B, rp, rp, Cp, dt, stream));
+    } else {
+      // ---- patch embed backward: LN, then conv weight/bias gradients (no gradient w.r.t. the image) ----
+      RUN(mtus_layernorm_bwd(G, A(p.pe_pre), F(p.pe_nw), FA(p.pe_mean), FA(p.pe_rstd), nullptr, dLN, GR(p.pe_nw), GR(p.pe_nb), p.M[0],
+                             p.C0, dt, stream));
+      mtus_gemm_desc d; memset(&d, 0, sizeof(d));
+      d.a = dLN; d.lda = p.C0; d.a_mn_major = 1;
+      d.b = A(p.cols); d.ldb = 64; d.b_mn_major = 1;
+      d.M = p.C0; d.N = 48; d.K = (int)p.M[0];
+      d.out = GR(p.pe_w); d.ld_out = 48; d.out_f32 = 1; d.atomic = 1;
+      d.split_k = 148;
+      d.dtype = dt; d.backend = be;
+      RUN(mtus_gemm(&d, stream));
+      RUN(mtus_colsum(dLN, GR(p.pe_b), p.M[0], p.C0, dt, stream));
+    }
+  }
+  return MTUS_OK;
+}

@@ -1,0 +1,291 @@
+"""Swin encoder factory: drop-in for ``/root/reference/code/models/encoders.py`` (swin branch).
+
+``build_encoder(config, task_ids)`` (encoders.py:665-691), ``SwinTransformerEncoder``
+(encoders.py:37-160) and ``SWIN_MODEL_MAPPING`` (encoders.py:14-19) keep their names, arguments,
+attributes (``is_timm_encoder``, ``out_channels``, ``output_stride``, ``supports_task_id``,
+``handles_moe``, ``use_moe``, ``get_moe_aux_loss``, ``get_moe_stats``) and the ``encoder.model.*``
+state-dict keys of timm's FeatureListNet, but the arithmetic runs in the sm_100a kernels of
+``libmtus_b200.so`` through ONE C-ABI call per direction (``mtus_swin_forward/backward``).
+There is no PyTorch / CPU fallback: on a box without the library or without CUDA the forward raises.
+"""
+
+import ctypes as C
+import math
+import os
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._native import FlatParamModule, enumerate_params, precision_to_dtype, is_channels_last_view
+
+# code/models/encoders.py:14-19
+SWIN_MODEL_MAPPING = {
+    "swin_t": "swin_tiny_patch4_window7_224",
+    "swin_s": "swin_small_patch4_window7_224",
+    "swin_b": "swin_base_patch4_window7_224",
+    "swin_l": "swin_large_patch4_window7_224",
+}
+
+# timm model registry entries reachable through the reference (name -> embed_dim, depths, heads, window)
+SWIN_ARCHS = {
+    "swin_tiny_patch4_window7_224": (96, (2, 2, 6, 2), (3, 6, 12, 24), 7),
+    "swin_small_patch4_window7_224": (96, (2, 2, 18, 2), (3, 6, 12, 24), 7),
+    "swin_base_patch4_window7_224": (128, (2, 2, 18, 2), (4, 8, 16, 32), 7),
+    "swin_large_patch4_window7_224": (192, (2, 2, 18, 2), (6, 12, 24, 48), 7),
+    "swin_base_patch4_window12_384": (128, (2, 2, 18, 2), (4, 8, 16, 32), 12),
+    "swin_large_patch4_window12_384": (192, (2, 2, 18, 2), (6, 12, 24, 48), 12),
+    "swin_micro_patch4_window7_test": (32, (2, 2, 2, 2), (1, 2, 4, 8), 7),  # test-only (see oracle/swin.py)
+}
+
+# hook used by parallel.GradAllReducer: called as fn(flat_grad, lo, hi) after each backward stage chunk
+_STAGE_GRAD_HOOK = None
+
+
+def default_precision() -> str:
+    return os.environ.get("MTUS_PRECISION", "bf16")
+
+
+class _FeatureInfo:
+    def __init__(self, chans, reds):
+        self._c, self._r = list(chans), list(reds)
+
+    def channels(self):
+        return list(self._c)
+
+    def reduction(self):
+        return list(self._r)
+
+
+class _SwinFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, core, x, *params):
+        needs_grad = any(ctx.needs_input_grad[2:])
+        feats, saved = core._run_forward(x, training_plan=needs_grad)
+        ctx.core = core
+        ctx.saved = saved
+        ctx.param_needs = ctx.needs_input_grad[2:]
+        return tuple(feats)
+
+    @staticmethod
+    def backward(ctx, *dfeats):
+        core = ctx.core
+        flat_grad = core._run_backward(ctx.saved, dfeats)
+        ctx.saved = None
+        return (None, None) + tuple(core.grad_views(flat_grad, ctx.param_needs))
+
+
+class SwinCore(FlatParamModule):
+    """Stands where timm's ``FeatureListNet(SwinTransformer)`` stands (``encoder.model``)."""
+
+    def __init__(self, name: str, img_size: int = 224, drop_path_rate: float = 0.1, precision: Optional[str] = None,
+                 output_dtype: Optional[str] = None, zero_copy_features: bool = False):
+        super().__init__()
+        if name not in SWIN_ARCHS:
+            raise RuntimeError(f"Unknown model ({name})")
+        self.arch_name = name
+        self.embed_dim, self.depths, self.num_heads, self.window = SWIN_ARCHS[name]
+        self.img_size = int(img_size)
+        if self.img_size % 4:
+            raise ValueError("image size must be a multiple of the patch size 4")
+        self.precision = precision or default_precision()
+        self.output_dtype = output_dtype          # None -> activation dtype; 'fp32' -> fp32 NCHW features
+        self.zero_copy_features = zero_copy_features
+        self.drop_path_rate = float(drop_path_rate)
+        self.backend = _lib.BACKEND_AUTO
+        nblk = sum(self.depths)
+        self._dpr = torch.linspace(0, self.drop_path_rate, nblk).tolist()   # timm: linspace(0, rate, sum(depths))
+        chans = [self.embed_dim * 2 ** i for i in range(4)]
+        self.feature_info = _FeatureInfo(chans, [4, 8, 16, 32])
+        res, r = [], self.img_size // 4
+        for i in range(4):
+            if i > 0:
+                r = (r + 1) // 2
+            res.append(r)
+        self.resolutions = res
+        cfg = self._cfg(1, True)
+        L = _lib.lib()
+        total = L.mtus_swin_param_count(C.byref(cfg))
+        if total <= 0:
+            raise RuntimeError("mtus_b200: invalid Swin configuration")
+        self._init_flat(enumerate_params(L.mtus_swin_param_info, cfg), total)
+        self._stage_slices = self._compute_stage_slices()
+        self.reset_parameters()
+
+    # -- configuration ---------------------------------------------------------------------------
+    def _cfg(self, batch: int, training: bool) -> _lib.SwinConfig:
+        dt, _ = precision_to_dtype(self.precision)
+        c = _lib.SwinConfig()
+        c.batch, c.img_size, c.embed_dim, c.window = batch, self.img_size, self.embed_dim, self.window
+        for i in range(4):
+            c.depths[i], c.heads[i] = self.depths[i], self.num_heads[i]
+        c.dtype, c.backend, c.training, c.ln_eps = dt, self.backend, int(training), 1e-5
+        return c
+
+    def _compute_stage_slices(self):
+        """[lo, hi) element ranges of the flat buffer: patch_embed, layers_0 .. layers_3."""
+        bounds = {}
+        for name, (p, off, numel, shape) in self._params_by_name.items():
+            key = name.split(".")[0]
+            lo, hi = bounds.get(key, (off, off))
+            bounds[key] = (min(lo, off), max(hi, off + ((numel + 7) // 8) * 8))
+        return [bounds["patch_embed"]] + [bounds[f"layers_{i}"] for i in range(4)]
+
+    def reset_parameters(self):
+        """timm init: trunc_normal(.02) Linear weights + rel-pos tables, zero biases, LN (1, 0); conv default."""
+        with torch.no_grad():
+            for name, (p, off, numel, shape) in self._params_by_name.items():
+                if name == "patch_embed.proj.weight":
+                    nn.init.kaiming_uniform_(p, a=math.sqrt(5))
+                elif name == "patch_embed.proj.bias":
+                    bound = 1.0 / math.sqrt(48)
+                    nn.init.uniform_(p, -bound, bound)
+                elif "norm" in name.split(".")[-2]:
+                    (nn.init.ones_ if name.endswith("weight") else nn.init.zeros_)(p)
+                elif name.endswith("relative_position_bias_table") or name.endswith(".weight"):
+                    nn.init.trunc_normal_(p, std=0.02)
+                else:
+                    nn.init.zeros_(p)
+
+    # -- execution -------------------------------------------------------------------------------
+    def _droppath_scales(self, batch: int, device):
+        if not self.training or self.drop_path_rate <= 0.0:
+            return None
+        keep = 1.0 - torch.tensor(self._dpr, device=device, dtype=torch.float32).repeat_interleave(2)  # [2*nblk]
+        mask = torch.rand(keep.numel(), batch, device=device) < keep[:, None]
+        return (mask.float() / keep[:, None]).contiguous()
+
+    def _run_forward(self, x: torch.Tensor, training_plan: bool):
+        if not x.is_cuda:
+            raise RuntimeError("mtus_b200: the Swin encoder runs only on CUDA (sm_100a); there is no CPU fallback")
+        B, Cin, H, W = x.shape
+        if Cin != 3:
+            raise ValueError("expected a 3-channel image")
+        # timm strict image size (encoders.py:58 threads img_size through for this reason)
+        assert H == self.img_size, f"Input height ({H}) doesn't match model ({self.img_size})."
+        assert W == self.img_size, f"Input width ({W}) doesn't match model ({self.img_size})."
+        L = _lib.lib()
+        dt, tdt = precision_to_dtype(self.precision)
+        flat = self.flat_params()
+        if flat.device != x.device:
+            raise RuntimeError("mtus_b200: encoder parameters and input live on different devices")
+        x_is_f32 = x.dtype == torch.float32
+        if not x_is_f32 and x.dtype != tdt:
+            x = x.to(tdt)
+        x = x.contiguous()
+        cfg = self._cfg(B, training_plan)
+        ws = torch.empty(L.mtus_swin_workspace_bytes(C.byref(cfg)), dtype=torch.uint8, device=x.device)
+        lp = None
+        if dt == _lib.BF16:
+            lp = torch.empty(self._n_flat, dtype=torch.bfloat16, device=x.device)
+            _lib.check(L.mtus_cast_f32_to_bf16(_lib.ptr(flat), _lib.ptr(lp), self._n_flat, _lib.stream_ptr()), "cast")
+        dp = self._droppath_scales(B, x.device)
+        out_f32 = self.output_dtype in ("fp32", "float32") and dt != _lib.F32
+        feats, feat_ptrs = [], [None] * 4
+        if self.zero_copy_features and not out_f32:
+            pass
+        else:
+            for i in range(4):
+                r, ch = self.resolutions[i], self.embed_dim * 2 ** i
+                feats.append(torch.empty(B, ch, r, r, dtype=torch.float32 if out_f32 else tdt, device=x.device))
+            feat_ptrs = feats
+        _lib.check(L.mtus_swin_forward(C.byref(cfg), _lib.ptr(x), int(x_is_f32), _lib.ptr(flat), _lib.ptr(lp), _lib.ptr(dp),
+                                       _lib.ptr(ws), _lib.ptr_array(feat_ptrs), 0, int(out_f32), _lib.stream_ptr()),
+                   "swin_forward")
+        if not feats:   # zero-copy: channels-last views of the stage outputs inside the workspace
+            es = 2 if dt == _lib.BF16 else 4
+            for i in range(4):
+                r, ch = self.resolutions[i], self.embed_dim * 2 ** i
+                off = L.mtus_swin_feature_offset(C.byref(cfg), i)
+                v = ws[off:off + B * r * r * ch * es].view(tdt).view(B, r, r, ch).permute(0, 3, 1, 2)
+                feats.append(v)
+        saved = (cfg, ws, lp, dp, flat, out_f32) if training_plan else None
+        return feats, saved
+
+    def _run_backward(self, saved, dfeats):
+        cfg, ws, lp, dp, flat, out_f32 = saved
+        L = _lib.lib()
+        dt, tdt = precision_to_dtype(self.precision)
+        flat_grad = torch.zeros(self._n_flat, dtype=torch.float32, device=flat.device)
+        want = torch.float32 if (out_f32 or dt == _lib.F32) else tdt
+        gs = [None if g is None else g.to(want) for g in dfeats]
+        layouts = [is_channels_last_view(g) for g in gs if g is not None]
+        nhwc = bool(layouts) and all(layouts) and not out_f32
+        gs = [None if g is None else (g if (nhwc or g.is_contiguous()) else g.contiguous()) for g in gs]
+        hook = _STAGE_GRAD_HOOK
+        chunks = [(4, 3), (3, 2), (2, 1), (1, 0)] if hook is not None else [(4, 0)]
+        for hi, lo in chunks:
+            _lib.check(L.mtus_swin_backward(C.byref(cfg), _lib.ptr(flat), _lib.ptr(lp), _lib.ptr(dp), _lib.ptr(ws),
+                                            _lib.ptr_array(gs), int(nhwc), int(want == torch.float32 and dt != _lib.F32),
+                                            _lib.ptr(flat_grad), hi, lo, _lib.stream_ptr()), "swin_backward")
+            if hook is not None:
+                s_lo, s_hi = self._stage_slices[lo + 1]
+                if lo == 0:
+                    s_lo = self._stage_slices[0][0]        # patch_embed gradients finish with stage 0
+                hook(flat_grad, s_lo, s_hi)
+        return flat_grad
+
+    def forward(self, x: torch.Tensor) -> List[torch.Tensor]:
+        """Returns the four stage outputs as [B,C,H,W] tensors (strides 4/8/16/32)."""
+        return list(_SwinFn.apply(self, x, *self.ordered_params()))
+
+
+class SwinTransformerEncoder(nn.Module):
+    """Same constructor / attributes as the reference wrapper (encoders.py:37-160)."""
+    is_timm_encoder = True
+
+    def __init__(self, model_name: str = "swin_b", pretrained: bool = True, img_size: int = 224,
+                 moe_config: Optional[dict] = None, task_ids: Optional[List[str]] = None,
+                 precision: Optional[str] = None, output_dtype: Optional[str] = None,
+                 zero_copy_features: bool = False, drop_path_rate: float = 0.1):
+        super().__init__()
+        full_model_name = SWIN_MODEL_MAPPING.get(model_name, model_name)
+        if pretrained:
+            raise RuntimeError(
+                "mtus_b200: ImageNet weights cannot be downloaded here; set model.encoder.pretrained: null and load a "
+                "checkpoint with load_state_dict (keys follow timm: encoder.model.layers_0.blocks.0...)")
+        self.model = SwinCore(full_model_name, img_size=img_size, drop_path_rate=drop_path_rate, precision=precision,
+                              output_dtype=output_dtype, zero_copy_features=zero_copy_features)
+        self._out_channels = self.model.feature_info.channels()
+        self.output_stride = 32
+        moe_cfg = moe_config or {}
+        self.use_moe = bool(moe_cfg.get("enabled", False))
+        if self.use_moe:
+            raise NotImplementedError("mtus_b200: MoE blocks are outside the hot path (SURVEY §2 row 9); disable model.moe")
+        self.moe_stage_indices = moe_cfg.get("stage_indices", None)
+        self.supports_task_id = False
+        self.handles_moe = False
+
+    def forward(self, x, task_id=None):
+        # the kernels already emit NCHW (or channels-last views): no permute().contiguous() pass (encoders.py:106)
+        return self.model(x)
+
+    def get_moe_aux_loss(self):
+        return torch.tensor(0.0, device=self.model.flat_params().device)
+
+    def get_moe_stats(self):
+        return []
+
+    @property
+    def out_channels(self):
+        return [3] + list(self._out_channels)
+
+
+def build_encoder(config, task_ids=None, precision: Optional[str] = None, output_dtype: Optional[str] = None,
+                  zero_copy_features: bool = False):
+    """Drop-in for ``build_encoder`` (encoders.py:665-691); only the ``swin_`` branch is in scope."""
+    encoder_name = config.get("model.encoder.name")
+    encoder_weights = config.get("model.encoder.pretrained")
+    img_size = config.get("data.image_size", 224)
+    if not encoder_name.startswith("swin_"):
+        raise NotImplementedError(f"mtus_b200 builds only the Swin encoders (got {encoder_name!r}); SURVEY §2 row 7")
+    pretrained = (encoder_weights == "imagenet" or encoder_weights is not None)
+    if precision is None:
+        mp = config.get("device.mixed_precision", None)
+        precision = default_precision() if mp is None else ("bf16" if mp else "fp32")
+    encoder = SwinTransformerEncoder(model_name=encoder_name, pretrained=pretrained, img_size=img_size,
+                                     moe_config=config.get("model.moe", {}), task_ids=task_ids, precision=precision,
+                                     output_dtype=output_dtype, zero_copy_features=zero_copy_features)
+    print(f"Loaded Swin Transformer: {encoder_name} (img_size={img_size}, precision={precision}, sm_100a kernels)")
+    return encoder

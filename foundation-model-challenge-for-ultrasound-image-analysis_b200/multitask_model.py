@@ -1,0 +1,113 @@
+"""``MultiTaskModel`` with the reference's constructor, ``forward(x, task_id)`` signature and routing
+(``/root/reference/code/models/multitask_model.py:13-362``), built on the native encoder / FPN.
+
+Kept: ``build_model(config)`` (:346), ``forward`` routing by task type incl. the ``ValueError`` on an
+unknown id (:187-188), ``use_fpn_for_{cls,reg}`` (:45-46), decoder aliasing (:294-303),
+``get_trainable_parameters`` (:282), ``freeze_encoder/unfreeze_encoder`` (:333-343),
+``get_moe_aux_loss/get_moe_stats`` (:310-331), attribute names (``encoder``, ``fpn_decoder_{seg,det,cls,reg}``,
+``heads``) and therefore the checkpoint keys.  Not provided (outside the hot path):
+FiLM, TaskPrompt2D, MoE -- requesting them raises.
+"""
+
+import torch
+import torch.nn as nn
+
+from .encoders import build_encoder
+from .decoders import build_decoders
+from .heads import build_all_heads
+
+
+class MultiTaskModel(nn.Module):
+    def __init__(self, config, precision=None, zero_copy_features=True):
+        super().__init__()
+        self.config = config
+        self.task_configs = config.get_task_configs()
+        for key in ("model.use_film", "model.task_prompt.enabled", "model.moe.enabled"):
+            if config.get(key, False):
+                raise NotImplementedError(f"mtus_b200: {key} is outside the hot path and not provided")
+        task_ids = [c["task_id"] for c in self.task_configs]
+        self.encoder = build_encoder(config, task_ids=task_ids, precision=precision, zero_copy_features=zero_copy_features)
+        self.precision = self.encoder.model.precision
+        encoder_channels = list(self.encoder.out_channels)
+        decoders = build_decoders(self.encoder, config, precision=self.precision)
+        self.fpn_decoder_seg = decoders["fpn_seg"]
+        self.fpn_decoder_det = decoders["fpn_det"]
+        self.fpn_decoder_cls = decoders["fpn_cls"]
+        self.fpn_decoder_reg = decoders["fpn_reg"]
+        self.use_fpn_for_cls = config.get("model.decoder.use_fpn_for_classification", True)
+        self.use_fpn_for_reg = config.get("model.decoder.use_fpn_for_regression", True)
+        self.fpn_out_channels = self.fpn_decoder_seg.out_channels
+        self.use_film = False
+        self.use_task_prompt = False
+        self.use_moe = False
+        self.heads = build_all_heads(self.task_configs, self.fpn_out_channels, encoder_channels,
+                                     config.config.get("model", {}) if hasattr(config, "config") else {})
+        self.task_id_to_name = {c["task_id"]: c["task_name"] for c in self.task_configs}
+
+    def _head(self, task_id, x):
+        # the heads are plain PyTorch modules with fp32 parameters: run them under autocast in bf16 mode
+        if self.precision == "bf16":
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return self.heads[task_id](x)
+        return self.heads[task_id](x)
+
+    def forward(self, x, task_id):
+        if task_id not in self.heads:
+            raise ValueError(f"Unknown task_id: {task_id}")
+        task_name = self.task_id_to_name[task_id]
+        features = self.encoder(x, task_id) if getattr(self.encoder, "supports_task_id", False) else self.encoder(x)
+        if task_name == "segmentation":
+            return self._head(task_id, self.fpn_decoder_seg(features))
+        if task_name == "detection":
+            return self._head(task_id, self.fpn_decoder_det(features))
+        if task_name == "classification":
+            if self.use_fpn_for_cls:
+                return self._head(task_id, self.fpn_decoder_cls(features))
+            return self._head(task_id, features)
+        if self.use_fpn_for_reg:
+            return self._head(task_id, self.fpn_decoder_reg(features))
+        return self._head(task_id, features)
+
+    def get_trainable_parameters(self):
+        encoder_params = list(self.encoder.parameters())
+        head_params = list(self.fpn_decoder_seg.parameters())
+        if self.fpn_decoder_det is not self.fpn_decoder_seg:
+            head_params += list(self.fpn_decoder_det.parameters())
+        if self.use_fpn_for_cls and self.fpn_decoder_cls not in (self.fpn_decoder_seg, self.fpn_decoder_det):
+            head_params += list(self.fpn_decoder_cls.parameters())
+        if self.use_fpn_for_reg and self.fpn_decoder_reg not in (self.fpn_decoder_seg, self.fpn_decoder_det,
+                                                                 self.fpn_decoder_cls):
+            head_params += list(self.fpn_decoder_reg.parameters())
+        head_params += list(self.heads.parameters())
+        return encoder_params, head_params
+
+    def get_moe_aux_loss(self):
+        return torch.tensor(0.0, device=next(self.parameters()).device)
+
+    def get_moe_stats(self):
+        return []
+
+    def freeze_encoder(self):
+        for p in self.encoder.parameters():
+            p.requires_grad = False
+
+    def unfreeze_encoder(self):
+        for p in self.encoder.parameters():
+            p.requires_grad = True
+
+
+def build_model(config, precision=None, zero_copy_features=True):
+    model = MultiTaskModel(config, precision=precision, zero_copy_features=zero_copy_features)
+    if config.get("model.encoder.freeze_encoder", False):
+        model.freeze_encoder()
+    return model
+
+
+def build_optimizer(model, config):
+    """AdamW with the reference's grouped learning rates (code/train.py:176-219): encoder x0.1, heads x1.0."""
+    lr = float(config.get("training.optimizer.learning_rate", 1e-4))
+    wd = float(config.get("training.optimizer.weight_decay", 1e-4))
+    enc, head = model.get_trainable_parameters()
+    groups = [{"params": enc, "lr": lr * float(config.get("training.optimizer.encoder_lr_multiplier", 0.1))},
+              {"params": head, "lr": lr * float(config.get("training.optimizer.head_lr_multiplier", 1.0))}]
+    return torch.optim.AdamW(groups, lr=lr, weight_decay=wd)

@@ -1,0 +1,197 @@
+"""Thin per-kernel Python wrappers over the C-ABI (torch tensors in, torch tensors out).
+
+Used by the parity tests and for experimentation; the models call the whole-encoder / whole-decoder
+executors instead.  Every function raises on a non-zero status -- no fallback.
+"""
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ptr, stream_ptr, check, lib, F32, BF16
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-5):
+    rows, Cc = x.numel() // x.shape[-1], x.shape[-1]
+    y = torch.empty_like(x)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    check(lib().mtus_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), rows, Cc, eps, _dt(x), stream_ptr()), "layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None):
+    rows, Cc = x.numel() // x.shape[-1], x.shape[-1]
+    dx = torch.empty_like(x)
+    dg = torch.zeros(Cc, dtype=torch.float32, device=x.device)
+    db = torch.zeros_like(dg)
+    check(lib().mtus_layernorm_bwd(ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dres), ptr(dx), ptr(dg), ptr(db), rows, Cc, _dt(x), stream_ptr()), "layernorm_bwd")
+    return dx, dg, db
+
+
+def patch_merge_ln_fwd(x, gamma, beta, eps=1e-5):
+    B, H, W, Cc = x.shape
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    y = torch.empty(B, Ho, Wo, 4 * Cc, dtype=x.dtype, device=x.device)
+    mean = torch.empty(B * Ho * Wo, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    check(lib().mtus_patch_merge_ln_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), B, H, W, Cc, eps, _dt(x), stream_ptr()), "patch_merge_ln_fwd")
+    return y, mean, rstd
+
+
+def patch_merge_ln_bwd(dy, x, gamma, mean, rstd, dres=None):
+    B, H, W, Cc = x.shape
+    dx = torch.empty_like(x)
+    dg = torch.zeros(4 * Cc, dtype=torch.float32, device=x.device)
+    db = torch.zeros_like(dg)
+    check(lib().mtus_patch_merge_ln_bwd(ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dres), ptr(dx), ptr(dg), ptr(db), B, H, W, Cc, _dt(x), stream_ptr()), "patch_merge_ln_bwd")
+    return dx, dg, db
+
+
+def linear_fwd(x, w, bias=None, gelu=False, res=None, rowscale=None, rows_per_sample=1, backend=0):
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty(M, N, dtype=x.dtype, device=x.device)
+    pre = torch.empty_like(y) if gelu else None
+    check(lib().mtus_linear_fwd(ptr(x), ptr(w), ptr(bias), ptr(y), ptr(pre), ptr(res), ptr(rowscale), rows_per_sample, M, N, K, _dt(x), backend, stream_ptr()), "linear_fwd")
+    return (y, pre) if gelu else y
+
+
+def linear_dgrad(dy, w, gelu_pre=None, rowscale=None, rows_per_sample=1, backend=0):
+    M, N = dy.shape
+    K = w.shape[1]
+    dx = torch.empty(M, K, dtype=dy.dtype, device=dy.device)
+    check(lib().mtus_linear_dgrad(ptr(dy), ptr(w), ptr(dx), ptr(gelu_pre), ptr(rowscale), rows_per_sample, M, N, K, _dt(dy), backend, stream_ptr()), "linear_dgrad")
+    return dx
+
+
+def linear_wgrad(dy, x, with_bias=True, backend=0):
+    M, N = dy.shape
+    K = x.shape[1]
+    dw = torch.zeros(N, K, dtype=torch.float32, device=dy.device)
+    db = torch.zeros(N, dtype=torch.float32, device=dy.device) if with_bias else None
+    check(lib().mtus_linear_wgrad(ptr(dy), ptr(x), ptr(dw), ptr(db), M, N, K, _dt(dy), backend, stream_ptr()), "linear_wgrad")
+    return dw, db
+
+
+def window_attn_fwd(qkv, table, qkv_bias, heads, window, shift):
+    B, H, W, C3 = qkv.shape
+    Cc = C3 // 3
+    out = torch.empty(B, H, W, Cc, dtype=qkv.dtype, device=qkv.device)
+    check(lib().mtus_window_attn_fwd(ptr(qkv), ptr(table), ptr(qkv_bias), ptr(out), B, H, W, Cc, heads, window, window, shift, shift, _dt(qkv), stream_ptr()), "window_attn_fwd")
+    return out
+
+
+def window_attn_bwd(dout, qkv, out, table, qkv_bias, heads, window, shift):
+    B, H, W, C3 = qkv.shape
+    Cc = C3 // 3
+    dqkv = torch.empty_like(qkv)
+    dtable = torch.zeros_like(table)
+    dbias = torch.zeros(C3, dtype=torch.float32, device=qkv.device)
+    check(lib().mtus_window_attn_bwd(ptr(dout), ptr(qkv), ptr(out), ptr(table), ptr(qkv_bias), ptr(dqkv), ptr(dtable), ptr(dbias), B, H, W, Cc, heads, window, window, shift, shift, _dt(qkv), stream_ptr()), "window_attn_bwd")
+    return dqkv, dtable, dbias
+
+
+def conv3x3_repack(w, dtype):
+    Cout, Cin = w.shape[0], w.shape[1]
+    wf = torch.empty(Cout, 9 * Cin, dtype=dtype, device=w.device)
+    wd = torch.empty(Cin, 9 * Cout, dtype=dtype, device=w.device)
+    check(lib().mtus_conv3x3_repack(ptr(w), ptr(wf), ptr(wd), Cout, Cin, F32 if dtype == torch.float32 else BF16, stream_ptr()), "conv3x3_repack")
+    return wf, wd
+
+
+def conv3x3_fwd(x, wf, backend=0):
+    B, H, W, Cin = x.shape
+    Cout = wf.shape[0]
+    y = torch.empty(B, H, W, Cout, dtype=x.dtype, device=x.device)
+    check(lib().mtus_conv3x3_fwd(ptr(x), ptr(wf), ptr(y), B, H, W, Cin, Cout, _dt(x), backend, stream_ptr()), "conv3x3_fwd")
+    return y
+
+
+def conv3x3_dgrad(dy, wd, backend=0):
+    B, H, W, Cout = dy.shape
+    Cin = wd.shape[0]
+    dx = torch.empty(B, H, W, Cin, dtype=dy.dtype, device=dy.device)
+    check(lib().mtus_conv3x3_dgrad(ptr(dy), ptr(wd), ptr(dx), B, H, W, Cin, Cout, _dt(dy), backend, stream_ptr()), "conv3x3_dgrad")
+    return dx
+
+
+def conv3x3_wgrad(dy, x, backend=0):
+    B, H, W, Cout = dy.shape
+    Cin = x.shape[3]
+    dwp = torch.zeros(Cout, 9 * Cin, dtype=torch.float32, device=dy.device)
+    check(lib().mtus_conv3x3_wgrad(ptr(dy), ptr(x), ptr(dwp), B, H, W, Cin, Cout, _dt(dy), backend, stream_ptr()), "conv3x3_wgrad")
+    dw = torch.zeros(Cout, Cin, 3, 3, dtype=torch.float32, device=dy.device)
+    check(lib().mtus_conv3x3_unpack_grad(ptr(dwp), ptr(dw), Cout, Cin, stream_ptr()), "conv3x3_unpack_grad")
+    return dw
+
+
+def groupnorm_relu_fwd(x, gamma, beta, groups=32, eps=1e-5):
+    B, H, W, Cc = x.shape
+    mean = torch.empty(B * groups, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    check(lib().mtus_groupnorm_stats(ptr(x), ptr(mean), ptr(rstd), B, H * W, Cc, groups, eps, _dt(x), stream_ptr()), "groupnorm_stats")
+    y = torch.empty_like(x)
+    check(lib().mtus_groupnorm_relu_fwd(ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(y), B, H * W, Cc, groups, _dt(x), stream_ptr()), "groupnorm_relu_fwd")
+    return y, mean, rstd
+
+
+def groupnorm_relu_bwd(dy, x, y, mean, rstd, gamma, groups=32):
+    B, H, W, Cc = x.shape
+    dx = torch.empty_like(x)
+    dg = torch.zeros(Cc, dtype=torch.float32, device=x.device)
+    db = torch.zeros_like(dg)
+    ws = torch.empty(2 * B * groups, dtype=torch.float32, device=x.device)
+    check(lib().mtus_groupnorm_relu_bwd(ptr(dy), ptr(x), ptr(y), ptr(mean), ptr(rstd), ptr(gamma), ptr(dx), ptr(dg), ptr(db), ptr(ws), B, H * W, Cc, groups, _dt(x), stream_ptr()), "groupnorm_relu_bwd")
+    return dx, dg, db
+
+
+def bilinear2x_fwd(x):
+    B, H, W, Cc = x.shape
+    y = torch.empty(B, 2 * H, 2 * W, Cc, dtype=x.dtype, device=x.device)
+    check(lib().mtus_bilinear2x_fwd(ptr(x), ptr(y), B, H, W, Cc, _dt(x), stream_ptr()), "bilinear2x_fwd")
+    return y
+
+
+def bilinear2x_bwd(dy):
+    B, H2, W2, Cc = dy.shape
+    dx = torch.empty(B, H2 // 2, W2 // 2, Cc, dtype=dy.dtype, device=dy.device)
+    check(lib().mtus_bilinear2x_bwd(ptr(dy), ptr(dx), B, H2 // 2, W2 // 2, Cc, _dt(dy), stream_ptr()), "bilinear2x_bwd")
+    return dx
+
+
+def upsample_add_fwd(skip, top):
+    B, H, W, Cc = skip.shape
+    y = torch.empty_like(skip)
+    check(lib().mtus_upsample_add_fwd(ptr(skip), ptr(top), ptr(y), B, H, W, Cc, _dt(skip), stream_ptr()), "upsample_add_fwd")
+    return y
+
+
+def upsample_add_bwd(dy):
+    B, H, W, Cc = dy.shape
+    dtop = torch.empty(B, H // 2, W // 2, Cc, dtype=dy.dtype, device=dy.device)
+    check(lib().mtus_upsample_add_bwd(ptr(dy), ptr(dtop), 0, B, H, W, Cc, _dt(dy), stream_ptr()), "upsample_add_bwd")
+    return dtop
+
+
+def nhwc_to_nchw(x):
+    B, H, W, Cc = x.shape
+    y = torch.empty(B, Cc, H, W, dtype=x.dtype, device=x.device)
+    check(lib().mtus_nhwc_to_nchw(ptr(x), ptr(y), B, H * W, Cc, _dt(x), 0, stream_ptr()), "nhwc_to_nchw")
+    return y
+
+
+def nchw_to_nhwc(x):
+    B, Cc, H, W = x.shape
+    y = torch.empty(B, H, W, Cc, dtype=x.dtype, device=x.device)
+    check(lib().mtus_nchw_to_nhwc(ptr(x), ptr(y), B, H * W, Cc, _dt(x), 0, stream_ptr()), "nchw_to_nhwc")
+    return y

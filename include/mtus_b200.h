@@ -1,0 +1,215 @@
+/*
+ * mtus_b200.h -- C ABI of the B200-native MTUS-Net hot path (Swin encoder + FPN decoder).
+ *
+ * The reference (HJJ-D/Foundation-Model-Challenge-for-Ultrasound-Image-Analysis) has no FFI /
+ * plugin interface: its boundary for this path is the Python module API
+ *   models.encoders.build_encoder          (code/models/encoders.py:665)
+ *   models.decoders.build_decoders         (code/models/decoders.py:63)
+ *   MultiTaskModel.forward(x, task_id)     (code/models/multitask_model.py:176)
+ * and the arithmetic lives in timm / segmentation_models_pytorch.  This
+ * header is the C-ABI a maintainer would bind from those call sites (ctypes stub in
+ * INTEGRATION.md).  Conventions: raw device pointers, explicit sizes, an int dtype
+ * (MTUS_F32 / MTUS_BF16 = storage type of activations; accumulation is always fp32;
+ * parameters gamma/beta/bias/rel-pos tables are always fp32), a cudaStream_t passed as void*,
+ * int status return (0 ok, <0 argument errors below, >0 a cudaError_t).  No function allocates,
+ * frees or synchronises; the caller owns every buffer.
+ */
+#ifndef MTUS_B200_H_
+#define MTUS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTUS_OK 0
+#define MTUS_ERR_BAD_ARG (-1)
+#define MTUS_ERR_UNSUPPORTED (-2)
+#define MTUS_ERR_DRIVER (-3)
+
+#define MTUS_F32 0
+#define MTUS_BF16 1
+
+#define MTUS_BACKEND_AUTO 0
+#define MTUS_BACKEND_SIMT 1    /* fp32-FMA engine (fp32 parity mode, bring-up) */
+#define MTUS_BACKEND_TCGEN05 2 /* tcgen05 + TMEM + TMA engine (bf16 storage only) */
+
+int mtus_version(void);
+const char* mtus_status_string(int status);
+
+/* ---- LayerNorm (timm norm1/norm2/PatchEmbed.norm; SURVEY 8a a3,a4) ------------------------- */
+int mtus_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                       int64_t rows, int C, float eps, int dtype, void* stream);
+/* dx = dres + LN'(dy) (dres optional); dgamma/dbeta are ACCUMULATED (caller zeroes them). */
+int mtus_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                       const void* dres, void* dx, float* dgamma, float* dbeta, int64_t rows, int C, int dtype,
+                       void* stream);
+
+/* ---- PatchMerging gather + LayerNorm(4C) (timm PatchMerging) ----------------- */
+int mtus_patch_merge_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                            float* rstd, int B, int H, int W, int C, float eps, int dtype, void* stream);
+int mtus_patch_merge_ln_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
+                            const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta, int B,
+                            int H, int W, int C, int dtype, void* stream);
+
+/* ---- generic fused GEMM: C[M,N] = sum_k A(m,k) B(n,k), fp32 accumulate --------------------- */
+typedef struct mtus_gemm_desc {
+  const void* a;  int64_t lda; int a_mn_major; int a_conv;  /* stored [rows][cols], cols contiguous */
+  const void* b;  int64_t ldb; int b_mn_major; int b_conv;  /* *_mn_major=0: (mn,k)=(row,col); 1: (mn,k)=(col,row) */
+  int conv_h, conv_w, conv_c;  /* NHWC geometry when a_conv/b_conv: implicit 3x3 im2col, col = tap*C + c */
+  int M, N, K;
+  const float* bias;           /* [N] or NULL */
+  int act;                     /* 0 none | 1 GELU (pre-activation also stored to aux) | 2 multiply by GELU'(aux) */
+  void* aux; int64_t ld_aux;
+  const void* res; int64_t ld_res; int res_mode; int res_h, res_w; /* 1 same row | 2 nearest-x2 gather */
+  const float* rowscale; int rows_per_sample; /* drop-path scale per sample */
+  void* out; int64_t ld_out; int out_f32; int atomic;
+  int split_k;
+  int dtype;
+  int backend;
+} mtus_gemm_desc;
+
+int mtus_gemm(const mtus_gemm_desc* desc, void* stream);
+
+/* nn.Linear forward: y[M,N] = x[M,K] w[N,K]^T + bias, optional GELU (h = pre-activation out),
+ * optional residual y = res + rowscale[m / rows_per_sample] * (...)  (timm qkv/proj/fc1/fc2/reduction; 8a a6,a7,a8). */
+int mtus_linear_fwd(const void* x, const void* w, const float* bias, void* y, void* gelu_pre, const void* res,
+                    const float* rowscale, int rows_per_sample, int64_t M, int N, int K, int dtype, int backend,
+                    void* stream);
+/* dx[M,K] = dy[M,N] w[N,K]  (optionally * GELU'(gelu_pre[M,K]), optionally scaled per sample) */
+int mtus_linear_dgrad(const void* dy, const void* w, void* dx, const void* gelu_pre, const float* rowscale,
+                      int rows_per_sample, int64_t M, int N, int K, int dtype, int backend, void* stream);
+/* dw[N,K] += dy[M,N]^T x[M,K] (fp32, accumulated); db[N] += colsum(dy) when db != NULL */
+int mtus_linear_wgrad(const void* dy, const void* x, float* dw, float* db, int64_t M, int N, int K, int dtype,
+                      int backend, void* stream);
+
+/* ---- elementwise helpers -------------------------------------------------------------------- */
+int mtus_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+int mtus_colsum(const void* x, float* out, int64_t rows, int C, int dtype, void* stream); /* out += */
+int mtus_scale_rows(const void* x, void* y, const float* rowscale, int rows_per_sample, int64_t rows, int C,
+                    int dtype, void* stream);
+int mtus_add(const void* a, const void* b, void* y, int64_t n, int dtype, void* stream);
+int mtus_nhwc_to_nchw(const void* x, void* y, int B, int HW, int C, int dtype, int out_f32, void* stream);
+int mtus_nchw_to_nhwc(const void* x, void* y, int B, int HW, int C, int dtype, int in_f32, void* stream);
+
+/* ---- PatchEmbed (timm PatchEmbed; 8a a3): 4x4/4 conv as im2col (K padded 48->64) + GEMM + LN -- */
+int mtus_patch_embed_im2col(const void* x_nchw, void* cols, int B, int H, int W, int x_is_f32, int dtype,
+                            void* stream);
+
+/* ---- fused shifted-window attention (timm _attn + WindowAttention; 8a a5,a6) ----------------
+ * qkv: [B,H,W,3C] NHWC (output of the qkv Linear, bias included), out: [B,H,W,C].
+ * The cyclic shift, zero padding to a multiple of the window, window partition/reverse, q scaling,
+ * relative-position bias, shift mask (-100), softmax and P@V all happen inside the kernel; nothing
+ * window-shaped is materialised in HBM.  qkv_bias ([3C], fp32) supplies q/k/v of the padded tokens
+ * (timm pads AFTER norm1, so pad tokens carry only the bias); may be NULL when H,W divide by window. */
+int mtus_window_attn_fwd(const void* qkv, const float* rel_table, const float* qkv_bias, void* out, int B, int H,
+                         int W, int C, int heads, int win_h, int win_w, int shift_h, int shift_w, int dtype,
+                         void* stream);
+/* out = the forward output (delta_i = dout_i . out_i); dqkv fully written; drel_table [(2wh-1)(2ww-1), heads] and dqkv_bias [3C] (may be NULL) ACCUMULATED. */
+int mtus_window_attn_bwd(const void* dout, const void* qkv, const void* out, const float* rel_table,
+                         const float* qkv_bias, void* dqkv, float* drel_table, float* dqkv_bias, int B, int H, int W,
+                         int C, int heads, int win_h, int win_w, int shift_h, int shift_w, int dtype, void* stream);
+
+/* ---- FPN pieces (smp FPNDecoder; 8a a11-a13), all NHWC --------------------------------------- */
+/* nearest-x2 top-down: y[b,h,w,:] = skip[b,h,w,:] + top[b,h/2,w/2,:] */
+int mtus_upsample_add_fwd(const void* skip, const void* top, void* y, int B, int H, int W, int C, int dtype,
+                          void* stream);
+/* dtop[b,i,j,:] = (acc ? dtop : 0) + sum of the 2x2 block of dy */
+int mtus_upsample_add_bwd(const void* dy, void* dtop, int accumulate, int B, int H, int W, int C, int dtype,
+                          void* stream);
+/* GroupNorm(G) statistics over (H*W, C/G) per (sample, group), NHWC */
+int mtus_groupnorm_stats(const void* x, float* mean, float* rstd, int B, int HW, int C, int G, float eps, int dtype,
+                         void* stream);
+/* y = relu(gn(x)) */
+int mtus_groupnorm_relu_fwd(const void* x, const float* mean, const float* rstd, const float* gamma,
+                            const float* beta, void* y, int B, int HW, int C, int G, int dtype, void* stream);
+/* dx; dgamma/dbeta ACCUMULATED.  y is the saved post-ReLU output (mask = y > 0). ws: 2*B*G floats. */
+int mtus_groupnorm_relu_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* rstd,
+                            const float* gamma, void* dx, float* dgamma, float* dbeta, float* ws, int B, int HW,
+                            int C, int G, int dtype, void* stream);
+/* bilinear x2, align_corners=True, NHWC */
+int mtus_bilinear2x_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
+int mtus_bilinear2x_bwd(const void* dy, void* dx, int B, int H, int W, int C, int dtype, void* stream);
+/* merge: nsrc NHWC maps [B,HW,C] -> NCHW out [B, nsrc*C (cat) | C (add), HW], times chanscale[b, c_out]
+ * (Dropout2d mask / (1-p); NULL = identity).  out dtype fp32 when out_f32. */
+int mtus_fpn_merge_fwd(const void* const* srcs, int nsrc, int policy_cat, const float* chanscale, void* out, int B,
+                       int HW, int C, int dtype, int out_f32, void* stream);
+int mtus_fpn_merge_bwd(const void* dout, int nsrc, int policy_cat, const float* chanscale, void* const* dsrcs, int B,
+                       int HW, int C, int dtype, int in_f32, void* stream);
+/* repack Conv2d weight [Cout,Cin,3,3] fp32 -> fwd [Cout, 9*Cin] and dgrad [Cin, 9*Cout] (taps flipped) */
+int mtus_conv3x3_repack(const float* w, void* w_fwd, void* w_dgrad, int Cout, int Cin, int dtype, void* stream);
+/* dw[Cout,Cin,3,3] (fp32, ACCUMULATED) from the packed [Cout, 9*Cin] gradient */
+int mtus_conv3x3_unpack_grad(const float* dw_packed, float* dw, int Cout, int Cin, void* stream);
+int mtus_conv3x3_fwd(const void* x, const void* w_fwd, void* y, int B, int H, int W, int Cin, int Cout, int dtype,
+                     int backend, void* stream);
+int mtus_conv3x3_dgrad(const void* dy, const void* w_dgrad, void* dx, int B, int H, int W, int Cin, int Cout,
+                       int dtype, int backend, void* stream);
+int mtus_conv3x3_wgrad(const void* dy, const void* x, float* dw_packed, int B, int H, int W, int Cin, int Cout,
+                       int dtype, int backend, void* stream);
+
+/* ---- whole-encoder / whole-decoder executors (C++ runtime; one call per direction) ------------ */
+typedef struct mtus_swin_config {
+  int batch, img_size, embed_dim;
+  int depths[4], heads[4];
+  int window;
+  int dtype;          /* activation storage dtype */
+  int backend;        /* GEMM backend */
+  int training;       /* 1: save activations for backward */
+  float ln_eps;
+} mtus_swin_config;
+
+/* number of fp32 elements in the flat parameter / gradient buffer, and the byte size of the
+ * activation workspace the caller must provide to forward (and keep until backward). */
+int64_t mtus_swin_param_count(const mtus_swin_config* cfg);
+int64_t mtus_swin_workspace_bytes(const mtus_swin_config* cfg);
+/* offset (elements) of a named tensor in the flat buffer; names follow timm's state-dict keys
+ * (patch_embed.proj.weight, layers_1.downsample.norm.weight, layers_2.blocks.3.attn.qkv.bias, ...).
+ * Returns -1 when unknown.  numel written to *numel. */
+int64_t mtus_swin_param_offset(const mtus_swin_config* cfg, const char* name, int64_t* numel);
+/* enumerate parameters: fills name (<=127 chars), offset, rank and shape of parameter idx; returns 0/-1 */
+int mtus_swin_param_info(const mtus_swin_config* cfg, int idx, char* name, int64_t* offset, int* rank,
+                         int64_t* shape);
+/* byte offset, inside the workspace, of the NHWC output [B,H_i,W_i,C_i] of stage i (valid after
+ * forward): lets the caller expose the features as zero-copy channels-last views. */
+int64_t mtus_swin_feature_offset(const mtus_swin_config* cfg, int stage);
+/* x: [B,3,S,S] NCHW (fp32 when x_is_f32 else dtype); params: flat fp32; params_lp: flat bf16 copy
+ * (required for dtype=BF16, produced by mtus_cast_f32_to_bf16); droppath: [n_blocks*2, B] fp32 scales
+ * or NULL; feats[4]: outputs (entries may be NULL = not materialised), feats_layout 0 = NCHW
+ * (the reference's permute(0,3,1,2).contiguous()), 1 = NHWC; fp32 when feats_f32 (NCHW only). */
+int mtus_swin_forward(const mtus_swin_config* cfg, const void* x, int x_is_f32, const float* params,
+                      const void* params_lp, const float* droppath, void* workspace, void* const* feats,
+                      int feats_layout, int feats_f32, void* stream);
+/* dfeats[4]: NCHW grads (NULL = zero); grads: flat fp32, ACCUMULATED into (caller zeroes).
+ * stage_hi/stage_lo: run backward for stages stage_hi-1 down to stage_lo (4,0 = everything), so the
+ * caller can interleave gradient all-reduce of finished stages with the remaining backward. */
+int mtus_swin_backward(const mtus_swin_config* cfg, const float* params, const void* params_lp,
+                       const float* droppath, void* workspace, const void* const* dfeats, int dfeats_layout,
+                       int dfeats_f32, float* grads, int stage_hi, int stage_lo, void* stream);
+
+typedef struct mtus_fpn_config {
+  int batch;
+  int in_channels[4]; /* c2..c5 channels (stride 4..32) */
+  int sizes[4];       /* spatial size (square) of c2..c5 */
+  int pyramid_channels, seg_channels;
+  int merge_cat;
+  int dtype, backend, training;
+} mtus_fpn_config;
+
+int64_t mtus_fpn_param_count(const mtus_fpn_config* cfg);
+int64_t mtus_fpn_workspace_bytes(const mtus_fpn_config* cfg);
+int mtus_fpn_param_info(const mtus_fpn_config* cfg, int idx, char* name, int64_t* offset, int* rank, int64_t* shape);
+/* feats[4]: encoder features c2..c5 (feats_layout 0 NCHW | 1 NHWC); chanscale: [B, out_channels]
+ * Dropout2d scales or NULL; out: NCHW [B, out_channels, S2, S2]. */
+int mtus_fpn_forward(const mtus_fpn_config* cfg, const void* const* feats, int feats_layout, int feats_f32,
+                     const float* params, const float* chanscale, void* workspace, void* out, int out_f32,
+                     void* stream);
+/* dfeats[4]: gradients w.r.t. c2..c5, fully written, in dfeats_layout; grads: flat fp32, ACCUMULATED. */
+int mtus_fpn_backward(const mtus_fpn_config* cfg, const void* const* feats, int feats_layout, int feats_f32,
+                      const float* params, const float* chanscale, void* workspace, const void* dout, int dout_f32,
+                      void* const* dfeats, int dfeats_layout, int dfeats_f32, float* grads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTUS_B200_H_ */

@@ -1,0 +1,341 @@
+"""GPU bring-up diagnostics (test infrastructure): runs every kernel group against a PyTorch reference in
+its own subprocess (a faulting kernel must not poison the rest) and prints error tables.
+
+    python tests/gpu_diag.py            # all groups
+    python tests/gpu_diag.py gemm_tc    # one group, in-process
+"""
+
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+GROUPS = ["elementwise", "gemm_simt", "gemm_tc", "attention", "fpn_ops", "model_fp32", "model_bf16_simt", "model_bf16_tc"]
+
+
+def err(a, b):
+    a, b = a.float(), b.float()
+    d = (a - b).abs().max().item()
+    rel = d / (b.abs().max().item() + 1e-12)
+    return d, rel
+
+
+def report(name, got, ref, tol):
+    import torch
+    d, rel = err(got, ref)
+    bad = not (rel <= tol) or not torch.isfinite(got.float()).all().item()
+    print(f"  {'FAIL' if bad else 'ok  '} {name:58s} max|d|={d:.3e} rel={rel:.3e} tol={tol:.0e}", flush=True)
+    return not bad
+
+
+def g_elementwise():
+    import torch
+    import torch.nn.functional as F
+    import mtus_b200 as m
+    from mtus_b200 import ops
+    ok = True
+    dev = "cuda"
+    for dt, tol in ((torch.float32, 2e-5), (torch.bfloat16, 2e-2)):
+        for rows, Cc in ((1000, 96), (3137, 128), (777, 512), (300, 768), (200, 1024), (100, 1536), (64, 3072)):
+            x = torch.randn(rows, Cc, device=dev).to(dt)
+            g = torch.randn(Cc, device=dev) * 0.5 + 1
+            b = torch.randn(Cc, device=dev) * 0.1
+            y, mean, rstd = ops.layernorm_fwd(x, g, b)
+            xr = x.float().requires_grad_(True)
+            gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+            yr = F.layer_norm(xr, (Cc,), gr, br, 1e-5)
+            ok &= report(f"ln_fwd {dt} [{rows},{Cc}]", y, yr, tol)
+            dy = torch.randn(rows, Cc, device=dev).to(dt)
+            dres = torch.randn(rows, Cc, device=dev).to(dt)
+            dx, dg, db = ops.layernorm_bwd(dy, x, g, mean, rstd, dres)
+            yr.backward(dy.float())
+            ok &= report(f"ln_bwd dx {dt} [{rows},{Cc}]", dx, xr.grad + dres.float(), tol)
+            ok &= report(f"ln_bwd dgamma {dt} [{rows},{Cc}]", dg, gr.grad, max(tol, 2e-4))
+            ok &= report(f"ln_bwd dbeta {dt} [{rows},{Cc}]", db, br.grad, max(tol, 2e-4))
+        for (B, H, W, Cc) in ((2, 8, 8, 32), (3, 7, 7, 64), (2, 14, 14, 128), (1, 5, 9, 768)):
+            x = torch.randn(B, H, W, Cc, device=dev).to(dt)
+            g = torch.randn(4 * Cc, device=dev) * 0.5 + 1
+            b = torch.randn(4 * Cc, device=dev) * 0.1
+            y, mean, rstd = ops.patch_merge_ln_fwd(x, g, b)
+            xr = x.float().requires_grad_(True)
+            xp = F.pad(xr, (0, 0, 0, W % 2, 0, H % 2))
+            Hp, Wp = xp.shape[1], xp.shape[2]
+            xg = xp.reshape(B, Hp // 2, 2, Wp // 2, 2, Cc).permute(0, 1, 3, 4, 2, 5).flatten(3)
+            yr = F.layer_norm(xg, (4 * Cc,), g, b, 1e-5)
+            ok &= report(f"merge_ln_fwd {dt} {B,H,W,Cc}", y, yr, tol)
+            dy = torch.randn_like(yr).to(dt)
+            dx, dg, db = ops.patch_merge_ln_bwd(dy, x, g, mean, rstd)
+            yr.backward(dy.float())
+            ok &= report(f"merge_ln_bwd {dt} {B,H,W,Cc}", dx, xr.grad, tol)
+        x = torch.randn(3, 7, 9, 40, device=dev).to(dt)
+        ok &= report(f"nhwc_to_nchw {dt}", ops.nhwc_to_nchw(x), x.permute(0, 3, 1, 2), 0)
+        ok &= report(f"nchw_to_nhwc {dt}", ops.nchw_to_nhwc(x.permute(0, 3, 1, 2).contiguous()), x, 0)
+    return ok
+
+
+def _lin_cases():
+    return [(256, 128, 128), (1000, 384, 128), (300, 96, 288), (777, 512, 2048), (1568, 2048, 512), (128, 64, 64), (100, 256, 1024)]
+
+
+def _gemm_group(backend, dts):
+    import torch
+    import torch.nn.functional as F
+    from mtus_b200 import ops
+    ok = True
+    dev = "cuda"
+    for dt, tol in dts:
+        for (M, N, K) in _lin_cases():
+            x = (torch.randn(M, K, device=dev) * 0.5).to(dt)
+            w = (torch.randn(N, K, device=dev) * 0.05).to(dt)
+            bias = torch.randn(N, device=dev) * 0.1
+            res = torch.randn(M, N, device=dev).to(dt)
+            rs = torch.rand(4, device=dev) + 0.5
+            rps = (M + 3) // 4
+            y = ops.linear_fwd(x, w, bias, backend=backend)
+            yr = x.float() @ w.float().t() + bias
+            ok &= report(f"linear_fwd {dt} M{M} N{N} K{K}", y, yr, tol)
+            y2 = ops.linear_fwd(x, w, bias, res=res, rowscale=rs, rows_per_sample=rps, backend=backend)
+            sc = rs[torch.arange(M, device=dev) // rps][:, None]
+            ok &= report(f"linear_fwd+res+rowscale", y2, res.float() + sc * yr, tol)
+            a, pre = ops.linear_fwd(x, w, bias, gelu=True, backend=backend)
+            ok &= report(f"linear_fwd+gelu (act)", a, F.gelu(yr), tol)
+            ok &= report(f"linear_fwd+gelu (pre)", pre, yr, tol)
+            dy = (torch.randn(M, N, device=dev) * 0.5).to(dt)
+            dx = ops.linear_dgrad(dy, w, backend=backend)
+            ok &= report(f"linear_dgrad", dx, dy.float() @ w.float(), tol)
+            hp = torch.randn(M, K, device=dev).to(dt)
+            dx2 = ops.linear_dgrad(dy, w, gelu_pre=hp, backend=backend)
+            hpf = hp.float().requires_grad_(True)
+            F.gelu(hpf).backward(dy.float() @ w.float())
+            ok &= report(f"linear_dgrad*gelu'", dx2, hpf.grad, tol)
+            dw, db = ops.linear_wgrad(dy, x, backend=backend)
+            ok &= report(f"linear_wgrad dw", dw, dy.float().t() @ x.float(), max(tol, 1e-4))
+            ok &= report(f"linear_wgrad db", db, dy.float().sum(0), max(tol, 1e-4))
+        for (B, H, W, Cin, Cout) in ((2, 7, 7, 64, 128), (2, 14, 14, 256, 128), (1, 28, 28, 128, 128), (2, 56, 56, 64, 64)):
+            x = (torch.randn(B, H, W, Cin, device=dev) * 0.5).to(dt)
+            w = torch.randn(Cout, Cin, 3, 3, device=dev) * 0.05
+            wf, wd = ops.conv3x3_repack(w, dt)
+            wq = wf.float().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2).contiguous()   # as stored (rounded) weights
+            xr = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+            wr = wq.clone().requires_grad_(True)
+            yr = F.conv2d(xr, wr, padding=1)
+            y = ops.conv3x3_fwd(x, wf, backend=backend)
+            ok &= report(f"conv3x3_fwd {dt} {B,H,W,Cin,Cout}", y, yr.permute(0, 2, 3, 1), tol)
+            dy = (torch.randn(B, H, W, Cout, device=dev) * 0.5).to(dt)
+            yr.backward(dy.float().permute(0, 3, 1, 2))
+            dx = ops.conv3x3_dgrad(dy, wd, backend=backend)
+            ok &= report(f"conv3x3_dgrad", dx, xr.grad.permute(0, 2, 3, 1), tol)
+            dw = ops.conv3x3_wgrad(dy, x, backend=(0 if backend == 2 else backend))  # tcgen05 conv wgrad: not yet -> auto
+            ok &= report(f"conv3x3_wgrad", dw, wr.grad, max(tol, 1e-4))
+    return ok
+
+
+def g_gemm_simt():
+    import torch
+    return _gemm_group(1, ((torch.float32, 2e-5), (torch.bfloat16, 2e-2)))
+
+
+def g_gemm_tc():
+    import torch
+    return _gemm_group(2, ((torch.bfloat16, 2e-2),))
+
+
+def _attn_ref(qkv, table, qkv_bias, heads, win, shift):
+    """Reference through the oracle's WindowAttention pieces (roll -> pad -> partition -> attention -> reverse)."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import swin as osw
+    B, H, W, C3 = qkv.shape
+    Cc = C3 // 3
+    x = qkv
+    if shift:
+        x = torch.roll(x, (-shift, -shift), (1, 2))
+    ph, pw = (win - H % win) % win, (win - W % win) % win
+    if ph or pw:
+        xb = qkv_bias.view(1, 1, 1, C3).expand(B, H + ph, W + pw, C3).clone()
+        xb[:, :H, :W] = x
+        x = xb
+    Hp, Wp = H + ph, W + pw
+    xw = osw.window_partition(x, (win, win)).view(-1, win * win, 3, heads, 32).permute(2, 0, 3, 1, 4)
+    q, k, v = xw[0] * (32 ** -0.5), xw[1], xw[2]
+    attn = q @ k.transpose(-2, -1)
+    idx = osw.relative_position_index(win, win).to(qkv.device)
+    attn = attn + table[idx.view(-1)].view(win * win, win * win, -1).permute(2, 0, 1).unsqueeze(0)
+    if shift:
+        blk = osw.SwinTransformerBlock.__new__(osw.SwinTransformerBlock)
+        blk.input_resolution, blk.window_size, blk.shift_size, blk.window_area = (H, W), (win, win), (shift, shift), win * win
+        mask = osw.SwinTransformerBlock.get_attn_mask(blk).to(qkv.device)
+        nW = mask.shape[0]
+        attn = (attn.view(-1, nW, heads, win * win, win * win) + mask.unsqueeze(1).unsqueeze(0)).view(-1, heads, win * win, win * win)
+    o = (attn.softmax(-1) @ v).transpose(1, 2).reshape(-1, win, win, Cc)
+    o = osw.window_reverse(o, (win, win), Hp, Wp)[:, :H, :W]
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    return o
+
+
+def g_attention():
+    import torch
+    from mtus_b200 import ops
+    ok = True
+    dev = "cuda"
+    cases = [(2, 14, 14, 2, 7, 0), (2, 14, 14, 2, 7, 3), (1, 56, 56, 4, 7, 3), (2, 7, 7, 8, 7, 0), (2, 4, 4, 1, 4, 0),
+             (1, 24, 24, 3, 12, 6), (2, 16, 16, 2, 7, 3), (1, 9, 9, 1, 7, 3)]
+    for dt, tol in ((torch.float32, 5e-5), (torch.bfloat16, 3e-2)):
+        for (B, H, W, heads, win, shift) in cases:
+            Cc = heads * 32
+            qkv = torch.randn(B, H, W, 3 * Cc, device=dev).to(dt)
+            table = torch.randn((2 * win - 1) ** 2, heads, device=dev) * 0.5
+            bias = torch.randn(3 * Cc, device=dev) * 0.5
+            out = ops.window_attn_fwd(qkv, table, bias, heads, win, shift)
+            qr = qkv.float().requires_grad_(True)
+            tr, br = table.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+            ref = _attn_ref(qr, tr, br, heads, win, shift)
+            ok &= report(f"attn_fwd {dt} B{B} {H}x{W} h{heads} w{win} s{shift}", out, ref, tol)
+            dout = torch.randn(B, H, W, Cc, device=dev).to(dt)
+            ref.backward(dout.float())
+            dqkv, dtab, dbias = ops.window_attn_bwd(dout, qkv, out, table, bias, heads, win, shift)
+            ok &= report(f"attn_bwd dqkv", dqkv, qr.grad, tol)
+            ok &= report(f"attn_bwd dtable", dtab, tr.grad, max(tol, 2e-4))
+            if br.grad is not None:
+                ok &= report(f"attn_bwd dqkv_bias (pad tokens)", dbias, br.grad, max(tol, 2e-4))
+    return ok
+
+
+def g_fpn_ops():
+    import torch
+    import torch.nn.functional as F
+    from mtus_b200 import ops
+    ok = True
+    dev = "cuda"
+    for dt, tol in ((torch.float32, 2e-5), (torch.bfloat16, 2e-2)):
+        for (B, H, W, Cc) in ((2, 7, 7, 128), (3, 14, 14, 128), (2, 56, 56, 128), (1, 28, 28, 64)):
+            x = (torch.randn(B, H, W, Cc, device=dev) * 2 + 0.3).to(dt)
+            g = torch.randn(Cc, device=dev) * 0.5 + 1
+            b = torch.randn(Cc, device=dev) * 0.1
+            y, mean, rstd = ops.groupnorm_relu_fwd(x, g, b)
+            xr = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+            gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+            yr = F.relu(F.group_norm(xr, 32, gr, br, 1e-5))
+            ok &= report(f"gn_relu_fwd {dt} {B,H,W,Cc}", y, yr.permute(0, 2, 3, 1), tol)
+            dy = torch.randn(B, H, W, Cc, device=dev).to(dt)
+            yr.backward(dy.float().permute(0, 3, 1, 2))
+            dx, dg, db = ops.groupnorm_relu_bwd(dy, x, y, mean, rstd, g)
+            ok &= report(f"gn_relu_bwd dx", dx, xr.grad.permute(0, 2, 3, 1), max(tol, 1e-4))
+            ok &= report(f"gn_relu_bwd dgamma", dg, gr.grad, max(tol, 3e-4))
+            ok &= report(f"gn_relu_bwd dbeta", db, br.grad, max(tol, 3e-4))
+            xr2 = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+            ur = F.interpolate(xr2, scale_factor=2.0, mode="bilinear", align_corners=True)
+            ok &= report(f"bilinear2x_fwd", ops.bilinear2x_fwd(x), ur.permute(0, 2, 3, 1), tol)
+            du = torch.randn(B, 2 * H, 2 * W, Cc, device=dev).to(dt)
+            ur.backward(du.float().permute(0, 3, 1, 2))
+            ok &= report(f"bilinear2x_bwd", ops.bilinear2x_bwd(du), xr2.grad.permute(0, 2, 3, 1), tol)
+            top = torch.randn(B, H, W, Cc, device=dev).to(dt)
+            skip = torch.randn(B, 2 * H, 2 * W, Cc, device=dev).to(dt)
+            refu = skip.float() + F.interpolate(top.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+            ok &= report(f"upsample_add_fwd", ops.upsample_add_fwd(skip, top), refu, tol)
+            ok &= report(f"upsample_add_bwd", ops.upsample_add_bwd(du), F.avg_pool2d(du.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1) * 4, tol)
+    return ok
+
+
+def _model_group(precision, gemm_env, tol, cos_min, variants):
+    import torch
+    torch.backends.cudnn.allow_tf32 = False          # the oracle (and the PyTorch heads) must be true fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    if gemm_env:
+        os.environ["MTUS_GEMM"] = gemm_env
+    import mtus_b200 as m
+    from oracle.model import OracleMultiTaskModel
+    ok = True
+    for (enc, img, batch, tasks) in variants:
+        cfg = m.make_config(enc, img, batch, mixed_precision=(precision == "bf16"), dropout=0.0,
+                            tasks=[t for t in m.tasks_27() if t["task_id"] in tasks])
+        torch.manual_seed(0)
+        oracle = OracleMultiTaskModel(cfg, drop_path_rate=0.0).cuda().eval()
+        model = m.build_model(cfg, precision=precision).cuda().eval()
+        model.load_state_dict(oracle.state_dict())
+        for p in list(oracle.parameters()):
+            p.requires_grad_(True)
+        gen = torch.Generator().manual_seed(1)
+        x = torch.randn(batch, 3, img, img, generator=gen).cuda()
+        # encoder features
+        fo = oracle.encoder(x)
+        fm = model.encoder(x)
+        for i, (a, b) in enumerate(zip(fm, fo)):
+            ok &= report(f"{enc}@{img} {precision} feature[{i}] {tuple(b.shape)}", a, b, tol)
+        for tid in tasks:
+            oracle.zero_grad(set_to_none=True)
+            model.zero_grad(set_to_none=True)
+            yo = oracle(x, tid)
+            ym = model(x, tid)
+            ok &= report(f"{enc}@{img} {precision} output[{tid}]", ym, yo, tol)
+            yo.float().square().mean().backward()
+            ym.float().square().mean().backward()
+            worst, worst_name, n = 1.0, "", 0
+            po = dict(oracle.named_parameters())
+            for name, p in model.named_parameters():
+                go = po[name].grad
+                if go is None:
+                    if p.grad is not None and p.grad.abs().max() > 0:
+                        print(f"  FAIL {name}: oracle has no grad but kernel path produced one")
+                        ok = False
+                    continue
+                if p.grad is None:
+                    print(f"  FAIL {name}: missing gradient")
+                    ok = False
+                    continue
+                a, b = p.grad.float().flatten(), go.float().flatten()
+                if b.norm() == 0 and a.norm() == 0:
+                    continue
+                c = torch.nn.functional.cosine_similarity(a, b, dim=0).item()
+                n += 1
+                if c < worst:
+                    worst, worst_name = c, name
+            bad = not (worst >= cos_min)
+            print(f"  {'FAIL' if bad else 'ok  '} {enc}@{img} {precision} grads[{tid}]: {n} tensors, min cosine {worst:.6f} ({worst_name})", flush=True)
+            ok &= not bad
+    return ok
+
+
+_VARIANTS_SMALL = [("swin_micro_patch4_window7_test", 56, 2, ["T2A_fetal_abdomen", "T1_fetal_planes"]),
+                   ("swin_micro_patch4_window7_test", 112, 2, ["T4A_fetal_brain", "T5_fetal_femur"]),
+                   ("swin_t", 224, 2, ["T2A_fetal_abdomen"])]
+
+
+def g_model_fp32():
+    return _model_group("fp32", None, 1e-4, 0.999, _VARIANTS_SMALL)
+
+
+def g_model_bf16_simt():
+    return _model_group("bf16", "simt", 2e-2, 0.99, _VARIANTS_SMALL[:2])
+
+
+def g_model_bf16_tc():
+    return _model_group("bf16", "tc", 2e-2, 0.99, _VARIANTS_SMALL)
+
+
+def main():
+    if len(sys.argv) > 1:
+        name = sys.argv[1]
+        t = time.time()
+        ok = globals()["g_" + name]()
+        import torch
+        torch.cuda.synchronize()
+        print(f"[{name}] {'PASS' if ok else 'FAIL'} in {time.time() - t:.1f}s", flush=True)
+        sys.exit(0 if ok else 1)
+    results = {}
+    for g in GROUPS:
+        print(f"=== {g} ===", flush=True)
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), g], timeout=600)
+            results[g] = r.returncode
+        except subprocess.TimeoutExpired:
+            results[g] = "timeout"
+    print("SUMMARY", results)
+
+
+if __name__ == "__main__":
+    main()
