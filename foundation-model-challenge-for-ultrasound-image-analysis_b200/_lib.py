@@ -56,6 +56,7 @@ _P = C.POINTER
 SIGNATURES = {
     "mtus_version": (i32, []),
     "mtus_status_string": (C.c_char_p, [i32]),
+    "mtus_launch_count": (i64, []),
     "mtus_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, f32, i32, vp]),
     "mtus_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
     "mtus_patch_merge_ln_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp]),

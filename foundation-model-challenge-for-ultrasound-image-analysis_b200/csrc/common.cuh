@@ -10,7 +10,10 @@
 typedef __nv_bfloat16 bf16;
 
 #define MTUS_CHECK_ARG(cond) do { if (!(cond)) return MTUS_ERR_BAD_ARG; } while (0)
-#define MTUS_LAUNCH_STATUS() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; } while (0)
+// every kernel launch of this library is counted (bench.py reports it as gpu_launches)
+extern "C" void mtus_internal_count_launches(int n);
+#define MTUS_LAUNCH_STATUS_N(n) do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; mtus_internal_count_launches(n); } while (0)
+#define MTUS_LAUNCH_STATUS() MTUS_LAUNCH_STATUS_N(1)
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

@@ -155,7 +155,7 @@ extern "C" int mtus_groupnorm_stats(const void* x, float* mean, float* rstd, int
     gn_stats_kernel<bf16, 1><<<grid, 256, sm, st>>>((const bf16*)x, mean, rstd, HW, C, G, ppc);
   } else return MTUS_ERR_UNSUPPORTED;
   gn_finalize_kernel<<<ceil_div(B * G, 256), 256, 0, st>>>(mean, rstd, B * G, 1.0f / ((float)HW * (C / G)), eps);
-  MTUS_LAUNCH_STATUS();
+  MTUS_LAUNCH_STATUS_N(3);
   return MTUS_OK;
 }
 
@@ -294,7 +294,7 @@ extern "C" int mtus_groupnorm_relu_bwd(const void* dy, const void* x, const void
     gn_bwd_reduce_kernel<bf16><<<grid, 256, sm, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, rstd, gamma, ws, dgamma, dbeta, B, HW, C, G, ppc);
     gn_bwd_apply_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, rstd, gamma, ws, (bf16*)dx, total, B, HW, C / 8, G, C / G);
   } else return MTUS_ERR_UNSUPPORTED;
-  MTUS_LAUNCH_STATUS();
+  MTUS_LAUNCH_STATUS_N(2);
   return MTUS_OK;
 }
 

@@ -4,7 +4,13 @@
 // vectorised, grid-stride kernels; HBM roofline, algorithmic bytes = one read + one write of the tensor.
 #include "common.cuh"
 
-extern "C" int mtus_version(void) { return 100; }
+#include <atomic>
+
+extern "C" int mtus_version(void) { return 101; }
+
+static std::atomic<int64_t> g_launches{0};
+extern "C" void mtus_internal_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" int64_t mtus_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" const char* mtus_status_string(int s) {
   if (s == MTUS_OK) return "ok";

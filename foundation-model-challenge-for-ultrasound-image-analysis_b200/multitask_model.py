@@ -103,11 +103,12 @@ def build_model(config, precision=None, zero_copy_features=True):
     return model
 
 
-def build_optimizer(model, config):
-    """AdamW with the reference's grouped learning rates (code/train.py:176-219): encoder x0.1, heads x1.0."""
+def build_optimizer(model, config, fused=None):
+    """AdamW with the reference's grouped learning rates (code/train.py:176-219): encoder x0.1, heads x1.0.
+    ``fused=True`` selects torch's multi-tensor fused CUDA AdamW (same update rule)."""
     lr = float(config.get("training.optimizer.learning_rate", 1e-4))
     wd = float(config.get("training.optimizer.weight_decay", 1e-4))
     enc, head = model.get_trainable_parameters()
     groups = [{"params": enc, "lr": lr * float(config.get("training.optimizer.encoder_lr_multiplier", 0.1))},
               {"params": head, "lr": lr * float(config.get("training.optimizer.head_lr_multiplier", 1.0))}]
-    return torch.optim.AdamW(groups, lr=lr, weight_decay=wd)
+    return torch.optim.AdamW(groups, lr=lr, weight_decay=wd, fused=fused)

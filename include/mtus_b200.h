@@ -37,6 +37,8 @@ extern "C" {
 
 int mtus_version(void);
 const char* mtus_status_string(int status);
+/* number of kernels this library has launched since it was loaded (bench.py: gpu_launches) */
+int64_t mtus_launch_count(void);
 
 /* ---- LayerNorm (timm norm1/norm2/PatchEmbed.norm; SURVEY 8a a3,a4) ------------------------- */
 int mtus_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,

@@ -1,0 +1,147 @@
+"""Host-side mirror of the reference interface (CPU only): factories, attributes, state-dict keys, error
+behaviour, sampler semantics.  No kernel is launched here."""
+import random
+
+import pytest
+import torch
+
+import mtus_b200 as m
+
+
+def _cfg(**kw):
+    tasks = [t for t in m.tasks_27() if t["task_id"] in ("T2A_fetal_abdomen", "T1_fetal_planes", "T4A_fetal_brain",
+                                                         "T5_fetal_femur")]
+    return m.make_config("swin_micro_patch4_window7_test", 64, 2, tasks=tasks, **kw)
+
+
+def test_config_interface():
+    cfg = m.swin_b_27task()
+    assert cfg.get("model.encoder.name") == "swin_b"
+    assert cfg.get("model.encoder.pretrained") is None
+    assert cfg.get("no.such.key", 7) == 7
+    tasks = cfg.get_task_configs()
+    assert len(tasks) == 27
+    kinds = [t["task_name"] for t in tasks]
+    assert (kinds.count("segmentation"), kinds.count("classification"), kinds.count("detection"),
+            kinds.count("Regression")) == (12, 9, 3, 3)
+    assert cfg.get_loss_config("detection")["type"] == "Detection"
+
+
+def test_encoder_factory_contract():
+    """encoders.py:665-691 / :37-160: name map, attributes, channels, strict pretrained handling."""
+    assert m.SWIN_MODEL_MAPPING["swin_b"] == "swin_base_patch4_window7_224"
+    cfg = m.make_config("swin_t", 224, 4)
+    enc = m.build_encoder(cfg)
+    assert enc.is_timm_encoder and enc.output_stride == 32
+    assert enc.out_channels == [3, 96, 192, 384, 768]
+    assert enc.supports_task_id is False and enc.handles_moe is False and enc.use_moe is False
+    assert enc.get_moe_stats() == []
+    assert enc.model.feature_info.channels() == [96, 192, 384, 768]
+    cfg.config["model"]["encoder"]["pretrained"] = "imagenet"
+    with pytest.raises(RuntimeError):
+        m.build_encoder(cfg)
+    cfg.config["model"]["encoder"]["pretrained"] = None
+    cfg.config["model"]["encoder"]["name"] = "vit_b"
+    with pytest.raises(NotImplementedError):
+        m.build_encoder(cfg)
+    with pytest.raises(RuntimeError):
+        m.SwinTransformerEncoder("swin_nonexistent", pretrained=False)
+
+
+def test_decoder_factory_contract():
+    """decoders.py:63-103: keys, aliasing when not separate, out_channels for cat / add."""
+    cfg = _cfg(separate_fpn=False)
+    enc = m.build_encoder(cfg)
+    dec = m.build_decoders(enc, cfg)
+    assert set(dec) == {"fpn_seg", "fpn_det", "fpn_cls", "fpn_reg"}
+    assert dec["fpn_det"] is dec["fpn_seg"] and dec["fpn_cls"] is dec["fpn_seg"] and dec["fpn_reg"] is dec["fpn_seg"]
+    assert dec["fpn_seg"].out_channels == 512
+    dec = m.build_decoders(enc, _cfg(separate_fpn=True, merge_policy="add"))
+    assert dec["fpn_det"] is not dec["fpn_seg"] and dec["fpn_seg"].out_channels == 128
+    with pytest.raises(ValueError):
+        m.FPNDecoder([3, 32, 64, 128, 256], 4, merge_policy="mul")
+
+
+def test_state_dict_keys_match_the_reference_layout():
+    """Checkpoints are bare state_dicts (train.py:695): keys and shapes must equal the oracle's (= timm / smp names)."""
+    from oracle.model import OracleMultiTaskModel
+    cfg = _cfg(dropout=0.0)
+    torch.manual_seed(0)
+    oracle = OracleMultiTaskModel(cfg)
+    model = m.build_model(cfg, precision="fp32")
+    so, sm = oracle.state_dict(), model.state_dict()
+    # buffers that are non-persistent in timm (relative_position_index, attn_mask) must not appear
+    assert set(sm) == set(so), sorted(set(sm) ^ set(so))[:10]
+    for k in so:
+        assert tuple(so[k].shape) == tuple(sm[k].shape), k
+    model.load_state_dict(so, strict=True)
+    flat = model.encoder.model.flat_params()
+    w = dict(model.named_parameters())["encoder.model.layers_1.blocks.0.attn.qkv.weight"]
+    assert w.data_ptr() >= flat.data_ptr() and torch.equal(w, so["encoder.model.layers_1.blocks.0.attn.qkv.weight"])
+    assert "encoder.model.layers_0.downsample.norm.weight" not in sm          # merge sits at the START of stages 1..3
+    assert "encoder.model.layers_1.downsample.reduction.weight" in sm
+    assert "fpn_decoder_seg.p4.skip_conv.weight" in sm and "fpn_decoder_seg.seg_blocks.0.block.2.block.1.bias" in sm
+
+
+def test_routing_and_errors_without_a_gpu():
+    cfg = _cfg()
+    model = m.build_model(cfg, precision="fp32")
+    x = torch.zeros(2, 3, 64, 64)
+    with pytest.raises(ValueError, match="Unknown task_id"):
+        model(x, "nope")                                                     # multitask_model.py:187-188
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(x, "T1_fetal_planes")                                          # the product path never runs on the CPU
+    enc_p, head_p = model.get_trainable_parameters()
+    assert len(enc_p) == len(list(model.encoder.parameters()))
+    ids = {id(p) for p in enc_p} | {id(p) for p in head_p}
+    # decoders that no task routes through (cls / reg when use_fpn_for_* is false) are left out, as in the
+    # reference (multitask_model.py:294-303)
+    unused = {id(p) for d in (model.fpn_decoder_cls, model.fpn_decoder_reg) for p in d.parameters()}
+    assert ids == {id(p) for p in model.parameters()} - unused
+    model.freeze_encoder()
+    assert not any(p.requires_grad for p in model.encoder.parameters())
+    model.unfreeze_encoder()
+    assert all(p.requires_grad for p in model.encoder.parameters())
+    for key in ("use_film",):
+        c2 = _cfg()
+        c2.config["model"][key] = True
+        with pytest.raises(NotImplementedError):
+            m.build_model(c2)
+
+
+def test_sampler_is_task_synchronous_and_partitions_the_global_batch():
+    """MultiTaskUniformSampler (data/dataset.py:140-192) made distributed: same task on every rank each step,
+    disjoint rank slices, rank-identical wrap-around reshuffle."""
+    rng = random.Random(0)
+    task_of = [rng.choice(["a", "b", "c"]) for _ in range(500)]
+    world, bs = 4, 8
+    samplers = [m.DistributedTaskSampler(task_of, bs, rank=r, world_size=world, steps_per_epoch=40, seed=42)
+                for r in range(world)]
+    assert len(samplers[0]) == 40
+    for batches in zip(*[iter(s) for s in samplers]):
+        tasks = {task_of[i] for b in batches for i in b}
+        assert len(tasks) == 1
+        flat = [i for b in batches for i in b]
+        assert all(len(b) == bs for b in batches)
+        # a global batch only repeats an index when a task is exhausted mid-batch
+        assert len(set(flat)) >= len(flat) - bs
+    s1 = m.DistributedTaskSampler(task_of, bs, 0, 1, steps_per_epoch=10, seed=7)
+    s2 = m.DistributedTaskSampler(task_of, bs, 0, 1, steps_per_epoch=10, seed=7)
+    assert list(s1) == list(s2)
+    with pytest.raises(ValueError):
+        m.DistributedTaskSampler(task_of, bs, rank=4, world_size=4)
+
+
+def test_synthetic_batches_have_the_documented_shapes():
+    g = torch.Generator().manual_seed(0)
+    for t in m.tasks_27()[::5]:
+        x, y = m.synthetic_batch(t, 3, 64, generator=g)
+        assert x.shape == (3, 3, 64, 64)
+        if t["task_name"] == "segmentation":
+            assert y.shape == (3, 64, 64) and y.dtype == torch.int64
+        elif t["task_name"] == "classification":
+            assert y.shape == (3,) and int(y.max()) < t["num_classes"]
+        elif t["task_name"] == "detection":
+            assert y.shape == (3, 4) and (y[:, 2] > y[:, 0]).all() and (y[:, 3] > y[:, 1]).all()
+        else:
+            assert y.shape == (3, 2 * t["num_classes"])

@@ -1,0 +1,174 @@
+"""Pins the oracle (CPU only): Swin restatement vs torchvision's independent implementation, FPN restatement vs a
+functional re-derivation, committed golden tensors (generated through the reference's own model code,
+tests/golden/make_golden.py), structural invariants, and -- where /root/reference exists -- the
+reference's MultiTaskModel running on the shims."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN, HAS_REFERENCE
+
+torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+
+
+# ---- Swin vs torchvision -------------------------------------------------------------------------
+@pytest.mark.parametrize("name,img", [("swin_tiny_patch4_window7_224", 224), ("swin_micro_patch4_window7_test", 224)])
+def test_swin_oracle_matches_torchvision(name, img):
+    from torchvision.models.swin_transformer import SwinTransformer
+    from oracle import swin
+    torch.manual_seed(0)
+    o = swin.create_model(name, features_only=True, img_size=img, drop_path_rate=0.0).eval()
+    ed, depths, heads, win = swin.SWIN_VARIANTS[name]
+    tv = SwinTransformer(patch_size=[4, 4], embed_dim=ed, depths=list(depths), num_heads=list(heads),
+                         window_size=[win, win], stochastic_depth_prob=0.0).features.eval()
+    missing = tv.load_state_dict(swin.to_torchvision_state_dict(o.state_dict()), strict=False)
+    assert not [k for k in missing.missing_keys if "relative_position_index" not in k], missing
+    assert not missing.unexpected_keys
+    x = torch.randn(2, 3, img, img, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        fo = o(x)
+        h, ft = x, []
+        for i, layer in enumerate(tv):
+            h = layer(h)
+            if i in (1, 3, 5, 7):
+                ft.append(h)
+    for a, b in zip(fo, ft):
+        assert a.shape == b.shape
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5), float((a - b).abs().max())
+
+
+def test_swin_structural_invariants():
+    from oracle import swin
+    for w in (7, 12):
+        idx = swin.relative_position_index(w, w)
+        n = w * w
+        assert idx.shape == (n, n)
+        assert (idx.diagonal() == ((2 * w - 1) ** 2 - 1) // 2).all()
+        assert idx.min() == 0 and idx.max() == (2 * w - 1) ** 2 - 1
+    blk = swin.SwinTransformerBlock(32, (14, 14), 1, 7, 3)
+    m = blk.get_attn_mask()
+    assert m.shape == (4, 49, 49) and set(m.unique().tolist()) == {-100.0, 0.0}
+    # window clipped + shift disabled when the resolution is not larger than the window (stage 4 at 224)
+    blk = swin.SwinTransformerBlock(32, (7, 7), 1, 7, 3)
+    assert blk.get_attn_mask() is None and tuple(blk.shift_size) == (0, 0)
+    blk = swin.SwinTransformerBlock(32, (4, 4), 1, 7, 3)
+    assert tuple(blk.window_size) == (4, 4)
+
+
+def test_swin_roll_then_pad_order():
+    """timm rolls THEN zero-pads; pad-then-roll (torchvision / HF) gives a different result."""
+    from oracle import swin
+    torch.manual_seed(0)
+    blk = swin.SwinTransformerBlock(32, (9, 9), 1, 7, 3).eval()
+    x = torch.randn(1, 9, 9, 32)
+    y = blk._attn(blk.norm1(x))
+    # manual restatement of the order
+    s = 3
+    h = torch.roll(blk.norm1(x), (-s, -s), (1, 2))
+    h = F.pad(h, (0, 0, 0, 5, 0, 5))
+    wins = swin.window_partition(h, (7, 7)).view(-1, 49, 32)
+    a = blk.attn(wins, mask=blk.get_attn_mask())
+    h = swin.window_reverse(a.view(-1, 7, 7, 32), (7, 7), 14, 14)[:, :9, :9]
+    ref = torch.roll(h, (s, s), (1, 2))
+    assert torch.allclose(y, ref, atol=1e-6)
+
+
+# ---- FPN vs functional re-derivation ---------------------------------------------------------------
+def test_fpn_oracle_matches_functional_rederivation():
+    from oracle import fpn
+    torch.manual_seed(0)
+    dec = fpn.FPNDecoder([3, 32, 64, 128, 256], 4, 64, 32, 0.0, "cat").eval()
+    feats = [torch.randn(2, c, s, s) for c, s in ((32, 16), (64, 8), (128, 4), (256, 2))]
+    sd = dec.state_dict()
+    c2, c3, c4, c5 = feats
+
+    def conv(x, k, pad=0):
+        return F.conv2d(x, sd[k + ".weight"], sd.get(k + ".bias"), padding=pad)
+
+    p5 = conv(c5, "p5")
+    p4 = F.interpolate(p5, scale_factor=2.0, mode="nearest") + conv(c4, "p4.skip_conv")
+    p3 = F.interpolate(p4, scale_factor=2.0, mode="nearest") + conv(c3, "p3.skip_conv")
+    p2 = F.interpolate(p3, scale_factor=2.0, mode="nearest") + conv(c2, "p2.skip_conv")
+    outs = []
+    for i, (p, nup) in enumerate(((p5, 3), (p4, 2), (p3, 1), (p2, 0))):
+        h = p
+        for l in range(max(nup, 1)):
+            pre = f"seg_blocks.{i}.block.{l}.block"
+            h = F.relu(F.group_norm(conv(h, pre + ".0", 1), 32, sd[pre + ".1.weight"], sd[pre + ".1.bias"], 1e-5))
+            if nup > 0:
+                h = F.interpolate(h, scale_factor=2.0, mode="bilinear", align_corners=True)
+        outs.append(h)
+    ref = torch.cat(outs, dim=1)
+    with torch.no_grad():
+        y = dec(feats)
+    assert y.shape == (2, 128, 16, 16) and dec.out_channels == 128
+    assert torch.allclose(y, ref, rtol=1e-5, atol=1e-6)
+    dec_add = fpn.FPNDecoder([3, 32, 64, 128, 256], 4, 64, 32, 0.0, "add").eval()
+    assert dec_add.out_channels == 32
+    with pytest.raises(ValueError):
+        fpn.FPNDecoder([3, 32, 64, 128, 256], 4, 64, 32, 0.0, "mul")
+
+
+# ---- goldens -----------------------------------------------------------------------------------------
+def _golden_case(name):
+    import sys
+    sys.path.insert(0, GOLDEN)
+    import make_golden
+    fx = torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
+    cfg, oracle, x = make_golden.build_case(name, fx["spec"])
+    for k, v in oracle.state_dict().items():
+        if v.is_floating_point():
+            s, a = fx["weight_checksums"][k]
+            assert abs(float(v.double().sum()) - s) <= 1e-9 * max(1.0, a), f"weight RNG drift in {k}"
+    return fx, cfg, oracle, x, make_golden.subsample
+
+
+@pytest.mark.parametrize("name", ["micro_64_4types", "config1_swin_t_224"])
+def test_oracle_reproduces_reference_goldens(name):
+    fx, cfg, oracle, x, sub = _golden_case(name)
+    spec = fx["spec"]
+    with torch.no_grad():
+        feats = oracle.encoder(x)
+    for f, g, (s, a) in zip(feats, fx["features"], fx["feature_sums"]):
+        assert torch.allclose(sub(f, spec["sub"]), g, rtol=1e-5, atol=1e-6)
+        assert abs(float(f.double().sum()) - s) <= 1e-6 * a
+    for tid in spec["tasks"]:
+        oracle.zero_grad(set_to_none=True)
+        out = oracle(x, tid)
+        assert torch.allclose(sub(out.detach(), spec["sub"]), fx["outputs"][tid], rtol=1e-5, atol=1e-6)
+        out.float().square().mean().backward()
+        norms = fx["grad_norms"][tid]
+        got = {k: p.grad for k, p in oracle.named_parameters() if p.grad is not None}
+        assert set(got) == set(norms)
+        for k, g in got.items():
+            assert abs(float(g.double().norm()) - norms[k]) <= 1e-4 * max(norms[k], 1e-12) + 1e-12, k
+        for k, g in fx["grads"][tid].items():
+            assert torch.allclose(got[k], g, rtol=1e-4, atol=1e-9), k
+
+
+# ---- the reference's own classes on the shims (authoring container only) -------------------------------
+@pytest.mark.skipif(not HAS_REFERENCE, reason="/root/reference is not present on this box")
+def test_reference_multitask_model_on_shims_equals_oracle_model():
+    import mtus_b200 as m
+    from oracle import shims
+    from oracle.model import OracleMultiTaskModel
+    models, _, _ = shims.import_reference_models("/root/reference")
+    tasks = [t for t in m.tasks_27() if t["task_id"] in ("T2A_fetal_head", "T2C_fetal_head", "T3A_breast_tumor",
+                                                         "T4A_fetal_femur", "T5_fetal_abdomen")]
+    cfg = m.make_config("swin_micro_patch4_window7_test", 64, 2, tasks=tasks, dropout=0.0, mixed_precision=False)
+    torch.manual_seed(0)
+    oracle = OracleMultiTaskModel(cfg, drop_path_rate=0.0).eval()
+    ref = models.build_model(cfg).eval()
+    ref.load_state_dict(oracle.state_dict(), strict=True)
+    assert list(ref.state_dict().keys()) == list(oracle.state_dict().keys())
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(3))
+    for t in tasks:
+        with torch.no_grad():
+            a, b = ref(x, t["task_id"]), oracle(x, t["task_id"])
+        assert torch.equal(a, b), t["task_id"]
+    with pytest.raises(ValueError):
+        ref(x, "no_such_task")
+    with pytest.raises(ValueError):
+        oracle(x, "no_such_task")

@@ -1,0 +1,111 @@
+"""Data-parallel host logic on CPU: world_size 2, gloo backend (SURVEY section 8e semantics)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class _Toy(nn.Module):
+    """Two heads behind a shared trunk: only the routed head receives a gradient (like the 27 task heads)."""
+
+    def __init__(self):
+        super().__init__()
+        self.trunk = nn.Linear(8, 8)
+        self.heads = nn.ModuleDict({"a": nn.Linear(8, 2), "b": nn.Linear(8, 3)})
+        self.task_id_to_name = {"a": "Regression", "b": "Regression"}
+
+    def forward(self, x, task_id):
+        return self.heads[task_id](torch.tanh(self.trunk(x)))
+
+
+class _FakeCore:
+    """Stands in for SwinCore: a flat gradient buffer reduced stage by stage from the backward hook."""
+
+    def __init__(self, n):
+        self._stage_slices = [(0, 8), (8, 24), (24, 40), (40, 56), (56, n)]
+        self._p = [nn.Parameter(torch.zeros(n))]
+
+    def ordered_params(self):
+        return self._p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import mtus_b200 as m
+    from mtus_b200 import encoders as enc_mod
+    torch.manual_seed(0)
+    model = _Toy()
+    # ---- 1. GradAllReducer.finish: mean of per-rank grads; params without grad stay None --------------------
+    x = torch.randn(4, 8, generator=torch.Generator().manual_seed(10 + rank))
+    y = torch.randn(4, 2, generator=torch.Generator().manual_seed(20 + rank))
+    loss = (model(x, "a") - y).square().mean()
+    loss.backward()
+    local = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    red = m.GradAllReducer(model)
+    with red:
+        pass
+    red.finish()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local)
+    ok = True
+    for k, p in model.named_parameters():
+        if k.startswith("heads.b"):
+            ok &= p.grad is None                     # idle head: never reduced into existence
+            continue
+        mean = sum(g[k] for g in gathered) / world
+        ok &= torch.allclose(p.grad, mean, atol=1e-7)
+    # ---- 2. trainer step keeps replicas identical and skips the idle head in AdamW ---------------------------
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-2, weight_decay=0.1)
+    before_b = model.heads["b"].weight.clone()
+    tr = m.DataParallelTrainer(model, opt, {"Regression": nn.MSELoss()}, gradient_clip=1.0)
+    for step in range(3):
+        xs = torch.randn(4, 8, generator=torch.Generator().manual_seed(100 + 7 * step + rank))
+        ys = torch.randn(4, 2, generator=torch.Generator().manual_seed(200 + 7 * step + rank))
+        tr.step(xs, ys, "a")
+    ok &= torch.equal(model.heads["b"].weight, before_b)      # no grad -> no decay, no moment update
+    flat = torch.cat([p.detach().flatten() for p in model.parameters()])
+    both = [None] * world
+    dist.all_gather_object(both, flat)
+    ok &= all(torch.equal(both[0], b) for b in both)
+    # ---- 3. stage hook: chunks reduced as backward finishes them, averaged once at the end ----------------------
+    n = 64
+    core = _FakeCore(n)
+    holder = nn.Module()
+    holder.encoder = nn.Module()
+    holder.encoder.model = core
+    red2 = m.GradAllReducer.__new__(m.GradAllReducer)
+    red2.model, red2.group, red2.world, red2.overlap = holder, None, world, True
+    red2._handles, red2._enc_params, red2._enc_reduced = [], {id(core._p[0])}, False
+    g = torch.full((n,), float(rank + 1))
+    with red2:
+        hook = enc_mod._STAGE_GRAD_HOOK
+        ok &= hook is not None
+        for lo_stage in (3, 2, 1, 0):
+            s_lo, s_hi = core._stage_slices[lo_stage + 1]
+            if lo_stage == 0:
+                s_lo = core._stage_slices[0][0]
+            hook(g, s_lo, s_hi)
+    ok &= enc_mod._STAGE_GRAD_HOOK is None
+    ok &= torch.allclose(g, torch.full((n,), sum(range(1, world + 1)) / world))
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
