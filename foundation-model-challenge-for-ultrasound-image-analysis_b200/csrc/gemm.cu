@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+static int g_no_tc2 = 0;
 static int g_force_backend = -1;  // MTUS_GEMM env override: "simt" | "tc"
 
 static int forced_backend() {
@@ -12,6 +13,7 @@ static int forced_backend() {
     g_force_backend = 0;
     if (e && !strcmp(e, "simt")) g_force_backend = MTUS_BACKEND_SIMT;
     if (e && !strcmp(e, "tc")) g_force_backend = MTUS_BACKEND_TCGEN05;
+    if (e && !strcmp(e, "tc1")) { g_force_backend = MTUS_BACKEND_TCGEN05; g_no_tc2 = 1; }  // A/B: one-tile-per-CTA engine
   }
   return g_force_backend;
 }
@@ -36,6 +38,7 @@ extern "C" int mtus_gemm(const mtus_gemm_desc* d, void* stream) {
   if (f) backend = f;
   if (backend == MTUS_BACKEND_AUTO) backend = (d->dtype == MTUS_BF16) ? MTUS_BACKEND_TCGEN05 : MTUS_BACKEND_SIMT;
   if (backend == MTUS_BACKEND_TCGEN05) {
+    if (!g_no_tc2 && mtus_gemm_tc2_supported(d)) return mtus_gemm_tc2(d, st);   // persistent TMA-in / TMA-out engine
     if (mtus_gemm_tc_supported(d)) return mtus_gemm_tc(d, ep, st);
     if (d->backend == MTUS_BACKEND_TCGEN05 && !f) return MTUS_ERR_UNSUPPORTED;  // explicit request: fail loudly
   }

@@ -1,0 +1,468 @@
+// Persistent, warp-specialised bf16 GEMM on the 5th-gen tensor cores (the main engine of the bf16 mode).
+//
+//   * one CTA per SM, static round-robin tile scheduler over (split, m-tile, n-tile) work items, n fastest so
+//     the CTAs running at the same time share A row-blocks / the whole weight matrix in L2;
+//   * warp 0 = TMA producer (A and B tiles, SWIZZLE_128B, 4-stage mbarrier ring that runs ahead across tiles),
+//     warp 1 = tcgen05.mma issuer (one elected thread, fp32 accumulators in TMEM, DOUBLE-BUFFERED: the epilogue of
+//     tile i overlaps the main loop of tile i+1), warp 2 = TMEM allocator, warp 3 = TMA loader of the epilogue
+//     operand (residual / saved pre-activation), warps 4-7 = epilogue;
+//   * epilogue: tcgen05.ld -> registers -> bias / GELU / GELU' / drop-path scale / residual -> swizzled shared
+//     memory -> TMA store (bf16) or TMA reduce-add (fp32, split-K weight gradients).  No per-thread global
+//     loads or stores: every byte of HBM traffic of this kernel moves through TMA, fully coalesced.
+//
+// Operand forms are those of gemm_tc.cu (K-major / MN-major / implicit-im2col 4-D boxes) plus the conv3x3 weight
+// gradient (both operands pixel-major 4-D boxes).  Replaces the cuBLAS / cuDNN calls behind timm's nn.Linear
+// layers and smp's FPN convolutions.
+//
+// Roofline: tensor pipe for K >= 512 (tcgen05 floor: 64 cycles per 128x128x16 MMA), HBM for the K = 128 / 256
+// layers of stages 1-2 whose epilogue traffic dominates (algorithmic bytes = A + B + every epilogue tensor once).
+#include "common.cuh"
+#include "internal.h"
+#include "tc_ptx.cuh"
+
+#define T2_BM 128
+#define T2_BK 64
+#define T2_THREADS 256
+#define T2_EPI_BAR 1
+
+struct T2Conv {   // geometry of conv operands (NHWC [B,H,W,C]); pixel tiles of th x tw
+  int H, W, C;
+  int th, tw, tiles_x, tiles_y;        // 128-pixel tile of the M dimension (fwd / dgrad)
+  int kth, ktw, ktiles_x, ktiles_y;    // 64-pixel tile of the K dimension (wgrad)
+};
+
+struct T2Epi {
+  const float* bias;      // [N] or null
+  const float* rowscale;  // per-sample scale or null
+  int rows_per_sample;
+  int act;                // 0 none | 1 GELU (pre-activation -> X out) | 2 multiply by GELU'(X in)
+  int x_mode;             // 0 none | 1 residual in (out += X) | 2 aux in (act 2) | 3 aux out (act 1)
+};
+
+template <int BN, bool OUT_F32>
+struct T2Smem {
+  static constexpr int A_BYTES = T2_BM * T2_BK * 2;
+  static constexpr int B_BYTES = BN * T2_BK * 2;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int SUB_BYTES = 128 * 128;                       // epilogue sub-tile: 128 rows x 128 bytes
+  static constexpr int STAGES = (BN == 256) ? 3 : ((BN == 128) ? 4 : 6);
+  static constexpr int EPI_OFF = STAGES * STAGE;
+  static constexpr int BAR_OFF = EPI_OFF + 4 * SUB_BYTES;           // X[2], D[2]
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+  static constexpr int SUB_COLS = OUT_F32 ? 32 : 64;
+  static constexpr int NSUB = BN / SUB_COLS;
+};
+
+// A_MODE: 0 K-major 2-D | 1 MN-major 2-D | 2 conv im2col (K-major, 128-pixel row tiles) | 3 conv pixel-major (wgrad)
+// B_MODE: 0 K-major 2-D | 1 MN-major 2-D | 2 conv pixel-major with tap shift (wgrad)
+template <int BN, int A_MODE, int B_MODE, bool OUT_F32>
+__global__ void __launch_bounds__(T2_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, int M, int N, int K,
+                int kb_per_split, int total_kb, int m_tiles, int n_tiles, int n_work, T2Conv cv, T2Epi ep) {
+  using S = T2Smem<BN, OUT_F32>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+  // barrier map: full[STAGES] empty[STAGES] tfull[2] tempty[2] xfull[2] xempty[2]
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * S::STAGES, bar_tfull = bar_empty + 8 * S::STAGES,
+                 bar_tempty = bar_tfull + 16, bar_xfull = bar_tempty + 16, bar_xempty = bar_xfull + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 8);
+  const uint32_t smem_x = smem_base + S::EPI_OFF, smem_d = smem_x + 2 * S::SUB_BYTES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool x_in = (ep.x_mode == 1 || ep.x_mode == 2);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
+    if (ep.x_mode) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S::STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4);
+      mbar_init(bar_xfull + 8 * b, 1); mbar_init(bar_xempty + 8 * b, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int mn_tiles = m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    // ================================ TMA producer: A / B tiles ================================
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < n_work; t += gridDim.x) {
+      const int z = t / mn_tiles, r = t - z * mn_tiles, m_blk = r / n_tiles, n_blk = r - m_blk * n_tiles;
+      const int kb0 = z * kb_per_split, nkb = min(kb_per_split, total_kb - kb0);
+      int cb = 0, cy0 = 0, cx0 = 0;
+      if (A_MODE == 2) {
+        int q = m_blk; const int tx = q % cv.tiles_x; q /= cv.tiles_x; const int ty = q % cv.tiles_y; cb = q / cv.tiles_y;
+        cy0 = ty * cv.th; cx0 = tx * cv.tw;
+      }
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const uint32_t s = it % S::STAGES, ph = (it / S::STAGES) & 1;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        const uint32_t full = bar_full + 8 * s;
+        const uint32_t sa = smem_base + s * S::STAGE, sb = sa + S::A_BYTES;
+        mbar_expect_tx(full, S::STAGE);
+        const int kb = kb0 + i, k0 = kb * T2_BK;
+        int pb = 0, py0 = 0, px0 = 0;                    // pixel patch of this k-block (conv wgrad)
+        if (A_MODE == 3 || B_MODE == 2) {
+          int q = kb; const int tx = q % cv.ktiles_x; q /= cv.ktiles_x; const int ty = q % cv.ktiles_y; pb = q / cv.ktiles_y;
+          py0 = ty * cv.kth; px0 = tx * cv.ktw;
+        }
+        if (A_MODE == 0) {
+          tma_load_2d(sa, &tmA, k0, m_blk * T2_BM, full);
+        } else if (A_MODE == 1) {
+          tma_load_2d(sa, &tmA, m_blk * T2_BM, k0, full);
+          tma_load_2d(sa + 8192, &tmA, m_blk * T2_BM + 64, k0, full);
+        } else if (A_MODE == 2) {   // K index = tap*C + c, 64 channels of one tap per k-block (C % 64 == 0)
+          const int tap = k0 / cv.C, c0 = k0 - tap * cv.C;
+          tma_load_4d(sa, &tmA, c0, cx0 + tap % 3 - 1, cy0 + tap / 3 - 1, cb, full);
+        } else {                    // dy [pixels, Cout]: 64 pixels x 2 chunks of 64 output channels
+          tma_load_4d(sa, &tmA, m_blk * T2_BM, px0, py0, pb, full);
+          tma_load_4d(sa + 8192, &tmA, m_blk * T2_BM + 64, px0, py0, pb, full);
+        }
+        if (B_MODE == 0) {
+          tma_load_2d(sb, &tmB, k0, n_blk * BN, full);
+        } else if (B_MODE == 1) {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, n_blk * BN + j * 64, k0, full);
+        } else {                    // x [pixels, Cin] shifted by the tap of this n-tile: N index = tap*C + c
+          const int n0 = n_blk * BN;
+          const int tap = n0 / cv.C, c0 = n0 - tap * cv.C;
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_4d(sb + j * 8192, &tmB, c0 + j * 64, px0 + tap % 3 - 1, py0 + tap / 3 - 1, pb, full);
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ================================ MMA issuer ================================
+    constexpr uint32_t idesc = umma_idesc(T2_BM, BN, (A_MODE == 1 || A_MODE == 3) ? 1 : 0, B_MODE != 0 ? 1 : 0);
+    uint32_t it = 0, tc = 0;
+    for (int t = blockIdx.x; t < n_work; t += gridDim.x, ++tc) {
+      const int z = t / mn_tiles;
+      const int kb0 = z * kb_per_split, nkb = min(kb_per_split, total_kb - kb0);
+      const uint32_t ab = tc & 1;
+      mbar_wait(bar_tempty + 8 * ab, ((tc >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ab * BN;
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const uint32_t s = it % S::STAGES, ph = (it / S::STAGES) & 1;
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * S::STAGE, sb = sa + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < T2_BK / 16; ++k) {
+          const uint64_t ad = (A_MODE == 1 || A_MODE == 3) ? umma_smem_desc(sa + k * 2048, 8192, 1024) : umma_smem_desc(sa + k * 32, 0, 1024);
+          const uint64_t bd = (B_MODE != 0) ? umma_smem_desc(sb + k * 2048, 8192, 1024) : umma_smem_desc(sb + k * 32, 0, 1024);
+          umma_bf16(tacc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_empty + 8 * s);
+      }
+      umma_commit(bar_tfull + 8 * ab);
+    }
+  } else if (warp == 3 && lane == 0) {
+    // ================================ TMA loader of the epilogue operand ================================
+    if (x_in) {
+      uint32_t e = 0;
+      for (int t = blockIdx.x; t < n_work; t += gridDim.x) {
+        const int z = t / mn_tiles, r = t - z * mn_tiles, m_blk = r / n_tiles, n_blk = r - m_blk * n_tiles;
+        for (int sub = 0; sub < S::NSUB; ++sub, ++e) {
+          const uint32_t b = e & 1;
+          mbar_wait(bar_xempty + 8 * b, ((e >> 1) & 1) ^ 1);
+          mbar_expect_tx(bar_xfull + 8 * b, S::SUB_BYTES);
+          tma_load_2d(smem_x + b * S::SUB_BYTES, &tmX, n_blk * BN + sub * S::SUB_COLS, m_blk * T2_BM, bar_xfull + 8 * b);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ================================
+    const int q = warp - 4, row = q * 32 + lane, etid = threadIdx.x - 128;
+    uint32_t tc = 0, e = 0;
+    for (int t = blockIdx.x; t < n_work; t += gridDim.x, ++tc) {
+      const int z = t / mn_tiles, r = t - z * mn_tiles, m_blk = r / n_tiles, n_blk = r - m_blk * n_tiles;
+      const uint32_t ab = tc & 1;
+      mbar_wait(bar_tfull + 8 * ab, (tc >> 1) & 1);
+      tc_fence_after();
+      float rs = 1.0f;
+      if (ep.rowscale) {
+        const int64_t m = (int64_t)m_blk * T2_BM + row;
+        if (m < M) rs = __ldg(ep.rowscale + m / ep.rows_per_sample);
+      }
+#pragma unroll 1
+      for (int sub = 0; sub < S::NSUB; ++sub, ++e) {
+        const uint32_t b = e & 1;
+        const uint32_t sx = smem_x + b * S::SUB_BYTES + row * 128, sd = smem_d + b * S::SUB_BYTES + row * 128;
+        const int n_sub = n_blk * BN + sub * S::SUB_COLS;
+        // the TMA store that read D[b] / X[b] two sub-tiles ago must have finished reading shared memory
+        if (etid == 0) bulk_wait_read<1>();
+        named_bar_sync(T2_EPI_BAR, 128);
+        if (x_in) mbar_wait(bar_xfull + 8 * b, (e >> 1) & 1);
+        if (OUT_F32) {
+          uint32_t v[32];
+          tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + ab * BN + sub * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {   // 8 chunks of 16 B (4 floats), 128B swizzle: chunk ^= row & 7
+            const uint32_t dst = sd + ((c ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[4 * c]), "r"(v[4 * c + 1]), "r"(v[4 * c + 2]), "r"(v[4 * c + 3]) : "memory");
+          }
+        } else {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + ab * BN + sub * 64 + half * 32, v);
+            uint32_t xr[16];
+            if (x_in) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint32_t src = sx + (((half * 4 + c) ^ (row & 7)) << 4);
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xr[4 * c]), "=r"(xr[4 * c + 1]), "=r"(xr[4 * c + 2]), "=r"(xr[4 * c + 3]) : "r"(src));
+              }
+            }
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (ep.bias) {
+              const float* bp = ep.bias + n_sub + half * 32;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (n_sub + half * 32 + j < N) f[j] += __ldg(bp + j);
+            }
+            uint32_t pre[16];
+            if (ep.act == 1) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                pre[j] = *reinterpret_cast<uint32_t*>(&h2);
+                f[2 * j] = gelu_f(f[2 * j]); f[2 * j + 1] = gelu_f(f[2 * j + 1]);
+              }
+            } else if (ep.act == 2) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xr[j]));
+                f[2 * j] *= gelu_grad_f(h.x); f[2 * j + 1] *= gelu_grad_f(h.y);
+              }
+            }
+            if (ep.rowscale) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] *= rs;
+            }
+            if (ep.x_mode == 1) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xr[j]));
+                f[2 * j] += h.x; f[2 * j + 1] += h.y;
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * c + 2 * j], f[8 * c + 2 * j + 1]);
+                o[j] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              const uint32_t off = (((half * 4 + c) ^ (row & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sd + off), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+              if (ep.act == 1)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sx + off), "r"(pre[4 * c]), "r"(pre[4 * c + 1]), "r"(pre[4 * c + 2]), "r"(pre[4 * c + 3]) : "memory");
+            }
+          }
+        }
+        if (sub == S::NSUB - 1) {       // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * ab);
+        }
+        if (x_in) { __syncwarp(); if (lane == 0) mbar_arrive(bar_xempty + 8 * b); }
+        fence_proxy_async();
+        named_bar_sync(T2_EPI_BAR, 128);
+        if (etid == 0) {
+          if (A_MODE == 2) {
+            int qq = m_blk; const int tx = qq % cv.tiles_x; qq /= cv.tiles_x; const int ty = qq % cv.tiles_y; const int cb = qq / cv.tiles_y;
+            tma_store_4d(&tmD, smem_d + b * S::SUB_BYTES, n_sub, tx * cv.tw, ty * cv.th, cb);
+          } else if (OUT_F32) {
+            tma_reduce_add_2d(&tmD, smem_d + b * S::SUB_BYTES, n_sub, m_blk * T2_BM);
+          } else {
+            tma_store_2d(&tmD, smem_d + b * S::SUB_BYTES, n_sub, m_blk * T2_BM);
+            if (ep.act == 1) tma_store_2d(&tmX, smem_x + b * S::SUB_BYTES, n_sub, m_blk * T2_BM);
+          }
+          bulk_commit();
+        }
+      }
+    }
+    if (etid == 0) bulk_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------
+static int make_map_2d_f32(CUtensorMap* m, const void* p, int64_t inner, int64_t outer, int64_t ld_elems, int box_inner,
+                           int box_outer) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return MTUS_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) || (ld_elems % 4)) return MTUS_ERR_BAD_ARG;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(p), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MTUS_OK : MTUS_ERR_DRIVER;
+}
+
+static int g_sm_count = 0;
+static int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    g_sm_count = n > 0 ? n : 148;
+  }
+  return g_sm_count;
+}
+
+template <int BN, int A_MODE, int B_MODE, bool OUT_F32>
+static int t2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tx, const CUtensorMap& td, int M,
+                     int N, int K, int kbps, int total_kb, int m_tiles, int n_tiles, int n_work, const T2Conv& cv,
+                     const T2Epi& ep, cudaStream_t st) {
+  auto kern = gemm_tc2_kernel<BN, A_MODE, B_MODE, OUT_F32>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Smem<BN, OUT_F32>::TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int grid = n_work < sm_count() ? n_work : sm_count();
+  kern<<<grid, T2_THREADS, T2Smem<BN, OUT_F32>::TOTAL, st>>>(ta, tb, tx, td, M, N, K, kbps, total_kb, m_tiles, n_tiles,
+                                                             n_work, cv, ep);
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}
+
+bool mtus_gemm_tc2_supported(const mtus_gemm_desc* d) {
+  if (d->dtype != MTUS_BF16) return false;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al16(d->a) || !al16(d->b) || !al16(d->out)) return false;
+  if (d->M <= 0 || d->N <= 0 || d->K <= 0) return false;
+  const bool wgrad_conv = d->b_conv && d->a_mn_major && d->b_mn_major;
+  if (d->a_conv && d->b_conv) return false;
+  if (d->b_conv && !wgrad_conv) return false;
+  if (d->a_conv && (d->a_mn_major || d->b_mn_major)) return false;
+  if ((d->a_conv || d->b_conv) && (d->conv_c % 64)) return false;
+  if (d->a_mn_major && !d->b_mn_major) return false;
+  if (!d->a_conv && !wgrad_conv && (d->lda % 8)) return false;
+  if (!d->b_conv && (d->ldb % 8)) return false;
+  if (d->out_f32) {
+    // fp32 output = accumulate (TMA reduce-add) with no epilogue ops: the weight-gradient form
+    if (!d->atomic || d->bias || d->act || d->res || d->rowscale) return false;
+    if (d->ld_out % 4) return false;
+    if (wgrad_conv && (d->lda % 64 || d->conv_c % 128 || d->M % 64)) return false;
+  } else {
+    if (d->atomic) return false;
+    if (d->ld_out % 8) return false;
+    if (d->res && (d->res_mode != 1 || d->ld_res % 8 || !al16(d->res))) return false;
+    if (d->act && (!d->aux || d->ld_aux % 8 || !al16(d->aux))) return false;
+    if (d->act == 2 && d->res) return false;        // one epilogue operand tile
+    if (d->act == 1 && d->res) return false;
+    if (d->a_conv && (d->bias || d->act || d->res || d->rowscale)) return false;
+    if (d->a_conv && (d->N % 64 || d->ld_out != d->N)) return false;
+  }
+  return true;
+}
+
+int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
+  if (!mtus_gemm_tc2_supported(d)) return MTUS_ERR_UNSUPPORTED;
+  const int M = d->M, N = d->N, K = d->K;
+  const bool wgrad_conv = d->b_conv != 0;
+  CUtensorMap ta, tb, tx, td;
+  T2Conv cv{};
+  int rc;
+  const int BN = (N > 64) ? 128 : 64;
+  int m_tiles = ceil_div(M, T2_BM), n_tiles = ceil_div(N, BN), total_kb = ceil_div(K, T2_BK);
+  if (d->a_conv || d->b_conv) {
+    cv.H = d->conv_h; cv.W = d->conv_w; cv.C = d->conv_c;
+    cv.tw = (cv.W >= 16) ? 16 : 8; cv.th = 128 / cv.tw;
+    cv.tiles_x = ceil_div(cv.W, cv.tw); cv.tiles_y = ceil_div(cv.H, cv.th);
+    cv.ktw = 8; cv.kth = 8;
+    cv.ktiles_x = ceil_div(cv.W, 8); cv.ktiles_y = ceil_div(cv.H, 8);
+  }
+  int am, bm;
+  if (d->a_conv) {
+    const int B = M / (cv.H * cv.W);
+    rc = make_map_conv(&ta, d->a, B, cv.H, cv.W, cv.C, cv.tw, cv.th);
+    m_tiles = B * cv.tiles_x * cv.tiles_y;
+    am = 2;
+  } else if (wgrad_conv) {           // A = dy [B,H,W,Cout] pixel-major, Cout = M = lda
+    const int B = K / (cv.H * cv.W);
+    rc = make_map_conv(&ta, d->a, B, cv.H, cv.W, (int)d->lda, cv.ktw, cv.kth);
+    total_kb = B * cv.ktiles_x * cv.ktiles_y;
+    am = 3;
+  } else if (!d->a_mn_major) { rc = make_map_2d(&ta, d->a, K, M, d->lda, T2_BK, T2_BM); am = 0; }
+  else { rc = make_map_2d(&ta, d->a, M, K, d->lda, 64, T2_BK); am = 1; }
+  if (rc) return rc;
+  if (wgrad_conv) {
+    const int B = K / (cv.H * cv.W);
+    rc = make_map_conv(&tb, d->b, B, cv.H, cv.W, cv.C, cv.ktw, cv.kth);
+    bm = 2;
+  } else if (!d->b_mn_major) { rc = make_map_2d(&tb, d->b, K, N, d->ldb, T2_BK, BN); bm = 0; }
+  else { rc = make_map_2d(&tb, d->b, N, K, d->ldb, 64, T2_BK); bm = 1; }
+  if (rc) return rc;
+  // D / X maps
+  T2Epi ep{};
+  ep.bias = d->bias; ep.rowscale = d->rowscale; ep.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1;
+  ep.act = d->act;
+  ep.x_mode = d->res ? 1 : (d->act == 2 ? 2 : (d->act == 1 ? 3 : 0));
+  if (d->out_f32) rc = make_map_2d_f32(&td, d->out, N, M, d->ld_out, 32, T2_BM);
+  else if (d->a_conv) rc = make_map_conv(&td, d->out, M / (cv.H * cv.W), cv.H, cv.W, N, cv.tw, cv.th);
+  else rc = make_map_2d(&td, d->out, N, M, d->ld_out, 64, T2_BM);
+  if (rc) return rc;
+  if (ep.x_mode == 1) rc = make_map_2d(&tx, d->res, N, M, d->ld_res, 64, T2_BM);
+  else if (ep.x_mode) rc = make_map_2d(&tx, d->aux, N, M, d->ld_aux, 64, T2_BM);
+  else tx = td;
+  if (rc) return rc;
+
+  int splits = d->split_k > 0 ? d->split_k : 1;
+  if (!d->out_f32) splits = 1;
+  if (splits > total_kb) splits = total_kb;
+  const int kbps = ceil_div(total_kb, splits);
+  splits = ceil_div(total_kb, kbps);
+  const int64_t n_work64 = (int64_t)splits * m_tiles * n_tiles;
+  if (n_work64 > (1ll << 30)) return MTUS_ERR_UNSUPPORTED;
+  const int n_work = (int)n_work64;
+
+#define T2_GO(BN_, AM_, BM_, F32_) return t2_launch<BN_, AM_, BM_, F32_>(ta, tb, tx, td, M, N, K, kbps, total_kb, m_tiles, n_tiles, n_work, cv, ep, st)
+  if (d->out_f32) {
+    if (BN == 128) {
+      if (am == 1 && bm == 1) T2_GO(128, 1, 1, true);
+      if (am == 3 && bm == 2) T2_GO(128, 3, 2, true);
+    } else {
+      if (am == 1 && bm == 1) T2_GO(64, 1, 1, true);
+    }
+  } else if (BN == 128) {
+    if (am == 0 && bm == 0) T2_GO(128, 0, 0, false);
+    if (am == 0 && bm == 1) T2_GO(128, 0, 1, false);
+    if (am == 2 && bm == 0) T2_GO(128, 2, 0, false);
+  } else {
+    if (am == 0 && bm == 0) T2_GO(64, 0, 0, false);
+    if (am == 0 && bm == 1) T2_GO(64, 0, 1, false);
+    if (am == 2 && bm == 0) T2_GO(64, 2, 0, false);
+  }
+#undef T2_GO
+  return MTUS_ERR_UNSUPPORTED;
+}

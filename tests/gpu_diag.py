@@ -77,7 +77,8 @@ def g_elementwise():
 
 
 def _lin_cases():
-    return [(256, 128, 128), (1000, 384, 128), (300, 96, 288), (777, 512, 2048), (1568, 2048, 512), (128, 64, 64), (100, 256, 1024)]
+    return [(256, 128, 128), (1000, 384, 128), (300, 96, 288), (777, 512, 2048), (1568, 2048, 512), (128, 64, 64), (100, 256, 1024),
+            (20000, 384, 128), (6272, 512, 1536), (3000, 48, 64)]   # > 148 tiles: several tiles per persistent CTA
 
 
 def _gemm_group(backend, dts):
@@ -116,7 +117,7 @@ def _gemm_group(backend, dts):
             dw, db = ops.linear_wgrad(dy, x, backend=backend)
             ok &= report(f"linear_wgrad dw", dw, dy.float().t() @ x.float(), max(tol, 1e-4))
             ok &= report(f"linear_wgrad db", db, dy.float().sum(0), max(tol, 1e-4))
-        for (B, H, W, Cin, Cout) in ((2, 7, 7, 64, 128), (2, 14, 14, 256, 128), (1, 28, 28, 128, 128), (2, 56, 56, 64, 64)):
+        for (B, H, W, Cin, Cout) in ((2, 7, 7, 64, 128), (2, 14, 14, 256, 128), (1, 28, 28, 128, 128), (2, 56, 56, 64, 64), (3, 56, 56, 128, 128)):
             x = (torch.randn(B, H, W, Cin, device=dev) * 0.5).to(dt)
             w = torch.randn(Cout, Cin, 3, 3, device=dev) * 0.05
             wf, wd = ops.conv3x3_repack(w, dt)
@@ -130,7 +131,7 @@ def _gemm_group(backend, dts):
             yr.backward(dy.float().permute(0, 3, 1, 2))
             dx = ops.conv3x3_dgrad(dy, wd, backend=backend)
             ok &= report(f"conv3x3_dgrad", dx, xr.grad.permute(0, 2, 3, 1), tol)
-            dw = ops.conv3x3_wgrad(dy, x, backend=(0 if backend == 2 else backend))  # tcgen05 conv wgrad: not yet -> auto
+            dw = ops.conv3x3_wgrad(dy, x, backend=(0 if (backend == 2 and Cin % 128) else backend))  # tcgen05 conv wgrad needs Cin % 128 == 0
             ok &= report(f"conv3x3_wgrad", dw, wr.grad, max(tol, 1e-4))
     return ok
 
