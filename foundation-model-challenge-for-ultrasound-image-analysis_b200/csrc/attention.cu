@@ -13,6 +13,8 @@
 // Stand-alone this op is HBM-bound (24.5 FLOP/B at N=49): algorithmic bytes per token =
 // 4*C*s forward (q,k,v in, o out), 8*C*s backward (q,k,v,o,do in; dq,dk,dv out).
 #include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 #define ATT_D 32          // head_dim is 32 for every Swin variant
 #define ATT_LD 33
@@ -198,6 +200,19 @@ __global__ void __launch_bounds__(ATT_THREADS) window_attn_bwd_kernel(const T* _
   for (int t = threadIdx.x; t < ntab; t += ATT_THREADS) atomicAdd(dtable + t * g.heads + h, s_bins[t]);
 }
 
+// tensor-core engine (attention_mma.cu): bf16, windows of up to 64 tokens.  MTUS_ATTN=simt forces the general engine.
+bool mtus_window_attn_mma_supported(int wh, int ww, int dtype);
+int mtus_window_attn_mma_fwd(const void* qkv, const float* rel_table, const float* qkv_bias, void* out, int B, int H, int W, int C,
+                             int heads, int win_h, int win_w, int shift_h, int shift_w, cudaStream_t st);
+int mtus_window_attn_mma_bwd(const void* dout, const void* qkv, const void* out, const float* rel_table, const float* qkv_bias,
+                             void* dqkv, float* drel_table, float* dqkv_bias, int B, int H, int W, int C, int heads, int win_h,
+                             int win_w, int shift_h, int shift_w, cudaStream_t st);
+static bool att_use_mma(int wh, int ww, int dtype) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("MTUS_ATTN"); forced = (e && !strcmp(e, "simt")) ? 1 : 0; }
+  return !forced && mtus_window_attn_mma_supported(wh, ww, dtype);
+}
+
 static int att_geom(AttGeom& g, int B, int H, int W, int C, int heads, int wh, int ww, int sh, int sw) {
   if (B < 0 || H <= 0 || W <= 0 || heads <= 0 || C != heads * ATT_D) return MTUS_ERR_BAD_ARG;
   if (wh <= 0 || ww <= 0 || wh > 16 || ww > 16 || sh < 0 || sw < 0 || sh >= wh || sw >= ww) return MTUS_ERR_BAD_ARG;
@@ -212,6 +227,8 @@ extern "C" int mtus_window_attn_fwd(const void* qkv, const float* rel_table, con
                                     int H, int W, int C, int heads, int win_h, int win_w, int shift_h, int shift_w,
                                     int dtype, void* stream) {
   MTUS_CHECK_ARG(qkv && rel_table && out);
+  if (att_use_mma(win_h, win_w, dtype))
+    return mtus_window_attn_mma_fwd(qkv, rel_table, qkv_bias, out, B, H, W, C, heads, win_h, win_w, shift_h, shift_w, (cudaStream_t)stream);
   AttGeom g;
   int rc = att_geom(g, B, H, W, C, heads, win_h, win_w, shift_h, shift_w);
   if (rc) return rc;
@@ -240,6 +257,9 @@ extern "C" int mtus_window_attn_bwd(const void* dout, const void* qkv, const voi
                                     int H, int W, int C, int heads, int win_h, int win_w, int shift_h, int shift_w,
                                     int dtype, void* stream) {
   MTUS_CHECK_ARG(dout && qkv && out && rel_table && dqkv && drel_table);
+  if (att_use_mma(win_h, win_w, dtype))
+    return mtus_window_attn_mma_bwd(dout, qkv, out, rel_table, qkv_bias, dqkv, drel_table, dqkv_bias, B, H, W, C, heads, win_h, win_w,
+                                    shift_h, shift_w, (cudaStream_t)stream);
   AttGeom g;
   int rc = att_geom(g, B, H, W, C, heads, win_h, win_w, shift_h, shift_w);
   if (rc) return rc;
