@@ -31,7 +31,7 @@ class GemmDesc(C.Structure):
         ("res", vp), ("ld_res", i64), ("res_mode", i32), ("res_h", i32), ("res_w", i32),
         ("rowscale", vp), ("rows_per_sample", i32),
         ("out", vp), ("ld_out", i64), ("out_f32", i32), ("atomic", i32),
-        ("split_k", i32), ("dtype", i32), ("backend", i32),
+        ("split_k", i32), ("dtype", i32), ("backend", i32), ("res_f32", i32),
     ]
 
 
@@ -72,8 +72,8 @@ SIGNATURES = {
     "mtus_nhwc_to_nchw": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_nchw_to_nhwc": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_patch_embed_im2col": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
-    "mtus_window_attn_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
-    "mtus_window_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "mtus_window_attn_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "mtus_window_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mtus_upsample_add_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_upsample_add_bwd": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "mtus_groupnorm_stats": (i32, [vp, vp, vp, i32, i32, i32, i32, f32, i32, vp]),

@@ -202,11 +202,11 @@ __global__ void __launch_bounds__(ATT_THREADS) window_attn_bwd_kernel(const T* _
 
 // tensor-core engine (attention_mma.cu): bf16, windows of up to 64 tokens.  MTUS_ATTN=simt forces the general engine.
 bool mtus_window_attn_mma_supported(int wh, int ww, int dtype);
-int mtus_window_attn_mma_fwd(const void* qkv, const float* rel_table, const float* qkv_bias, void* out, int B, int H, int W, int C,
-                             int heads, int win_h, int win_w, int shift_h, int shift_w, cudaStream_t st);
-int mtus_window_attn_mma_bwd(const void* dout, const void* qkv, const void* out, const float* rel_table, const float* qkv_bias,
-                             void* dqkv, float* drel_table, float* dqkv_bias, int B, int H, int W, int C, int heads, int win_h,
-                             int win_w, int shift_h, int shift_w, cudaStream_t st);
+int mtus_window_attn_mma_fwd(const void* qkv, const float* rel_table, const float* qkv_bias, void* out, float* lse, int B, int H, int W,
+                             int C, int heads, int win_h, int win_w, int shift_h, int shift_w, cudaStream_t st);
+int mtus_window_attn_mma_bwd(const void* dout, const void* qkv, const void* out, const float* lse, const float* rel_table,
+                             const float* qkv_bias, void* dqkv, float* drel_table, float* dqkv_bias, float* dqkv_colsum, int B, int H,
+                             int W, int C, int heads, int win_h, int win_w, int shift_h, int shift_w, cudaStream_t st);
 static bool att_use_mma(int wh, int ww, int dtype) {
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("MTUS_ATTN"); forced = (e && !strcmp(e, "simt")) ? 1 : 0; }
@@ -223,12 +223,12 @@ static int att_geom(AttGeom& g, int B, int H, int W, int C, int heads, int wh, i
   return MTUS_OK;
 }
 
-extern "C" int mtus_window_attn_fwd(const void* qkv, const float* rel_table, const float* qkv_bias, void* out, int B,
-                                    int H, int W, int C, int heads, int win_h, int win_w, int shift_h, int shift_w,
+extern "C" int mtus_window_attn_fwd(const void* qkv, const float* rel_table, const float* qkv_bias, void* out, float* lse,
+                                    int B, int H, int W, int C, int heads, int win_h, int win_w, int shift_h, int shift_w,
                                     int dtype, void* stream) {
   MTUS_CHECK_ARG(qkv && rel_table && out);
   if (att_use_mma(win_h, win_w, dtype))
-    return mtus_window_attn_mma_fwd(qkv, rel_table, qkv_bias, out, B, H, W, C, heads, win_h, win_w, shift_h, shift_w, (cudaStream_t)stream);
+    return mtus_window_attn_mma_fwd(qkv, rel_table, qkv_bias, out, lse, B, H, W, C, heads, win_h, win_w, shift_h, shift_w, (cudaStream_t)stream);
   AttGeom g;
   int rc = att_geom(g, B, H, W, C, heads, win_h, win_w, shift_h, shift_w);
   if (rc) return rc;
@@ -252,14 +252,14 @@ extern "C" int mtus_window_attn_fwd(const void* qkv, const float* rel_table, con
   return MTUS_OK;
 }
 
-extern "C" int mtus_window_attn_bwd(const void* dout, const void* qkv, const void* out, const float* rel_table,
-                                    const float* qkv_bias, void* dqkv, float* drel_table, float* dqkv_bias, int B,
-                                    int H, int W, int C, int heads, int win_h, int win_w, int shift_h, int shift_w,
-                                    int dtype, void* stream) {
+extern "C" int mtus_window_attn_bwd(const void* dout, const void* qkv, const void* out, const float* lse,
+                                    const float* rel_table, const float* qkv_bias, void* dqkv, float* drel_table,
+                                    float* dqkv_bias, float* dqkv_colsum, int B, int H, int W, int C, int heads, int win_h,
+                                    int win_w, int shift_h, int shift_w, int dtype, void* stream) {
   MTUS_CHECK_ARG(dout && qkv && out && rel_table && dqkv && drel_table);
   if (att_use_mma(win_h, win_w, dtype))
-    return mtus_window_attn_mma_bwd(dout, qkv, out, rel_table, qkv_bias, dqkv, drel_table, dqkv_bias, B, H, W, C, heads, win_h, win_w,
-                                    shift_h, shift_w, (cudaStream_t)stream);
+    return mtus_window_attn_mma_bwd(dout, qkv, out, lse, rel_table, qkv_bias, dqkv, drel_table, dqkv_bias, dqkv_colsum, B, H, W, C, heads,
+                                    win_h, win_w, shift_h, shift_w, (cudaStream_t)stream);
   AttGeom g;
   int rc = att_geom(g, B, H, W, C, heads, win_h, win_w, shift_h, shift_w);
   if (rc) return rc;
@@ -280,5 +280,6 @@ extern "C" int mtus_window_attn_bwd(const void* dout, const void* qkv, const voi
     window_attn_bwd_kernel<bf16><<<(unsigned)blocks, ATT_THREADS, smem, st>>>((const bf16*)dout, (const bf16*)qkv, (const bf16*)out, rel_table, qkv_bias, (bf16*)dqkv, drel_table, dqkv_bias, g);
   } else return MTUS_ERR_UNSUPPORTED;
   MTUS_LAUNCH_STATUS();
+  if (dqkv_colsum) return mtus_colsum(dqkv, dqkv_colsum, (int64_t)B * H * W, 3 * C, dtype, stream);   // general engine: separate pass
   return MTUS_OK;
 }

@@ -91,6 +91,33 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return cdf + x * pdf;
 }
 
+// Fast exact-GELU for the tensor-core epilogues: erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below
+// bf16 resolution) on ex2 / rcp; erf(x/sqrt2) and the Gaussian pdf of GELU' share the same exponential.
+__device__ __forceinline__ float erf_as_core(float x, float& e_out) {   // returns erf(|x|/sqrt2); e_out = exp(-x^2/2)
+  const float au = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, au, 1.0f)));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  float e;                                                  // exp(-x^2/2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-0.72134752044448170f * x * x));
+  e_out = e;
+  return fmaf(-p, e, 1.0f);
+}
+__device__ __forceinline__ float gelu_fast_f(float x) {
+  float e;
+  const float er = copysignf(erf_as_core(x, e), x);
+  return 0.5f * x * (1.0f + er);
+}
+__device__ __forceinline__ float gelu_grad_fast_f(float x) {
+  float e;
+  const float er = copysignf(erf_as_core(x, e), x);
+  return fmaf(x * 0.3989422804014327f, e, 0.5f * (1.0f + er));
+}
+
 // ---- fused GEMM epilogue (shared by the SIMT fp32 GEMM and the tcgen05 bf16 GEMM) -----------
 struct EpiParams {
   const float* bias;       // [N] fp32 or null

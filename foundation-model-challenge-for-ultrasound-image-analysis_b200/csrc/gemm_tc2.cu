@@ -19,10 +19,12 @@
 #include "common.cuh"
 #include "internal.h"
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 
 #define T2_BM 128
 #define T2_BK 64
-#define T2_THREADS 256
+#define T2_THREADS 384
+#define T2_EPI_THREADS 256
 #define T2_EPI_BAR 1
 
 struct T2Conv {   // geometry of conv operands (NHWC [B,H,W,C]); pixel tiles of th x tw
@@ -37,6 +39,7 @@ struct T2Epi {
   int rows_per_sample;
   int act;                // 0 none | 1 GELU (pre-activation -> X out) | 2 multiply by GELU'(X in)
   int x_mode;             // 0 none | 1 residual in (out += X) | 2 aux in (act 2) | 3 aux out (act 1)
+  int reduce;             // fp32 output: 1 = TMA reduce-add into the destination (split-K weight gradients), 0 = store
 };
 
 template <int BN, bool OUT_F32>
@@ -83,8 +86,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S::STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4);
-      mbar_init(bar_xfull + 8 * b, 1); mbar_init(bar_xempty + 8 * b, 4);
+      mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 8);
+      mbar_init(bar_xfull + 8 * b, 1); mbar_init(bar_xempty + 8 * b, 8);
     }
     fence_barrier_init();
   }
@@ -186,8 +189,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp >= 4) {
-    // ================================ epilogue ================================
-    const int q = warp - 4, row = q * 32 + lane, etid = threadIdx.x - 128;
+    // ================================ epilogue (8 warps: lane quarter q, column half hf) ================================
+    const int ew = warp - 4, q = ew & 3, hf = ew >> 2, row = q * 32 + lane, etid = threadIdx.x - 128;
+    constexpr int CH = OUT_F32 ? 16 : 32;     // accumulator columns per thread per sub-tile (64 bytes of output)
     uint32_t tc = 0, e = 0;
     for (int t = blockIdx.x; t < n_work; t += gridDim.x, ++tc) {
       const int z = t / mn_tiles, r = t - z * mn_tiles, m_blk = r / n_tiles, n_blk = r - m_blk * n_tiles;
@@ -204,95 +208,102 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t b = e & 1;
         const uint32_t sx = smem_x + b * S::SUB_BYTES + row * 128, sd = smem_d + b * S::SUB_BYTES + row * 128;
         const int n_sub = n_blk * BN + sub * S::SUB_COLS;
+        const int n0 = n_sub + hf * CH;
         // the TMA store that read D[b] / X[b] two sub-tiles ago must have finished reading shared memory
         if (etid == 0) bulk_wait_read<1>();
-        named_bar_sync(T2_EPI_BAR, 128);
+        named_bar_sync(T2_EPI_BAR, T2_EPI_THREADS);
         if (x_in) mbar_wait(bar_xfull + 8 * b, (e >> 1) & 1);
-        if (OUT_F32) {
-          uint32_t v[32];
-          tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + ab * BN + sub * 32, v);
-          tmem_ld_wait();
+        uint32_t v[CH];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * BN + sub * S::SUB_COLS + hf * CH;
+        if (OUT_F32) tmem_ld16_nowait(taddr, *reinterpret_cast<uint32_t(*)[16]>(v));
+        else tmem_ld32_nowait(taddr, *reinterpret_cast<uint32_t(*)[32]>(v));
+        uint32_t xr[16];
+        if (x_in) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {   // 8 chunks of 16 B (4 floats), 128B swizzle: chunk ^= row & 7
-            const uint32_t dst = sd + ((c ^ (row & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[4 * c]), "r"(v[4 * c + 1]), "r"(v[4 * c + 2]), "r"(v[4 * c + 3]) : "memory");
-          }
-        } else {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
-            tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + ab * BN + sub * 64 + half * 32, v);
-            uint32_t xr[16];
-            if (x_in) {
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const uint32_t src = sx + (((half * 4 + c) ^ (row & 7)) << 4);
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xr[4 * c]), "=r"(xr[4 * c + 1]), "=r"(xr[4 * c + 2]), "=r"(xr[4 * c + 3]) : "r"(src));
-              }
-            }
-            tmem_ld_wait();
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            if (ep.bias) {
-              const float* bp = ep.bias + n_sub + half * 32;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (n_sub + half * 32 + j < N) f[j] += __ldg(bp + j);
-            }
-            uint32_t pre[16];
-            if (ep.act == 1) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                pre[j] = *reinterpret_cast<uint32_t*>(&h2);
-                f[2 * j] = gelu_f(f[2 * j]); f[2 * j + 1] = gelu_f(f[2 * j + 1]);
-              }
-            } else if (ep.act == 2) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xr[j]));
-                f[2 * j] *= gelu_grad_f(h.x); f[2 * j + 1] *= gelu_grad_f(h.y);
-              }
-            }
-            if (ep.rowscale) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] *= rs;
-            }
-            if (ep.x_mode == 1) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xr[j]));
-                f[2 * j] += h.x; f[2 * j + 1] += h.y;
-              }
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint32_t o[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * c + 2 * j], f[8 * c + 2 * j + 1]);
-                o[j] = *reinterpret_cast<uint32_t*>(&h2);
-              }
-              const uint32_t off = (((half * 4 + c) ^ (row & 7)) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sd + off), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-              if (ep.act == 1)
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sx + off), "r"(pre[4 * c]), "r"(pre[4 * c + 1]), "r"(pre[4 * c + 2]), "r"(pre[4 * c + 3]) : "memory");
-            }
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t src = sx + (((hf * 4 + c) ^ (row & 7)) << 4);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xr[4 * c]), "=r"(xr[4 * c + 1]), "=r"(xr[4 * c + 2]), "=r"(xr[4 * c + 3]) : "r"(src));
           }
         }
+        tmem_ld_wait();
         if (sub == S::NSUB - 1) {       // accumulator fully read: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * ab);
         }
+        float f[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[j]);
+        if (ep.bias) {
+          if (n0 + CH <= N) {
+#pragma unroll
+            for (int j = 0; j < CH / 4; ++j) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j);
+              f[4 * j] += bv.x; f[4 * j + 1] += bv.y; f[4 * j + 2] += bv.z; f[4 * j + 3] += bv.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) if (n0 + j < N) f[j] += __ldg(ep.bias + n0 + j);
+          }
+        }
+        if (OUT_F32) {
+          if (ep.rowscale) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) f[j] *= rs;
+          }
+          if (ep.x_mode == 1) {            // fp32 residual stream
+#pragma unroll
+            for (int j = 0; j < CH; ++j) f[j] += __uint_as_float(xr[j]);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t off = (((hf * 4 + c) ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sd + off), "r"(__float_as_uint(f[4 * c])), "r"(__float_as_uint(f[4 * c + 1])),
+                         "r"(__float_as_uint(f[4 * c + 2])), "r"(__float_as_uint(f[4 * c + 3])) : "memory");
+          }
+        } else {
+          uint32_t pre[16];
+          if (ep.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              pre[j] = pack2_bf16(f[2 * j], f[2 * j + 1]);
+              f[2 * j] = gelu_fast_f(f[2 * j]); f[2 * j + 1] = gelu_fast_f(f[2 * j + 1]);
+            }
+          } else if (ep.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xr[j]));
+              f[2 * j] *= gelu_grad_fast_f(h.x); f[2 * j + 1] *= gelu_grad_fast_f(h.y);
+            }
+          }
+          if (ep.rowscale) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) f[j] *= rs;
+          }
+          if (ep.x_mode == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xr[j]));
+              f[2 * j] += h.x; f[2 * j + 1] += h.y;
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t off = (((hf * 4 + c) ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sd + off), "r"(pack2_bf16(f[8 * c], f[8 * c + 1])), "r"(pack2_bf16(f[8 * c + 2], f[8 * c + 3])),
+                         "r"(pack2_bf16(f[8 * c + 4], f[8 * c + 5])), "r"(pack2_bf16(f[8 * c + 6], f[8 * c + 7])) : "memory");
+            if (ep.act == 1)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sx + off), "r"(pre[4 * c]), "r"(pre[4 * c + 1]), "r"(pre[4 * c + 2]), "r"(pre[4 * c + 3]) : "memory");
+          }
+        }
         if (x_in) { __syncwarp(); if (lane == 0) mbar_arrive(bar_xempty + 8 * b); }
         fence_proxy_async();
-        named_bar_sync(T2_EPI_BAR, 128);
+        named_bar_sync(T2_EPI_BAR, T2_EPI_THREADS);
         if (etid == 0) {
           if (A_MODE == 2) {
             int qq = m_blk; const int tx = qq % cv.tiles_x; qq /= cv.tiles_x; const int ty = qq % cv.tiles_y; const int cb = qq / cv.tiles_y;
             tma_store_4d(&tmD, smem_d + b * S::SUB_BYTES, n_sub, tx * cv.tw, ty * cv.th, cb);
-          } else if (OUT_F32) {
+          } else if (OUT_F32 && ep.reduce) {
             tma_reduce_add_2d(&tmD, smem_d + b * S::SUB_BYTES, n_sub, m_blk * T2_BM);
           } else {
             tma_store_2d(&tmD, smem_d + b * S::SUB_BYTES, n_sub, m_blk * T2_BM);
@@ -355,6 +366,22 @@ static int t2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   return MTUS_OK;
 }
 
+// 128x256 tiles halve the L2 -> SM operand traffic per flop (the main-loop limiter) but quantise worse on small
+// problems: pick them when the estimated time (waves x per-tile cost, L2-bound model) is lower.
+static bool t2_prefer_bn256(int M, int N, int K) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("MTUS_BN"); forced = e ? atoi(e) : 0; }
+  if (forced == 128) return false;
+  if (forced == 256) return true;
+  const int sms = sm_count();
+  const int64_t mt = ceil_div(M, T2_BM);
+  const int64_t t128 = mt * ceil_div(N, 128), t256 = mt * ceil_div(N, 256);
+  const double w128 = (double)((t128 + sms - 1) / sms), w256 = (double)((t256 + sms - 1) / sms);
+  // per-tile cost ~ max(MMA, operand bytes / L2 share) + epilogue drain; in units of "128x128 k-blocks"
+  const double c128 = 1.0 * K + 300.0, c256 = 1.55 * K + 600.0;
+  return w256 * c256 < w128 * c128;
+}
+
 bool mtus_gemm_tc2_supported(const mtus_gemm_desc* d) {
   if (d->dtype != MTUS_BF16) return false;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -369,12 +396,16 @@ bool mtus_gemm_tc2_supported(const mtus_gemm_desc* d) {
   if (!d->a_conv && !wgrad_conv && (d->lda % 8)) return false;
   if (!d->b_conv && (d->ldb % 8)) return false;
   if (d->out_f32) {
-    // fp32 output = accumulate (TMA reduce-add) with no epilogue ops: the weight-gradient form
-    if (!d->atomic || d->bias || d->act || d->res || d->rowscale) return false;
+    // fp32 output: either accumulate (TMA reduce-add, split-K weight gradients) or a plain store with an optional
+    // bias / drop-path scale / fp32 residual (the fp32 residual stream of the bf16 mode)
+    if (d->act) return false;
     if (d->ld_out % 4) return false;
-    if (wgrad_conv && (d->lda % 64 || d->conv_c % 128 || d->M % 64)) return false;
+    if (d->atomic && (d->bias || d->res || d->rowscale)) return false;
+    if (d->res && (!d->res_f32 || d->res_mode != 1 || d->ld_res % 4 || !al16(d->res))) return false;
+    if (d->a_conv) return false;
+    if (wgrad_conv && (!d->atomic || d->lda % 64 || d->conv_c % 128 || d->M % 64)) return false;
   } else {
-    if (d->atomic) return false;
+    if (d->atomic || d->res_f32) return false;
     if (d->ld_out % 8) return false;
     if (d->res && (d->res_mode != 1 || d->ld_res % 8 || !al16(d->res))) return false;
     if (d->act && (!d->aux || d->ld_aux % 8 || !al16(d->aux))) return false;
@@ -382,6 +413,7 @@ bool mtus_gemm_tc2_supported(const mtus_gemm_desc* d) {
     if (d->act == 1 && d->res) return false;
     if (d->a_conv && (d->bias || d->act || d->res || d->rowscale)) return false;
     if (d->a_conv && (d->N % 64 || d->ld_out != d->N)) return false;
+    if (wgrad_conv) return false;
   }
   return true;
 }
@@ -393,7 +425,8 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
   CUtensorMap ta, tb, tx, td;
   T2Conv cv{};
   int rc;
-  const int BN = (N > 64) ? 128 : 64;
+  int BN = (N > 64) ? 128 : 64;
+  if (!d->out_f32 && !d->a_conv && !d->b_conv && N >= 256 && t2_prefer_bn256(M, N, K)) BN = 256;
   int m_tiles = ceil_div(M, T2_BM), n_tiles = ceil_div(N, BN), total_kb = ceil_div(K, T2_BK);
   if (d->a_conv || d->b_conv) {
     cv.H = d->conv_h; cv.W = d->conv_w; cv.C = d->conv_c;
@@ -428,17 +461,19 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
   ep.bias = d->bias; ep.rowscale = d->rowscale; ep.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1;
   ep.act = d->act;
   ep.x_mode = d->res ? 1 : (d->act == 2 ? 2 : (d->act == 1 ? 3 : 0));
+  ep.reduce = d->atomic ? 1 : 0;
   if (d->out_f32) rc = make_map_2d_f32(&td, d->out, N, M, d->ld_out, 32, T2_BM);
   else if (d->a_conv) rc = make_map_conv(&td, d->out, M / (cv.H * cv.W), cv.H, cv.W, N, cv.tw, cv.th);
   else rc = make_map_2d(&td, d->out, N, M, d->ld_out, 64, T2_BM);
   if (rc) return rc;
-  if (ep.x_mode == 1) rc = make_map_2d(&tx, d->res, N, M, d->ld_res, 64, T2_BM);
+  if (ep.x_mode == 1 && d->out_f32) rc = make_map_2d_f32(&tx, d->res, N, M, d->ld_res, 32, T2_BM);
+  else if (ep.x_mode == 1) rc = make_map_2d(&tx, d->res, N, M, d->ld_res, 64, T2_BM);
   else if (ep.x_mode) rc = make_map_2d(&tx, d->aux, N, M, d->ld_aux, 64, T2_BM);
   else tx = td;
   if (rc) return rc;
 
   int splits = d->split_k > 0 ? d->split_k : 1;
-  if (!d->out_f32) splits = 1;
+  if (!d->atomic) splits = 1;
   if (splits > total_kb) splits = total_kb;
   const int kbps = ceil_div(total_kb, splits);
   splits = ceil_div(total_kb, kbps);
@@ -449,11 +484,16 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
 #define T2_GO(BN_, AM_, BM_, F32_) return t2_launch<BN_, AM_, BM_, F32_>(ta, tb, tx, td, M, N, K, kbps, total_kb, m_tiles, n_tiles, n_work, cv, ep, st)
   if (d->out_f32) {
     if (BN == 128) {
+      if (am == 0 && bm == 0) T2_GO(128, 0, 0, true);
       if (am == 1 && bm == 1) T2_GO(128, 1, 1, true);
       if (am == 3 && bm == 2) T2_GO(128, 3, 2, true);
     } else {
+      if (am == 0 && bm == 0) T2_GO(64, 0, 0, true);
       if (am == 1 && bm == 1) T2_GO(64, 1, 1, true);
     }
+  } else if (BN == 256) {
+    if (am == 0 && bm == 0) T2_GO(256, 0, 0, false);
+    if (am == 0 && bm == 1) T2_GO(256, 0, 1, false);
   } else if (BN == 128) {
     if (am == 0 && bm == 0) T2_GO(128, 0, 0, false);
     if (am == 0 && bm == 1) T2_GO(128, 0, 1, false);

@@ -22,7 +22,7 @@ struct PInfo { std::string name; int64_t off; int rank; int64_t shape[4]; int64_
 
 struct BlockP { int64_t n1w, n1b, table, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b, fc2w, fc2b; };
 struct StageP { int64_t mg_nw, mg_nb, mg_red; std::vector<BlockP> blk; int64_t begin, end; };
-struct BlockA { size_t mean1, rstd1, ln1, qkv, attn, xmid, mean2, rstd2, ln2, h, a, xout; };
+struct BlockA { size_t mean1, rstd1, ln1, qkv, attn, lse, xmid, mean2, rstd2, ln2, h, a, xout; };
 struct StageA { size_t mg_ln, mg_mean, mg_rstd, xin; std::vector<BlockA> blk; };
 
 struct Plan {
@@ -135,10 +135,10 @@ bool build_plan(const mtus_swin_config* c, Plan& p) {
     s.xin = xin;
     s.blk.resize(p.depths[i]);
     // inference: per-stage buffers are recycled (three rotating residual-stream buffers)
-    size_t sh_mean1 = 0, sh_rstd1 = 0, sh_ln1 = 0, sh_qkv = 0, sh_attn = 0, sh_mean2 = 0, sh_rstd2 = 0, sh_ln2 = 0, sh_h = 0, sh_a = 0, rot[3] = {0, 0, 0};
+    size_t sh_mean1 = 0, sh_rstd1 = 0, sh_ln1 = 0, sh_qkv = 0, sh_attn = 0, sh_lse = 0, sh_mean2 = 0, sh_rstd2 = 0, sh_ln2 = 0, sh_h = 0, sh_a = 0, rot[3] = {0, 0, 0};
     if (!p.training) {
       sh_mean1 = a.take((size_t)p.M[i] * 4); sh_rstd1 = a.take((size_t)p.M[i] * 4); sh_ln1 = a.take(MC); sh_qkv = a.take(3 * MC);
-      sh_attn = a.take(MC); sh_mean2 = a.take((size_t)p.M[i] * 4); sh_rstd2 = a.take((size_t)p.M[i] * 4); sh_ln2 = a.take(MC);
+      sh_attn = a.take(MC); sh_lse = a.take((size_t)p.M[i] * p.heads[i] * 4); sh_mean2 = a.take((size_t)p.M[i] * 4); sh_rstd2 = a.take((size_t)p.M[i] * 4); sh_ln2 = a.take(MC);
       sh_h = a.take(4 * MC); sh_a = sh_h;               // GELU output overwrites its input in inference
       rot[0] = xin; rot[1] = a.take(MC); rot[2] = a.take(MC);
     }
@@ -146,10 +146,10 @@ bool build_plan(const mtus_swin_config* c, Plan& p) {
       BlockA& b = s.blk[j];
       if (p.training) {
         b.mean1 = a.take((size_t)p.M[i] * 4); b.rstd1 = a.take((size_t)p.M[i] * 4); b.ln1 = a.take(MC); b.qkv = a.take(3 * MC);
-        b.attn = a.take(MC); b.xmid = a.take(MC); b.mean2 = a.take((size_t)p.M[i] * 4); b.rstd2 = a.take((size_t)p.M[i] * 4);
+        b.attn = a.take(MC); b.lse = a.take((size_t)p.M[i] * p.heads[i] * 4); b.xmid = a.take(MC); b.mean2 = a.take((size_t)p.M[i] * 4); b.rstd2 = a.take((size_t)p.M[i] * 4);
         b.ln2 = a.take(MC); b.h = a.take(4 * MC); b.a = a.take(4 * MC); b.xout = a.take(MC);
       } else {
-        b.mean1 = sh_mean1; b.rstd1 = sh_rstd1; b.ln1 = sh_ln1; b.qkv = sh_qkv; b.attn = sh_attn; b.mean2 = sh_mean2; b.rstd2 = sh_rstd2;
+        b.mean1 = sh_mean1; b.rstd1 = sh_rstd1; b.ln1 = sh_ln1; b.qkv = sh_qkv; b.attn = sh_attn; b.lse = sh_lse; b.mean2 = sh_mean2; b.rstd2 = sh_rstd2;
         b.ln2 = sh_ln2; b.h = sh_h; b.a = sh_a;
         b.xmid = rot[(2 * j + 1) % 3]; b.xout = rot[(2 * j + 2) % 3];   // x_in of block j is rot[(2j) % 3]
       }
@@ -263,7 +263,7 @@ extern "C" int mtus_swin_forward(const mtus_swin_config* cfg, const void* x, int
       const float* dp2 = droppath ? droppath + (size_t)(2 * gblk + 1) * p.B : nullptr;
       RUN(mtus_layernorm_fwd(A(xin), F(bp.n1w), F(bp.n1b), A(ba.ln1), FA(ba.mean1), FA(ba.rstd1), M, Cc, p.eps, dt, stream));
       RUN(mtus_linear_fwd(A(ba.ln1), W(bp.qkvw), F(bp.qkvb), A(ba.qkv), nullptr, nullptr, nullptr, 1, M, 3 * Cc, Cc, dt, be, stream));
-      RUN(mtus_window_attn_fwd(A(ba.qkv), F(bp.table), F(bp.qkvb), A(ba.attn), p.B, res, res, Cc, p.heads[i], p.win[i], p.win[i],
+      RUN(mtus_window_attn_fwd(A(ba.qkv), F(bp.table), F(bp.qkvb), A(ba.attn), FA(ba.lse), p.B, res, res, Cc, p.heads[i], p.win[i], p.win[i],
                                shift, shift, dt, stream));
       RUN(mtus_linear_fwd(A(ba.attn), W(bp.projw), F(bp.projb), A(ba.xmid), nullptr, A(xin), dp1, rps, M, Cc, Cc, dt, be, stream));
       RUN(mtus_layernorm_fwd(A(ba.xmid), F(bp.n2w), F(bp.n2b), A(ba.ln2), FA(ba.mean2), FA(ba.rstd2), M, Cc, p.eps, dt, stream));
@@ -340,9 +340,9 @@ extern "C" int mtus_swin_backward(const mtus_swin_config* cfg, const float* para
       if (dp1) { RUN(mtus_scale_rows(G, tmpS, dp1, rps, M, Cc, dt, stream)); dy1 = tmpS; }
       RUN(mtus_linear_wgrad(dy1, A(ba.attn), GR(bp.projw), GR(bp.projb), M, Cc, Cc, dt, be, stream));
       RUN(mtus_linear_dgrad(dy1, W(bp.projw), dLN, nullptr, nullptr, 1, M, Cc, Cc, dt, be, stream));
-      RUN(mtus_window_attn_bwd(dLN, A(ba.qkv), A(ba.attn), F(bp.table), F(bp.qkvb), dQKV, GR(bp.table), GR(bp.qkvb), p.B, res, res, Cc,
+      RUN(mtus_window_attn_bwd(dLN, A(ba.qkv), A(ba.attn), FA(ba.lse), F(bp.table), F(bp.qkvb), dQKV, GR(bp.table), GR(bp.qkvb), GR(bp.qkvb), p.B, res, res, Cc,
                                p.heads[i], p.win[i], p.win[i], shift, shift, dt, stream));
-      RUN(mtus_linear_wgrad(dQKV, A(ba.ln1), GR(bp.qkvw), GR(bp.qkvb), M, 3 * Cc, Cc, dt, be, stream));
+      RUN(mtus_linear_wgrad(dQKV, A(ba.ln1), GR(bp.qkvw), nullptr, M, 3 * Cc, Cc, dt, be, stream));   // bias grad: fused in attention bwd
       RUN(mtus_linear_dgrad(dQKV, W(bp.qkvw), dLN, nullptr, nullptr, 1, M, 3 * Cc, Cc, dt, be, stream));
       RUN(mtus_layernorm_bwd(dLN, A(xin), F(bp.n1w), FA(ba.mean1), FA(ba.rstd1), G, G, GR(bp.n1w), GR(bp.n1b), M, Cc, dt, stream));
     }

@@ -83,22 +83,27 @@ def linear_wgrad(dy, x, with_bias=True, backend=0):
     return dw, db
 
 
-def window_attn_fwd(qkv, table, qkv_bias, heads, window, shift):
+def window_attn_fwd(qkv, table, qkv_bias, heads, window, shift, return_lse=False):
     B, H, W, C3 = qkv.shape
     Cc = C3 // 3
     out = torch.empty(B, H, W, Cc, dtype=qkv.dtype, device=qkv.device)
-    check(lib().mtus_window_attn_fwd(ptr(qkv), ptr(table), ptr(qkv_bias), ptr(out), B, H, W, Cc, heads, window, window, shift, shift, _dt(qkv), stream_ptr()), "window_attn_fwd")
-    return out
+    lse = torch.empty(B * H * W, heads, dtype=torch.float32, device=qkv.device)
+    check(lib().mtus_window_attn_fwd(ptr(qkv), ptr(table), ptr(qkv_bias), ptr(out), ptr(lse), B, H, W, Cc, heads, window, window, shift, shift, _dt(qkv), stream_ptr()), "window_attn_fwd")
+    return (out, lse) if return_lse else out
 
 
-def window_attn_bwd(dout, qkv, out, table, qkv_bias, heads, window, shift):
+def window_attn_bwd(dout, qkv, out, table, qkv_bias, heads, window, shift, lse=None, with_colsum=False):
+    """Returns (dqkv, dtable, dbias[, dcolsum]); dbias = gradient reaching the qkv bias through padded tokens."""
     B, H, W, C3 = qkv.shape
     Cc = C3 // 3
+    if lse is None:   # recompute what forward would have saved
+        _, lse = window_attn_fwd(qkv, table, qkv_bias, heads, window, shift, return_lse=True)
     dqkv = torch.empty_like(qkv)
     dtable = torch.zeros_like(table)
     dbias = torch.zeros(C3, dtype=torch.float32, device=qkv.device)
-    check(lib().mtus_window_attn_bwd(ptr(dout), ptr(qkv), ptr(out), ptr(table), ptr(qkv_bias), ptr(dqkv), ptr(dtable), ptr(dbias), B, H, W, Cc, heads, window, window, shift, shift, _dt(qkv), stream_ptr()), "window_attn_bwd")
-    return dqkv, dtable, dbias
+    dcol = torch.zeros(C3, dtype=torch.float32, device=qkv.device) if with_colsum else None
+    check(lib().mtus_window_attn_bwd(ptr(dout), ptr(qkv), ptr(out), ptr(lse), ptr(table), ptr(qkv_bias), ptr(dqkv), ptr(dtable), ptr(dbias), ptr(dcol), B, H, W, Cc, heads, window, window, shift, shift, _dt(qkv), stream_ptr()), "window_attn_bwd")
+    return (dqkv, dtable, dbias, dcol) if with_colsum else (dqkv, dtable, dbias)
 
 
 def conv3x3_repack(w, dtype):

@@ -70,6 +70,7 @@ typedef struct mtus_gemm_desc {
   int split_k;
   int dtype;
   int backend;
+  int res_f32;                 /* residual (and out, with out_f32) in fp32: the fp32 residual stream of the bf16 mode */
 } mtus_gemm_desc;
 
 int mtus_gemm(const mtus_gemm_desc* desc, void* stream);
@@ -104,14 +105,20 @@ int mtus_patch_embed_im2col(const void* x_nchw, void* cols, int B, int H, int W,
  * The cyclic shift, zero padding to a multiple of the window, window partition/reverse, q scaling,
  * relative-position bias, shift mask (-100), softmax and P@V all happen inside the kernel; nothing
  * window-shaped is materialised in HBM.  qkv_bias ([3C], fp32) supplies q/k/v of the padded tokens
- * (timm pads AFTER norm1, so pad tokens carry only the bias); may be NULL when H,W divide by window. */
-int mtus_window_attn_fwd(const void* qkv, const float* rel_table, const float* qkv_bias, void* out, int B, int H,
-                         int W, int C, int heads, int win_h, int win_w, int shift_h, int shift_w, int dtype,
+ * (timm pads AFTER norm1, so pad tokens carry only the bias); may be NULL when H,W divide by window.
+ * lse (may be NULL): [B*H*W, heads] fp32 log-sum-exp of every score row, saved for the backward pass. */
+int mtus_window_attn_fwd(const void* qkv, const float* rel_table, const float* qkv_bias, void* out, float* lse, int B,
+                         int H, int W, int C, int heads, int win_h, int win_w, int shift_h, int shift_w, int dtype,
                          void* stream);
-/* out = the forward output (delta_i = dout_i . out_i); dqkv fully written; drel_table [(2wh-1)(2ww-1), heads] and dqkv_bias [3C] (may be NULL) ACCUMULATED. */
-int mtus_window_attn_bwd(const void* dout, const void* qkv, const void* out, const float* rel_table,
-                         const float* qkv_bias, void* dqkv, float* drel_table, float* dqkv_bias, int B, int H, int W,
-                         int C, int heads, int win_h, int win_w, int shift_h, int shift_w, int dtype, void* stream);
+/* out = the forward output (delta_i = dout_i . out_i); lse = what forward wrote (required by the tensor-core engine:
+ * bf16, windows of <= 64 tokens; [B*H*W, heads] fp32, log2 domain; may be NULL for the general engine);
+ * dqkv fully written; drel_table [(2wh-1)(2ww-1), heads] and dqkv_bias [3C] (gradient reaching the bias through
+ * padded tokens; may be NULL when H,W divide by the window) are ACCUMULATED; dqkv_colsum [3C] (may be NULL)
+ * += column sums of dqkv over real tokens, i.e. the qkv Linear's bias gradient. */
+int mtus_window_attn_bwd(const void* dout, const void* qkv, const void* out, const float* lse, const float* rel_table,
+                         const float* qkv_bias, void* dqkv, float* drel_table, float* dqkv_bias, float* dqkv_colsum,
+                         int B, int H, int W, int C, int heads, int win_h, int win_w, int shift_h, int shift_w, int dtype,
+                         void* stream);
 
 /* ---- FPN pieces (smp FPNDecoder; 8a a11-a13), all NHWC --------------------------------------- */
 /* nearest-x2 top-down: y[b,h,w,:] = skip[b,h,w,:] + top[b,h/2,w/2,:] */

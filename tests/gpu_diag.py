@@ -200,8 +200,9 @@ def g_attention():
             ok &= report(f"attn_fwd {dt} B{B} {H}x{W} h{heads} w{win} s{shift}", out, ref, tol)
             dout = torch.randn(B, H, W, Cc, device=dev).to(dt)
             ref.backward(dout.float())
-            dqkv, dtab, dbias = ops.window_attn_bwd(dout, qkv, out, table, bias, heads, win, shift)
+            dqkv, dtab, dbias, dcol = ops.window_attn_bwd(dout, qkv, out, table, bias, heads, win, shift, with_colsum=True)
             ok &= report(f"attn_bwd dqkv", dqkv, qr.grad, tol)
+            ok &= report(f"attn_bwd colsum(dqkv) (qkv Linear bias grad)", dcol, qr.grad.sum((0, 1, 2)), max(tol, 2e-4))
             ok &= report(f"attn_bwd dtable", dtab, tr.grad, max(tol, 2e-4))
             if br.grad is not None:
                 ok &= report(f"attn_bwd dqkv_bias (pad tokens)", dbias, br.grad, max(tol, 2e-4))
