@@ -31,7 +31,7 @@ class GemmDesc(C.Structure):
         ("res", vp), ("ld_res", i64), ("res_mode", i32), ("res_h", i32), ("res_w", i32),
         ("rowscale", vp), ("rows_per_sample", i32),
         ("out", vp), ("ld_out", i64), ("out_f32", i32), ("atomic", i32),
-        ("split_k", i32), ("dtype", i32), ("backend", i32), ("res_f32", i32),
+        ("split_k", i32), ("dtype", i32), ("backend", i32), ("res_f32", i32), ("out_colsum", vp),
     ]
 
 
@@ -63,12 +63,19 @@ SIGNATURES = {
     "mtus_patch_merge_ln_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_gemm": (i32, [_P(GemmDesc), vp]),
     "mtus_linear_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, vp]),
-    "mtus_linear_dgrad": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, vp]),
+    "mtus_linear_fwd_stream": (i32, [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, vp]),
+    "mtus_linear_dgrad": (i32, [vp, vp, vp, vp, vp, i32, vp, i64, i32, i32, i32, i32, vp]),
+    "mtus_layernorm_fwd_mixed": (i32, [vp, i32, vp, vp, vp, i32, vp, vp, i64, i32, f32, i32, vp]),
+    "mtus_layernorm_bwd_mixed": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i64, i32, i32, vp]),
+    "mtus_patch_merge_ln_fwd_mixed": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp]),
+    "mtus_patch_merge_ln_bwd_mixed": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_linear_wgrad": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
     "mtus_cast_f32_to_bf16": (i32, [vp, vp, i64, vp]),
     "mtus_colsum": (i32, [vp, vp, i64, i32, i32, vp]),
     "mtus_scale_rows": (i32, [vp, vp, vp, i32, i64, i32, i32, vp]),
     "mtus_add": (i32, [vp, vp, vp, i64, i32, vp]),
+    "mtus_scale_cast_colsum": (i32, [vp, vp, i32, vp, vp, i64, i32, i32, vp]),
+    "mtus_convert": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mtus_nhwc_to_nchw": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_nchw_to_nhwc": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_patch_embed_im2col": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),

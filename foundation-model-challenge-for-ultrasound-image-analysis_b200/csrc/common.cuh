@@ -39,6 +39,10 @@ template <> struct IO<float> {
   }
   static __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
   static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+  static __device__ __forceinline__ void load8_reg(const float (&v)[8], float (&r)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = v[i];
+  }
 };
 
 template <> struct IO<bf16> {
@@ -70,6 +74,10 @@ template <> struct IO<bf16> {
   }
   static __device__ __forceinline__ float ld(const bf16* p) { return __bfloat162float(*p); }
   static __device__ __forceinline__ void st(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+  static __device__ __forceinline__ void load8_reg(const float (&v)[8], float (&r)[8]) {   // value after rounding to bf16
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+  }
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -134,6 +142,7 @@ struct EpiParams {
   int64_t ld_out;
   int out_f32;             // 1: out is fp32 regardless of the activation dtype
   int atomic;              // 1: atomicAdd into the fp32 out (split-K wgrad)
+  int res_f32;             // 1: the residual is fp32 regardless of the activation dtype (fp32 residual stream)
 };
 
 // Applies the epilogue to 4 consecutive columns (n0..n0+3) of row m.  nvalid = columns in range.
@@ -169,9 +178,14 @@ __device__ __forceinline__ void epilogue4(const EpiParams& ep, int64_t m, int n0
       const int y = rem / ep.W, x = rem - y * ep.W;
       rm = (b * (ep.H >> 1) + (y >> 1)) * (ep.W >> 1) + (x >> 1);
     }
-    const T* r = reinterpret_cast<const T*>(ep.res) + rm * ep.ld_res + n0;
     float t[4] = {0.f, 0.f, 0.f, 0.f};
-    if (nvalid == 4) IO<T>::load4(r, t); else for (int j = 0; j < nvalid; ++j) t[j] = IO<T>::ld(r + j);
+    if (ep.res_f32) {
+      const float* r = reinterpret_cast<const float*>(ep.res) + rm * ep.ld_res + n0;
+      if (nvalid == 4) IO<float>::load4(r, t); else for (int j = 0; j < nvalid; ++j) t[j] = IO<float>::ld(r + j);
+    } else {
+      const T* r = reinterpret_cast<const T*>(ep.res) + rm * ep.ld_res + n0;
+      if (nvalid == 4) IO<T>::load4(r, t); else for (int j = 0; j < nvalid; ++j) t[j] = IO<T>::ld(r + j);
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] += t[j];
   }

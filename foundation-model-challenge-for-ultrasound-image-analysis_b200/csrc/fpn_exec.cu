@@ -256,10 +256,10 @@ extern "C" int mtus_fpn_backward(const mtus_fpn_config* cfg, const void* const* 
     MTUS_CHECK_ARG(dfeats[k]);
     if (dfeats_layout == 1) {
       MTUS_CHECK_ARG(!(dfeats_f32 && dt != MTUS_F32));
-      RUN(mtus_linear_dgrad(A(p.gP[k]), W(p.lat_w[k]), dfeats[k], nullptr, nullptr, 1, M, p.P, p.cin[k], dt, be, stream));
+      RUN(mtus_linear_dgrad(A(p.gP[k]), W(p.lat_w[k]), dfeats[k], nullptr, nullptr, 1, nullptr, M, p.P, p.cin[k], dt, be, stream));
     } else {
       void* tmp = A(p.tmpL);
-      RUN(mtus_linear_dgrad(A(p.gP[k]), W(p.lat_w[k]), tmp, nullptr, nullptr, 1, M, p.P, p.cin[k], dt, be, stream));
+      RUN(mtus_linear_dgrad(A(p.gP[k]), W(p.lat_w[k]), tmp, nullptr, nullptr, 1, nullptr, M, p.P, p.cin[k], dt, be, stream));
       RUN(mtus_nhwc_to_nchw(tmp, dfeats[k], p.B, p.size[k] * p.size[k], p.cin[k], dt, dfeats_f32, stream));
     }
   }

@@ -32,6 +32,7 @@ extern "C" int mtus_gemm(const mtus_gemm_desc* d, void* stream) {
   ep.res = d->res; ep.ld_res = d->ld_res; ep.res_mode = d->res_mode; ep.H = d->res_h; ep.W = d->res_w;
   ep.rowscale = d->rowscale; ep.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1;
   ep.out = d->out; ep.ld_out = d->ld_out; ep.out_f32 = d->out_f32; ep.atomic = d->atomic;
+  ep.res_f32 = d->res_f32;
   cudaStream_t st = (cudaStream_t)stream;
   int backend = d->backend;
   const int f = forced_backend();
@@ -39,10 +40,18 @@ extern "C" int mtus_gemm(const mtus_gemm_desc* d, void* stream) {
   if (backend == MTUS_BACKEND_AUTO) backend = (d->dtype == MTUS_BF16) ? MTUS_BACKEND_TCGEN05 : MTUS_BACKEND_SIMT;
   if (backend == MTUS_BACKEND_TCGEN05) {
     if (!g_no_tc2 && mtus_gemm_tc2_supported(d)) return mtus_gemm_tc2(d, st);   // persistent TMA-in / TMA-out engine
-    if (mtus_gemm_tc_supported(d)) return mtus_gemm_tc(d, ep, st);
-    if (d->backend == MTUS_BACKEND_TCGEN05 && !f) return MTUS_ERR_UNSUPPORTED;  // explicit request: fail loudly
   }
-  return mtus_gemm_simt(d, ep, st);
+  int rc;
+  if (backend == MTUS_BACKEND_TCGEN05 && !d->res_f32 && mtus_gemm_tc_supported(d)) rc = mtus_gemm_tc(d, ep, st);
+  else if (backend == MTUS_BACKEND_TCGEN05 && d->backend == MTUS_BACKEND_TCGEN05 && !f) return MTUS_ERR_UNSUPPORTED;  // explicit request: fail loudly
+  else rc = mtus_gemm_simt(d, ep, st);
+  if (rc) return rc;
+  // engines without the fused column sum: one stand-alone pass over the stored output
+  if (d->out_colsum) {
+    MTUS_CHECK_ARG(!d->out_f32 || d->dtype == MTUS_F32);
+    return mtus_colsum(d->out, d->out_colsum, d->M, d->N, d->dtype, stream);
+  }
+  return MTUS_OK;
 }
 
 static int pick_splits(int64_t tiles, int64_t k_blocks) {
@@ -72,8 +81,26 @@ extern "C" int mtus_linear_fwd(const void* x, const void* w, const float* bias, 
   return mtus_gemm(&d, stream);
 }
 
+// y (fp32) = res (fp32, optional) + rowscale * (x w^T + bias): Linear layers that write the fp32 residual stream
+extern "C" int mtus_linear_fwd_stream(const void* x, const void* w, const float* bias, float* y, const float* res,
+                                      const float* rowscale, int rows_per_sample, int64_t M, int N, int K, int dtype,
+                                      int backend, void* stream) {
+  MTUS_CHECK_ARG(x && w && y && M >= 0 && M < (1ll << 31));
+  mtus_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.a = x; d.lda = K; d.b = w; d.ldb = K;
+  d.M = (int)M; d.N = N; d.K = K;
+  d.bias = bias;
+  if (res) { d.res = res; d.ld_res = N; d.res_mode = 1; d.res_f32 = 1; }
+  d.rowscale = rowscale; d.rows_per_sample = rows_per_sample;
+  d.out = y; d.ld_out = N; d.out_f32 = 1;
+  d.dtype = dtype; d.backend = backend;
+  return mtus_gemm(&d, stream);
+}
+
 extern "C" int mtus_linear_dgrad(const void* dy, const void* w, void* dx, const void* gelu_pre, const float* rowscale,
-                                 int rows_per_sample, int64_t M, int N, int K, int dtype, int backend, void* stream) {
+                                 int rows_per_sample, float* dx_colsum, int64_t M, int N, int K, int dtype, int backend,
+                                 void* stream) {
   MTUS_CHECK_ARG(dy && w && dx && M >= 0 && M < (1ll << 31));
   mtus_gemm_desc d;
   memset(&d, 0, sizeof(d));
@@ -83,6 +110,7 @@ extern "C" int mtus_linear_dgrad(const void* dy, const void* w, void* dx, const 
   if (gelu_pre) { d.act = 2; d.aux = const_cast<void*>(gelu_pre); d.ld_aux = K; }
   d.rowscale = rowscale; d.rows_per_sample = rows_per_sample;
   d.out = dx; d.ld_out = K;
+  d.out_colsum = dx_colsum;
   d.dtype = dtype; d.backend = backend;
   return mtus_gemm(&d, stream);
 }

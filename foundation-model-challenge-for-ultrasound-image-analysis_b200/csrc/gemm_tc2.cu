@@ -40,6 +40,7 @@ struct T2Epi {
   int act;                // 0 none | 1 GELU (pre-activation -> X out) | 2 multiply by GELU'(X in)
   int x_mode;             // 0 none | 1 residual in (out += X) | 2 aux in (act 2) | 3 aux out (act 1)
   int reduce;             // fp32 output: 1 = TMA reduce-add into the destination (split-K weight gradients), 0 = store
+  float* colsum;          // bf16 output only: colsum[n] += sum over rows of the stored (rounded) output (bias gradients)
 };
 
 template <int BN, bool OUT_F32>
@@ -295,6 +296,25 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (ep.act == 1)
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sx + off), "r"(pre[4 * c]), "r"(pre[4 * c + 1]), "r"(pre[4 * c + 2]), "r"(pre[4 * c + 3]) : "memory");
           }
+          if (ep.colsum) {
+            // column sums of the 32 rows of this warp: recursive halving over the lanes (31 shuffles); lane l ends
+            // up with column l of this 32-column chunk; rows beyond M contribute nothing
+            const bool row_ok = (int64_t)m_blk * T2_BM + row < M;
+            float cs[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cs[j] = row_ok ? __bfloat162float(__float2bfloat16_rn(f[j])) : 0.f;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+              const bool hi = (lane & off) != 0;
+#pragma unroll
+              for (int j = 0; j < off; ++j) {
+                const float send = hi ? cs[j] : cs[j + off];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+                cs[j] = (hi ? cs[j + off] : cs[j]) + recv;
+              }
+            }
+            if (n0 + lane < N) atomicAdd(ep.colsum + n0 + lane, cs[0]);
+          }
         }
         if (x_in) { __syncwarp(); if (lane == 0) mbar_arrive(bar_xempty + 8 * b); }
         fence_proxy_async();
@@ -402,7 +422,7 @@ bool mtus_gemm_tc2_supported(const mtus_gemm_desc* d) {
     if (d->ld_out % 4) return false;
     if (d->atomic && (d->bias || d->res || d->rowscale)) return false;
     if (d->res && (!d->res_f32 || d->res_mode != 1 || d->ld_res % 4 || !al16(d->res))) return false;
-    if (d->a_conv) return false;
+    if (d->a_conv || d->out_colsum) return false;
     if (wgrad_conv && (!d->atomic || d->lda % 64 || d->conv_c % 128 || d->M % 64)) return false;
   } else {
     if (d->atomic || d->res_f32) return false;
@@ -462,6 +482,7 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
   ep.act = d->act;
   ep.x_mode = d->res ? 1 : (d->act == 2 ? 2 : (d->act == 1 ? 3 : 0));
   ep.reduce = d->atomic ? 1 : 0;
+  ep.colsum = d->out_colsum;
   if (d->out_f32) rc = make_map_2d_f32(&td, d->out, N, M, d->ld_out, 32, T2_BM);
   else if (d->a_conv) rc = make_map_conv(&td, d->out, M / (cv.H * cv.W), cv.H, cv.W, N, cv.tw, cv.th);
   else rc = make_map_2d(&td, d->out, N, M, d->ld_out, 64, T2_BM);

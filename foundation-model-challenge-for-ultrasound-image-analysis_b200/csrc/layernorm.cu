@@ -278,3 +278,329 @@ extern "C" int mtus_patch_merge_ln_bwd(const void* dy, const void* x, const floa
   if (dtype == MTUS_BF16) return ln_launch<bf16, 1>(false, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, 4 * C, 0.f, g, st);
   return MTUS_ERR_UNSUPPORTED;
 }
+
+// =================================================================================================
+// Mixed-precision variants for the fp32 residual stream (bf16 mode) -- also used, with every type float, by
+// the fp32 mode so the executors have a single schedule.
+//   forward : x (TX) -> y (TY); statistics in fp32.
+//   backward: dx (fp32, optional) = dres (fp32, optional) + LN'(dy);  dx_lp (T, optional) = rowscale[sample] * dx
+//             rounded to the GEMM operand type, together with its column sums (lp_colsum += sum_rows dx_lp): the
+//             operand of the next weight-gradient GEMM and the bias gradient of that Linear come out of this pass,
+//             so no separate cast / drop-path scale / column-sum kernels run over the gradient stream.
+// =================================================================================================
+template <typename TX, typename TY, int NV, int WPR, int MODE>
+__global__ void __launch_bounds__(128) lnx_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, TY* __restrict__ y,
+                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                      int64_t rows, int C, float eps, MergeGeom g) {
+  __shared__ float red[2][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rpb = 4 / WPR;
+  const int sub = (WPR == 1) ? 0 : warp;
+  const float invC = 1.0f / (float)C;
+  for (int64_t row0 = (int64_t)blockIdx.x * rpb; row0 < rows; row0 += (int64_t)gridDim.x * rpb) {
+    const int64_t row = row0 + ((WPR == 1) ? warp : 0);
+    const bool active = row < rows;
+    float v[NV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = ((sub * NV + i) * 32 + lane) * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[i][k] = 0.f;
+      if (active && col < C) {
+        bool valid; const TX* p = ln_src<TX, MODE>(x, row, col, C, g, valid);
+        if (valid) IO<TX>::load8(p, v[i]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += v[i][k];
+      }
+    }
+    s = warp_sum(s);
+    if (WPR > 1) {
+      if (lane == 0) red[0][warp] = s;
+      __syncthreads();
+      s = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+    }
+    const float mean = s * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = ((sub * NV + i) * 32 + lane) * 8;
+      if (active && col < C) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float d = v[i][k] - mean; q += d * d; }
+      }
+    }
+    q = warp_sum(q);
+    if (WPR > 1) {
+      if (lane == 0) red[1][warp] = q;
+      __syncthreads();
+      q = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+    }
+    const float rstd = rsqrtf(q * invC + eps);
+    if (active) {
+      if (lane == 0 && sub == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int col = ((sub * NV + i) * 32 + lane) * 8;
+        if (col < C) {
+          float gm[8], bt[8], o[8];
+          IO<float>::load8(gamma + col, gm);
+          IO<float>::load8(beta + col, bt);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = (v[i][k] - mean) * rstd * gm[k] + bt[k];
+          IO<TY>::store8(y + row * C + col, o);
+        }
+      }
+    }
+    if (WPR > 1) __syncthreads();
+  }
+}
+
+struct LnxBwdArgs {
+  const void* dy; const void* x; const float* gamma; const float* mean; const float* rstd;
+  const float* dres; float* dx; void* dx_lp; const float* lp_rowscale; int rows_per_sample; float* lp_colsum;
+  float* dgamma; float* dbeta; int64_t rows; int C;
+};
+
+template <typename T, typename TDY, typename TX, int NV, int WPR, int MODE>
+__global__ void __launch_bounds__(128) lnx_bwd_kernel(LnxBwdArgs a, MergeGeom g) {
+  __shared__ float red[2][4];
+  extern __shared__ float acc_smem[];                         // WPR==1: [3][4 warps][Cx] partial dgamma / dbeta / colsum
+  const TDY* __restrict__ dy = reinterpret_cast<const TDY*>(a.dy);
+  const TX* __restrict__ x = reinterpret_cast<const TX*>(a.x);
+  T* __restrict__ dx_lp = reinterpret_cast<T*>(a.dx_lp);
+  const int C = a.C;
+  const int64_t rows = a.rows;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rpb = 4 / WPR;
+  const int sub = (WPR == 1) ? 0 : warp;
+  const float invC = 1.0f / (float)C;
+  const bool want_cs = a.lp_colsum != nullptr;
+  float adg[NV][8], adb[NV][8], acs[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { adg[i][k] = 0.f; adb[i][k] = 0.f; acs[i][k] = 0.f; }
+
+  for (int64_t row0 = (int64_t)blockIdx.x * rpb; row0 < rows; row0 += (int64_t)gridDim.x * rpb) {
+    const int64_t row = row0 + ((WPR == 1) ? warp : 0);
+    const bool active = row < rows;
+    const float mean = active ? a.mean[row] : 0.f, rstd = active ? a.rstd[row] : 0.f;
+    float xh[NV][8], gy[NV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = ((sub * NV + i) * 32 + lane) * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { xh[i][k] = 0.f; gy[i][k] = 0.f; }
+      if (active && col < C) {
+        float xv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dv[8], gm[8];
+        bool valid; const TX* p = ln_src<TX, MODE>(x, row, col, C, g, valid);
+        if (valid) IO<TX>::load8(p, xv);
+        IO<TDY>::load8(dy + row * C + col, dv);
+        IO<float>::load8(a.gamma + col, gm);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          xh[i][k] = (xv[k] - mean) * rstd;
+          gy[i][k] = dv[k] * gm[k];
+          s1 += gy[i][k];
+          s2 += gy[i][k] * xh[i][k];
+          adg[i][k] += dv[k] * xh[i][k];
+          adb[i][k] += dv[k];
+        }
+      }
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (WPR > 1) {
+      if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
+      __syncthreads();
+      s1 = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+      s2 = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+    }
+    s1 *= invC; s2 *= invC;
+    if (active) {
+      float rsc = 1.0f;
+      if (a.lp_rowscale) {
+        rsc = __ldg(a.lp_rowscale + row / a.rows_per_sample);   // rows_per_sample in units of this kernel's rows
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int col = ((sub * NV + i) * 32 + lane) * 8;
+        if (col < C) {
+          float o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = rstd * (gy[i][k] - s1 - xh[i][k] * s2);
+          bool valid; const TX* p = ln_src<TX, MODE>(x, row, col, C, g, valid);
+          if (valid) {
+            const int64_t off = p - x;
+            if (a.dres) {
+              float r[8]; IO<float>::load8(a.dres + off, r);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) o[k] += r[k];
+            }
+            if (a.dx) IO<float>::store8(a.dx + off, o);
+            if (dx_lp) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) o[k] *= rsc;
+              IO<T>::store8(dx_lp + off, o);
+              if (want_cs) {
+                // sum what the GEMM will read: the rounded values
+                float rr[8]; IO<T>::load8_reg(o, rr);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acs[i][k] += rr[k];
+              }
+            }
+          }
+        }
+      }
+    }
+    if (WPR > 1) __syncthreads();
+  }
+  // parameter gradients / column sums: reduce over the block, then one atomicAdd per column per block
+  const int Cc = (MODE == 0) ? C : g.C;                        // columns of the un-gathered tensor (lp_colsum)
+  if (WPR == 1) {
+    float* sg = acc_smem; float* sb = acc_smem + 4 * C; float* sc = acc_smem + 8 * C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 8;
+      if (col < C) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sg[warp * C + col + k] = adg[i][k]; sb[warp * C + col + k] = adb[i][k]; sc[warp * C + col + k] = acs[i][k]; }
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      atomicAdd(a.dgamma + c, sg[c] + sg[C + c] + sg[2 * C + c] + sg[3 * C + c]);
+      atomicAdd(a.dbeta + c, sb[c] + sb[C + c] + sb[2 * C + c] + sb[3 * C + c]);
+      if (want_cs) atomicAdd(a.lp_colsum + (c % Cc), sc[c] + sc[C + c] + sc[2 * C + c] + sc[3 * C + c]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = ((sub * NV + i) * 32 + lane) * 8;
+      if (col < C) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          atomicAdd(a.dgamma + col + k, adg[i][k]); atomicAdd(a.dbeta + col + k, adb[i][k]);
+          if (want_cs) atomicAdd(a.lp_colsum + ((col + k) % Cc), acs[i][k]);
+        }
+      }
+    }
+  }
+}
+
+template <typename TX, typename TY, int MODE>
+static int lnx_fwd_launch(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int64_t rows, int C,
+                          float eps, MergeGeom g, cudaStream_t st) {
+  if (rows == 0) return MTUS_OK;
+  MTUS_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 4096);
+  const int nvec = C / 8;
+#define LNX_CASE(NV_, WPR_)                                                                                                \
+  {                                                                                                                        \
+    const int rpb = 4 / WPR_;                                                                                              \
+    int64_t blocks = (rows + rpb - 1) / rpb;                                                                               \
+    if (blocks > 148 * 16) blocks = 148 * 16;                                                                              \
+    lnx_fwd_kernel<TX, TY, NV_, WPR_, MODE><<<(int)blocks, 128, 0, st>>>((const TX*)x, gamma, beta, (TY*)y, mean, rstd, rows, C, eps, g); \
+  }
+  if (nvec <= 32) LNX_CASE(1, 1)
+  else if (nvec <= 64) LNX_CASE(2, 1)
+  else if (nvec <= 96) LNX_CASE(3, 1)
+  else if (nvec <= 128) LNX_CASE(1, 4)
+  else if (nvec <= 256) LNX_CASE(2, 4)
+  else if (nvec <= 384) LNX_CASE(3, 4)
+  else LNX_CASE(4, 4)
+#undef LNX_CASE
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}
+
+template <typename T, typename TDY, typename TX, int MODE>
+static int lnx_bwd_launch(const LnxBwdArgs& a, MergeGeom g, cudaStream_t st) {
+  if (a.rows == 0) return MTUS_OK;
+  const int C = a.C;
+  MTUS_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 4096);
+  const int nvec = C / 8;
+#define LNX_CASE(NV_, WPR_)                                                                                  \
+  {                                                                                                          \
+    const int rpb = 4 / WPR_;                                                                                \
+    int64_t blocks = (a.rows + rpb - 1) / rpb;                                                               \
+    if (blocks > 148 * 4) blocks = 148 * 4;                                                                  \
+    const size_t sm = (WPR_ == 1) ? (size_t)12 * C * sizeof(float) : 0;                                      \
+    auto kern = lnx_bwd_kernel<T, TDY, TX, NV_, WPR_, MODE>;                                                 \
+    if (sm > 48 * 1024) {                                                                                    \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);      \
+      if (e != cudaSuccess) return (int)e;                                                                   \
+    }                                                                                                        \
+    kern<<<(int)blocks, 128, sm, st>>>(a, g);                                                                \
+  }
+  if (nvec <= 32) LNX_CASE(1, 1)
+  else if (nvec <= 64) LNX_CASE(2, 1)
+  else if (nvec <= 96) LNX_CASE(3, 1)
+  else if (nvec <= 128) LNX_CASE(1, 4)
+  else if (nvec <= 256) LNX_CASE(2, 4)
+  else if (nvec <= 384) LNX_CASE(3, 4)
+  else LNX_CASE(4, 4)
+#undef LNX_CASE
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}
+
+extern "C" int mtus_layernorm_fwd_mixed(const void* x, int x_f32, const float* gamma, const float* beta, void* y, int y_f32,
+                                        float* mean, float* rstd, int64_t rows, int C, float eps, int dtype, void* stream) {
+  MTUS_CHECK_ARG(x && gamma && beta && y && mean && rstd && rows >= 0);
+  MergeGeom g{};
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool xf = x_f32 || dtype == MTUS_F32, yf = y_f32 || dtype == MTUS_F32;
+  if (xf && yf) return lnx_fwd_launch<float, float, 0>(x, gamma, beta, y, mean, rstd, rows, C, eps, g, st);
+  if (dtype != MTUS_BF16) return MTUS_ERR_UNSUPPORTED;
+  if (xf && !yf) return lnx_fwd_launch<float, bf16, 0>(x, gamma, beta, y, mean, rstd, rows, C, eps, g, st);
+  if (!xf && yf) return lnx_fwd_launch<bf16, float, 0>(x, gamma, beta, y, mean, rstd, rows, C, eps, g, st);
+  return mtus_layernorm_fwd(x, gamma, beta, y, mean, rstd, rows, C, eps, dtype, stream);
+}
+
+// x: fp32 [B,H,W,C] (the residual stream); y: dtype [B,Ho,Wo,4C]
+extern "C" int mtus_patch_merge_ln_fwd_mixed(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                                             int B, int H, int W, int C, float eps, int dtype, void* stream) {
+  MTUS_CHECK_ARG(x && gamma && beta && y && mean && rstd && B >= 0 && H > 0 && W > 0 && C % 8 == 0);
+  MergeGeom g{B, H, W, C, (H + 1) / 2, (W + 1) / 2};
+  const int64_t rows = (int64_t)B * g.Ho * g.Wo;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MTUS_F32) return lnx_fwd_launch<float, float, 1>(x, gamma, beta, y, mean, rstd, rows, 4 * C, eps, g, st);
+  if (dtype == MTUS_BF16) return lnx_fwd_launch<float, bf16, 1>(x, gamma, beta, y, mean, rstd, rows, 4 * C, eps, g, st);
+  return MTUS_ERR_UNSUPPORTED;
+}
+
+extern "C" int mtus_layernorm_bwd_mixed(const void* dy, int dy_f32, const void* x, int x_f32, const float* gamma, const float* mean,
+                                        const float* rstd, const float* dres, float* dx, void* dx_lp, const float* lp_rowscale,
+                                        int rows_per_sample, float* lp_colsum, float* dgamma, float* dbeta, int64_t rows, int C,
+                                        int dtype, void* stream) {
+  MTUS_CHECK_ARG(dy && x && gamma && mean && rstd && (dx || dx_lp) && dgamma && dbeta && rows >= 0);
+  MTUS_CHECK_ARG(!lp_colsum || dx_lp);
+  LnxBwdArgs a{dy, x, gamma, mean, rstd, dres, dx, dx_lp, lp_rowscale, rows_per_sample > 0 ? rows_per_sample : 1, lp_colsum,
+               dgamma, dbeta, rows, C};
+  MergeGeom g{};
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool df = dy_f32 || dtype == MTUS_F32, xf = x_f32 || dtype == MTUS_F32;
+  if (dtype == MTUS_F32) return lnx_bwd_launch<float, float, float, 0>(a, g, st);
+  if (dtype != MTUS_BF16) return MTUS_ERR_UNSUPPORTED;
+  if (!df && xf) return lnx_bwd_launch<bf16, bf16, float, 0>(a, g, st);
+  if (df && !xf) return lnx_bwd_launch<bf16, float, bf16, 0>(a, g, st);
+  return MTUS_ERR_UNSUPPORTED;
+}
+
+// dy: dtype [B,Ho,Wo,4C]; x / dres / dx: fp32 [B,H,W,C]; dx_lp: dtype [B,H,W,C]; lp_colsum: [C]
+extern "C" int mtus_patch_merge_ln_bwd_mixed(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                                             const float* dres, float* dx, void* dx_lp, const float* lp_rowscale, int rows_per_sample,
+                                             float* lp_colsum, float* dgamma, float* dbeta, int B, int H, int W, int C, int dtype,
+                                             void* stream) {
+  MTUS_CHECK_ARG(dy && x && gamma && mean && rstd && (dx || dx_lp) && dgamma && dbeta && B >= 0 && H > 0 && W > 0 && C % 8 == 0);
+  MergeGeom g{B, H, W, C, (H + 1) / 2, (W + 1) / 2};
+  (void)rows_per_sample;                                      // one sample = Ho*Wo gathered rows
+  LnxBwdArgs a{dy, x, gamma, mean, rstd, dres, dx, dx_lp, lp_rowscale, g.Ho * g.Wo, lp_colsum,
+               dgamma, dbeta, (int64_t)B * g.Ho * g.Wo, 4 * C};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MTUS_F32) return lnx_bwd_launch<float, float, float, 1>(a, g, st);
+  if (dtype == MTUS_BF16) return lnx_bwd_launch<bf16, bf16, float, 1>(a, g, st);
+  return MTUS_ERR_UNSUPPORTED;
+}

@@ -234,3 +234,98 @@ extern "C" int mtus_patch_embed_im2col(const void* x, void* cols, int B, int H, 
   MTUS_LAUNCH_STATUS();
   return MTUS_OK;
 }
+
+// ---- fp32 gradient stream -> GEMM operand copy: y = T(rowscale[sample] * g), colsum += column sums of y ----------
+template <typename T>
+__global__ void __launch_bounds__(256) scale_cast_colsum_kernel(const float* __restrict__ g, const float* __restrict__ rowscale,
+                                                                int rows_per_sample, T* __restrict__ y, float* __restrict__ colsum,
+                                                                int64_t rows, int C, int64_t rows_per_chunk) {
+  __shared__ float red[8][32][9];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + tx) * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+  const int64_t r1 = min(rows, r0 + rows_per_chunk);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < C) {
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      float v[8], q[8];
+      IO<float>::load8(g + r * C + col, v);
+      const float s = rowscale ? __ldg(rowscale + r / rows_per_sample) : 1.0f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] *= s;
+      IO<T>::store8(y + r * C + col, v);
+      IO<T>::load8_reg(v, q);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += q[k];
+    }
+  }
+  if (colsum) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[ty][tx][k] = acc[k];
+    __syncthreads();
+    if (ty == 0 && col < C) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += red[j][tx][k];
+        atomicAdd(colsum + col + k, s);
+      }
+    }
+  }
+}
+
+extern "C" int mtus_scale_cast_colsum(const float* g, const float* rowscale, int rows_per_sample, void* y, float* colsum,
+                                      int64_t rows, int C, int dtype, void* stream) {
+  MTUS_CHECK_ARG(g && y && rows >= 0 && C > 0 && C % 8 == 0);
+  if (rows == 0) return MTUS_OK;
+  const int cb = ceil_div(C, 256);
+  int chunks = ceil_div(148 * 4, cb);
+  const int64_t maxc = (rows + 63) / 64;
+  if (chunks > maxc) chunks = (int)maxc;
+  if (chunks < 1) chunks = 1;
+  const int64_t rpc = (rows + chunks - 1) / chunks;
+  dim3 grid(cb, (unsigned)((rows + rpc - 1) / rpc));
+  const int rps = rows_per_sample > 0 ? rows_per_sample : 1;
+  if (dtype == MTUS_F32) scale_cast_colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(g, rowscale, rps, (float*)y, colsum, rows, C, rpc);
+  else if (dtype == MTUS_BF16) scale_cast_colsum_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(g, rowscale, rps, (bf16*)y, colsum, rows, C, rpc);
+  else return MTUS_ERR_UNSUPPORTED;
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}
+
+// ---- generic layout / type conversion of a [B][R][Cc] tensor: optional transpose to [B][Cc][R], fp32 <-> dtype ----
+template <typename TI, typename TO>
+__global__ void convert_kernel(const TI* __restrict__ x, TO* __restrict__ y, int64_t n8) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    float v[8];
+    IO<TI>::load8(x + i * 8, v);
+    IO<TO>::store8(y + i * 8, v);
+  }
+}
+
+extern "C" int mtus_convert(const void* x, void* y, int B, int R, int Cc, int transpose, int in_f32, int out_f32, int dtype,
+                            void* stream) {
+  MTUS_CHECK_ARG(x && y && B >= 0 && R > 0 && Cc > 0 && B <= 65535);
+  if (B == 0) return MTUS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool fi = in_f32 || dtype == MTUS_F32, fo = out_f32 || dtype == MTUS_F32;
+  if (!fi || !fo) MTUS_CHECK_ARG(dtype == MTUS_BF16);
+  if (transpose) {
+    if (fi && fo) return transpose_launch<float, float>(x, y, B, R, Cc, st);
+    if (fi) return transpose_launch<float, bf16>(x, y, B, R, Cc, st);
+    if (fo) return transpose_launch<bf16, float>(x, y, B, R, Cc, st);
+    return transpose_launch<bf16, bf16>(x, y, B, R, Cc, st);
+  }
+  const int64_t n = (int64_t)B * R * Cc;
+  MTUS_CHECK_ARG(n % 8 == 0);
+  if (fi == fo) {
+    cudaError_t e = cudaMemcpyAsync(y, x, (size_t)n * (fi ? 4 : 2), cudaMemcpyDeviceToDevice, st);
+    return e == cudaSuccess ? MTUS_OK : (int)e;
+  }
+  if (fi) convert_kernel<float, bf16><<<grid_for(n / 8, 256), 256, 0, st>>>((const float*)x, (bf16*)y, n / 8);
+  else convert_kernel<bf16, float><<<grid_for(n / 8, 256), 256, 0, st>>>((const bf16*)x, (float*)y, n / 8);
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}

@@ -23,7 +23,7 @@ struct PInfo { std::string name; int64_t off; int rank; int64_t shape[4]; int64_
 struct BlockP { int64_t n1w, n1b, table, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b, fc2w, fc2b; };
 struct StageP { int64_t mg_nw, mg_nb, mg_red; std::vector<BlockP> blk; int64_t begin, end; };
 struct BlockA { size_t mean1, rstd1, ln1, qkv, attn, lse, xmid, mean2, rstd2, ln2, h, a, xout; };
-struct StageA { size_t mg_ln, mg_mean, mg_rstd, xin; std::vector<BlockA> blk; };
+struct StageA { size_t mg_ln, mg_mean, mg_rstd, xin, feat; std::vector<BlockA> blk; };
 
 struct Plan {
   int B, S, C0, window, dtype, backend, training;
@@ -31,7 +31,7 @@ struct Plan {
   int depths[4], heads[4];
   int C[4], res[4], win[4], shift[4];
   int64_t M[4];
-  size_t es;  // activation element size
+  size_t es;  // activation / GEMM-operand element size; the residual stream (x0, xin, xmid, xout) is always fp32
   // params
   int64_t pe_w, pe_b, pe_nw, pe_nb;
   StageP sp[4];
@@ -40,7 +40,7 @@ struct Plan {
   // activations
   size_t cols, pe_pre, pe_mean, pe_rstd, x0;
   StageA sa[4];
-  size_t G, dLN, dQKV, dH, tmpS;
+  size_t G, Gb, dLN, dQKV, dH, tmpF;
   size_t ws_bytes;
 };
 
@@ -121,16 +121,18 @@ bool build_plan(const mtus_swin_config* c, Plan& p) {
   p.pe_pre = a.take((size_t)p.M[0] * p.C0 * es);
   p.pe_mean = a.take((size_t)p.M[0] * 4);
   p.pe_rstd = a.take((size_t)p.M[0] * 4);
-  p.x0 = a.take((size_t)p.M[0] * p.C0 * es);
+  p.x0 = a.take((size_t)p.M[0] * p.C0 * 4);
   for (int i = 0; i < 4; ++i) {
     StageA& s = p.sa[i];
-    const size_t MC = (size_t)p.M[i] * p.C[i] * es;
+    const size_t MC = (size_t)p.M[i] * p.C[i] * es;      // one activation map in the operand dtype
+    const size_t MX = (size_t)p.M[i] * p.C[i] * 4;       // one residual-stream map (fp32)
+    const size_t ML = (size_t)p.M[i] * p.heads[i] * 4;   // log-sum-exp rows
     size_t xin = p.x0;
     if (i > 0) {
       s.mg_ln = a.take(MC * 2);                          // [M_i, 4 C_{i-1}] = [M_i, 2 C_i]
       s.mg_mean = a.take((size_t)p.M[i] * 4);
       s.mg_rstd = a.take((size_t)p.M[i] * 4);
-      xin = a.take(MC);
+      xin = a.take(MX);
     }
     s.xin = xin;
     s.blk.resize(p.depths[i]);
@@ -138,27 +140,30 @@ bool build_plan(const mtus_swin_config* c, Plan& p) {
     size_t sh_mean1 = 0, sh_rstd1 = 0, sh_ln1 = 0, sh_qkv = 0, sh_attn = 0, sh_lse = 0, sh_mean2 = 0, sh_rstd2 = 0, sh_ln2 = 0, sh_h = 0, sh_a = 0, rot[3] = {0, 0, 0};
     if (!p.training) {
       sh_mean1 = a.take((size_t)p.M[i] * 4); sh_rstd1 = a.take((size_t)p.M[i] * 4); sh_ln1 = a.take(MC); sh_qkv = a.take(3 * MC);
-      sh_attn = a.take(MC); sh_lse = a.take((size_t)p.M[i] * p.heads[i] * 4); sh_mean2 = a.take((size_t)p.M[i] * 4); sh_rstd2 = a.take((size_t)p.M[i] * 4); sh_ln2 = a.take(MC);
-      sh_h = a.take(4 * MC); sh_a = sh_h;               // GELU output overwrites its input in inference
-      rot[0] = xin; rot[1] = a.take(MC); rot[2] = a.take(MC);
+      sh_attn = a.take(MC); sh_lse = a.take(ML); sh_mean2 = a.take((size_t)p.M[i] * 4); sh_rstd2 = a.take((size_t)p.M[i] * 4); sh_ln2 = a.take(MC);
+      sh_h = a.take(4 * MC); sh_a = a.take(4 * MC);
+      rot[0] = xin; rot[1] = a.take(MX); rot[2] = a.take(MX);
     }
     for (int j = 0; j < p.depths[i]; ++j) {
       BlockA& b = s.blk[j];
       if (p.training) {
         b.mean1 = a.take((size_t)p.M[i] * 4); b.rstd1 = a.take((size_t)p.M[i] * 4); b.ln1 = a.take(MC); b.qkv = a.take(3 * MC);
-        b.attn = a.take(MC); b.lse = a.take((size_t)p.M[i] * p.heads[i] * 4); b.xmid = a.take(MC); b.mean2 = a.take((size_t)p.M[i] * 4); b.rstd2 = a.take((size_t)p.M[i] * 4);
-        b.ln2 = a.take(MC); b.h = a.take(4 * MC); b.a = a.take(4 * MC); b.xout = a.take(MC);
+        b.attn = a.take(MC); b.lse = a.take(ML); b.xmid = a.take(MX); b.mean2 = a.take((size_t)p.M[i] * 4); b.rstd2 = a.take((size_t)p.M[i] * 4);
+        b.ln2 = a.take(MC); b.h = a.take(4 * MC); b.a = a.take(4 * MC); b.xout = a.take(MX);
       } else {
         b.mean1 = sh_mean1; b.rstd1 = sh_rstd1; b.ln1 = sh_ln1; b.qkv = sh_qkv; b.attn = sh_attn; b.lse = sh_lse; b.mean2 = sh_mean2; b.rstd2 = sh_rstd2;
         b.ln2 = sh_ln2; b.h = sh_h; b.a = sh_a;
         b.xmid = rot[(2 * j + 1) % 3]; b.xout = rot[(2 * j + 2) % 3];   // x_in of block j is rot[(2j) % 3]
       }
     }
+    // stage output as an NHWC map in the operand dtype (what the FPN consumes); fp32 mode: the stream itself
+    s.feat = (p.dtype == MTUS_F32) ? s.blk.back().xout : a.take(MC);
   }
   if (p.training) {
-    const size_t MC0 = (size_t)p.M[0] * p.C0 * es;      // M_i*C_i is largest at stage 0
-    p.G = a.take(MC0); p.dLN = a.take(MC0); p.tmpS = a.take(MC0); p.dQKV = a.take(3 * MC0); p.dH = a.take(4 * MC0);
-  } else p.G = p.dLN = p.tmpS = p.dQKV = p.dH = 0;
+    const size_t E0 = (size_t)p.M[0] * p.C0;            // M_i*C_i is largest at stage 0
+    p.G = a.take(E0 * 4); p.tmpF = a.take(E0 * 4); p.Gb = a.take(E0 * es); p.dLN = a.take(E0 * es);
+    p.dQKV = a.take(3 * E0 * es); p.dH = a.take(4 * E0 * es);
+  } else p.G = p.Gb = p.dLN = p.tmpF = p.dQKV = p.dH = 0;
   p.ws_bytes = a.off;
   return true;
 }
@@ -187,7 +192,7 @@ extern "C" int64_t mtus_swin_workspace_bytes(const mtus_swin_config* cfg) {
 extern "C" int64_t mtus_swin_feature_offset(const mtus_swin_config* cfg, int stage) {
   Plan p;
   if (!build_plan(cfg, p) || stage < 0 || stage > 3) return -1;
-  return (int64_t)p.sa[stage].blk.back().xout;
+  return (int64_t)p.sa[stage].feat;
 }
 
 extern "C" int mtus_swin_param_info(const mtus_swin_config* cfg, int idx, char* name, int64_t* offset, int* rank,
@@ -228,8 +233,7 @@ extern "C" int mtus_swin_forward(const mtus_swin_config* cfg, const void* x, int
   auto A = [&](size_t off) -> void* { return ws + off; };
   auto FA = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
 
-  // ---- patch embed: im2col -> GEMM(K=48, +bias) -> LayerNorm ----
-  const int r0 = p.res[0];
+  // ---- patch embed: im2col -> GEMM(K=48, +bias) -> LayerNorm (output: the fp32 residual stream) ----
   RUN(mtus_patch_embed_im2col(x, A(p.cols), p.B, p.S, p.S, x_is_f32 || dt == MTUS_F32, dt, stream));
   {
     mtus_gemm_desc d; memset(&d, 0, sizeof(d));
@@ -238,8 +242,7 @@ extern "C" int mtus_swin_forward(const mtus_swin_config* cfg, const void* x, int
     d.out = A(p.pe_pre); d.ld_out = p.C0; d.dtype = dt; d.backend = be;
     RUN(mtus_gemm(&d, stream));
   }
-  RUN(mtus_layernorm_fwd(A(p.pe_pre), F(p.pe_nw), F(p.pe_nb), A(p.x0), FA(p.pe_mean), FA(p.pe_rstd), p.M[0], p.C0, p.eps, dt, stream));
-  (void)r0;
+  RUN(mtus_layernorm_fwd_mixed(A(p.pe_pre), 0, F(p.pe_nw), F(p.pe_nb), A(p.x0), 1, FA(p.pe_mean), FA(p.pe_rstd), p.M[0], p.C0, p.eps, dt, stream));
 
   int gblk = 0;
   for (int i = 0; i < 4; ++i) {
@@ -249,10 +252,9 @@ extern "C" int mtus_swin_forward(const mtus_swin_config* cfg, const void* x, int
     if (i > 0) {
       const StageA& s = p.sa[i];
       const size_t prev_out = p.sa[i - 1].blk.back().xout;
-      RUN(mtus_patch_merge_ln_fwd(A(prev_out), F(p.sp[i].mg_nw), F(p.sp[i].mg_nb), A(s.mg_ln), FA(s.mg_mean), FA(s.mg_rstd), p.B,
-                                  p.res[i - 1], p.res[i - 1], p.C[i - 1], p.eps, dt, stream));
-      RUN(mtus_linear_fwd(A(s.mg_ln), W(p.sp[i].mg_red), nullptr, A(p.sa[i].xin), nullptr, nullptr, nullptr, 1, M, Cc,
-                          4 * p.C[i - 1], dt, be, stream));
+      RUN(mtus_patch_merge_ln_fwd_mixed(A(prev_out), F(p.sp[i].mg_nw), F(p.sp[i].mg_nb), A(s.mg_ln), FA(s.mg_mean), FA(s.mg_rstd), p.B,
+                                        p.res[i - 1], p.res[i - 1], p.C[i - 1], p.eps, dt, stream));
+      RUN(mtus_linear_fwd_stream(A(s.mg_ln), W(p.sp[i].mg_red), nullptr, FA(p.sa[i].xin), nullptr, nullptr, 1, M, Cc, 4 * p.C[i - 1], dt, be, stream));
     }
     for (int j = 0; j < p.depths[i]; ++j, ++gblk) {
       const BlockP& bp = p.sp[i].blk[j];
@@ -261,23 +263,23 @@ extern "C" int mtus_swin_forward(const mtus_swin_config* cfg, const void* x, int
       const int shift = (j % 2) ? p.shift[i] : 0;
       const float* dp1 = droppath ? droppath + (size_t)(2 * gblk) * p.B : nullptr;
       const float* dp2 = droppath ? droppath + (size_t)(2 * gblk + 1) * p.B : nullptr;
-      RUN(mtus_layernorm_fwd(A(xin), F(bp.n1w), F(bp.n1b), A(ba.ln1), FA(ba.mean1), FA(ba.rstd1), M, Cc, p.eps, dt, stream));
+      RUN(mtus_layernorm_fwd_mixed(A(xin), 1, F(bp.n1w), F(bp.n1b), A(ba.ln1), 0, FA(ba.mean1), FA(ba.rstd1), M, Cc, p.eps, dt, stream));
       RUN(mtus_linear_fwd(A(ba.ln1), W(bp.qkvw), F(bp.qkvb), A(ba.qkv), nullptr, nullptr, nullptr, 1, M, 3 * Cc, Cc, dt, be, stream));
       RUN(mtus_window_attn_fwd(A(ba.qkv), F(bp.table), F(bp.qkvb), A(ba.attn), FA(ba.lse), p.B, res, res, Cc, p.heads[i], p.win[i], p.win[i],
                                shift, shift, dt, stream));
-      RUN(mtus_linear_fwd(A(ba.attn), W(bp.projw), F(bp.projb), A(ba.xmid), nullptr, A(xin), dp1, rps, M, Cc, Cc, dt, be, stream));
-      RUN(mtus_layernorm_fwd(A(ba.xmid), F(bp.n2w), F(bp.n2b), A(ba.ln2), FA(ba.mean2), FA(ba.rstd2), M, Cc, p.eps, dt, stream));
+      RUN(mtus_linear_fwd_stream(A(ba.attn), W(bp.projw), F(bp.projb), FA(ba.xmid), FA(xin), dp1, rps, M, Cc, Cc, dt, be, stream));
+      RUN(mtus_layernorm_fwd_mixed(A(ba.xmid), 1, F(bp.n2w), F(bp.n2b), A(ba.ln2), 0, FA(ba.mean2), FA(ba.rstd2), M, Cc, p.eps, dt, stream));
       // fc1 + GELU: pre-activation -> h (saved for backward), activation -> a
       RUN(mtus_linear_fwd(A(ba.ln2), W(bp.fc1w), F(bp.fc1b), A(ba.a), A(ba.h), nullptr, nullptr, 1, M, 4 * Cc, Cc, dt, be, stream));
-      RUN(mtus_linear_fwd(A(ba.a), W(bp.fc2w), F(bp.fc2b), A(ba.xout), nullptr, A(ba.xmid), dp2, rps, M, Cc, 4 * Cc, dt, be, stream));
+      RUN(mtus_linear_fwd_stream(A(ba.a), W(bp.fc2w), F(bp.fc2b), FA(ba.xout), FA(ba.xmid), dp2, rps, M, Cc, 4 * Cc, dt, be, stream));
     }
+    // stage output (fp32 stream) -> caller's feature tensor, or the in-workspace NHWC copy for zero-copy consumers
+    const size_t xo = p.sa[i].blk.back().xout;
     if (feats[i]) {
-      if (feats_layout == 0) RUN(mtus_nhwc_to_nchw(A(p.sa[i].blk.back().xout), feats[i], p.B, res * res, Cc, dt, feats_f32, stream));
-      else {
-        MTUS_CHECK_ARG(!(feats_f32 && dt != MTUS_F32));
-        cudaError_t e = cudaMemcpyAsync(feats[i], A(p.sa[i].blk.back().xout), (size_t)M * Cc * p.es, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
-        if (e != cudaSuccess) return (int)e;
-      }
+      MTUS_CHECK_ARG(!(feats_f32 && feats_layout != 0 && dt != MTUS_F32));
+      RUN(mtus_convert(A(xo), feats[i], p.B, res * res, Cc, feats_layout == 0 ? 1 : 0, 1, feats_f32, dt, stream));
+    } else if (dt != MTUS_F32) {
+      RUN(mtus_convert(A(xo), A(p.sa[i].feat), p.B, res * res, Cc, 0, 1, 0, dt, stream));
     }
   }
   return MTUS_OK;
@@ -302,7 +304,20 @@ extern "C" int mtus_swin_backward(const mtus_swin_config* cfg, const float* para
   auto GR = [&](int64_t off) { return grads + off; };
   auto A = [&](size_t off) -> void* { return ws + off; };
   auto FA = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
-  void* G = A(p.G); void* dLN = A(p.dLN); void* tmpS = A(p.tmpS); void* dQKV = A(p.dQKV); void* dH = A(p.dH);
+  float* G = FA(p.G); float* tmpF = FA(p.tmpF);
+  void* Gb = A(p.Gb); void* dLN = A(p.dLN); void* dQKV = A(p.dQKV); void* dH = A(p.dH);
+  // The gradient w.r.t. the residual stream lives in fp32 (G).  Gb is its copy in the GEMM operand dtype, already
+  // multiplied by the drop-path scale of the branch that consumes it; whoever writes Gb also adds its column sums to
+  // the bias gradient of that branch's output Linear, so no separate cast / scale / column-sum passes exist.
+
+  // dfeat (caller layout / dtype) -> fp32 NHWC
+  auto load_dfeat = [&](int i, float* dst) -> int {
+    const int64_t M = p.M[i];
+    if (dfeats_layout == 0) return mtus_convert(dfeats[i], dst, p.B, p.C[i], p.res[i] * p.res[i], 1, dfeats_f32, 1, dt, stream);
+    if (dfeats_f32 && dt != MTUS_F32) return MTUS_ERR_BAD_ARG;
+    return mtus_convert(dfeats[i], dst, p.B, p.res[i] * p.res[i], p.C[i], 0, dt == MTUS_F32, 1, dt, stream);
+    (void)M;
+  };
 
   int gblk_end = 0;
   for (int i = 0; i < stage_hi; ++i) gblk_end += p.depths[i];
@@ -311,57 +326,59 @@ extern "C" int mtus_swin_backward(const mtus_swin_config* cfg, const float* para
     const int Cc = p.C[i], res = p.res[i];
     const int64_t M = p.M[i];
     const int rps = res * res;
-    if (i == 3) {  // top of the chain: G = NHWC(dfeat3) or zero
-      if (dfeats[3] && dfeats_layout == 0) RUN(mtus_nchw_to_nhwc(dfeats[3], G, p.B, res * res, Cc, dt, dfeats_f32, stream));
-      else if (dfeats[3]) {
-        MTUS_CHECK_ARG(!(dfeats_f32 && dt != MTUS_F32));
-        cudaError_t e = cudaMemcpyAsync(G, dfeats[3], (size_t)M * Cc * p.es, cudaMemcpyDeviceToDevice, st);
-        if (e != cudaSuccess) return (int)e;
-      } else { cudaError_t e = cudaMemsetAsync(G, 0, (size_t)M * Cc * p.es, st); if (e != cudaSuccess) return (int)e; }
-    }
     int gblk = gblk_end - 1;
+    if (i == 3) {  // top of the chain: G = NHWC(dfeat3) or zero, Gb = dp2 * G for the last block's fc2
+      if (dfeats[3]) RUN(load_dfeat(3, G));
+      else { cudaError_t e = cudaMemsetAsync(G, 0, (size_t)M * Cc * 4, st); if (e != cudaSuccess) return (int)e; }
+      const BlockP& bl = p.sp[3].blk.back();
+      const float* dp2 = droppath ? droppath + (size_t)(2 * gblk + 1) * p.B : nullptr;
+      RUN(mtus_scale_cast_colsum(G, dp2, rps, Gb, GR(bl.fc2b), M, Cc, dt, stream));
+    }
     for (int j = p.depths[i] - 1; j >= 0; --j, --gblk) {
       const BlockP& bp = p.sp[i].blk[j];
       const BlockA& ba = p.sa[i].blk[j];
       const size_t xin = block_xin(p, i, j);
       const int shift = (j % 2) ? p.shift[i] : 0;
       const float* dp1 = droppath ? droppath + (size_t)(2 * gblk) * p.B : nullptr;
-      const float* dp2 = droppath ? droppath + (size_t)(2 * gblk + 1) * p.B : nullptr;
-      // ---- MLP branch ----
-      const void* dy2 = G;
-      if (dp2) { RUN(mtus_scale_rows(G, tmpS, dp2, rps, M, Cc, dt, stream)); dy2 = tmpS; }
-      RUN(mtus_linear_wgrad(dy2, A(ba.a), GR(bp.fc2w), GR(bp.fc2b), M, Cc, 4 * Cc, dt, be, stream));
-      RUN(mtus_linear_dgrad(dy2, W(bp.fc2w), dH, A(ba.h), nullptr, 1, M, Cc, 4 * Cc, dt, be, stream));
-      RUN(mtus_linear_wgrad(dH, A(ba.ln2), GR(bp.fc1w), GR(bp.fc1b), M, 4 * Cc, Cc, dt, be, stream));
-      RUN(mtus_linear_dgrad(dH, W(bp.fc1w), dLN, nullptr, nullptr, 1, M, 4 * Cc, Cc, dt, be, stream));
-      RUN(mtus_layernorm_bwd(dLN, A(ba.xmid), F(bp.n2w), FA(ba.mean2), FA(ba.rstd2), G, G, GR(bp.n2w), GR(bp.n2b), M, Cc, dt, stream));
-      // ---- attention branch ----
-      const void* dy1 = G;
-      if (dp1) { RUN(mtus_scale_rows(G, tmpS, dp1, rps, M, Cc, dt, stream)); dy1 = tmpS; }
-      RUN(mtus_linear_wgrad(dy1, A(ba.attn), GR(bp.projw), GR(bp.projb), M, Cc, Cc, dt, be, stream));
-      RUN(mtus_linear_dgrad(dy1, W(bp.projw), dLN, nullptr, nullptr, 1, M, Cc, Cc, dt, be, stream));
-      RUN(mtus_window_attn_bwd(dLN, A(ba.qkv), A(ba.attn), FA(ba.lse), F(bp.table), F(bp.qkvb), dQKV, GR(bp.table), GR(bp.qkvb), GR(bp.qkvb), p.B, res, res, Cc,
-                               p.heads[i], p.win[i], p.win[i], shift, shift, dt, stream));
-      RUN(mtus_linear_wgrad(dQKV, A(ba.ln1), GR(bp.qkvw), nullptr, M, 3 * Cc, Cc, dt, be, stream));   // bias grad: fused in attention bwd
-      RUN(mtus_linear_dgrad(dQKV, W(bp.qkvw), dLN, nullptr, nullptr, 1, M, 3 * Cc, Cc, dt, be, stream));
-      RUN(mtus_layernorm_bwd(dLN, A(xin), F(bp.n1w), FA(ba.mean1), FA(ba.rstd1), G, G, GR(bp.n1w), GR(bp.n1b), M, Cc, dt, stream));
+      // ---- MLP branch (Gb = dp2 * G; fc2.bias gradient already accumulated by the producer of Gb) ----
+      RUN(mtus_linear_wgrad(Gb, A(ba.a), GR(bp.fc2w), nullptr, M, Cc, 4 * Cc, dt, be, stream));
+      RUN(mtus_linear_dgrad(Gb, W(bp.fc2w), dH, A(ba.h), nullptr, 1, GR(bp.fc1b), M, Cc, 4 * Cc, dt, be, stream));
+      RUN(mtus_linear_wgrad(dH, A(ba.ln2), GR(bp.fc1w), nullptr, M, 4 * Cc, Cc, dt, be, stream));
+      RUN(mtus_linear_dgrad(dH, W(bp.fc1w), dLN, nullptr, nullptr, 1, nullptr, M, 4 * Cc, Cc, dt, be, stream));
+      RUN(mtus_layernorm_bwd_mixed(dLN, 0, A(ba.xmid), 1, F(bp.n2w), FA(ba.mean2), FA(ba.rstd2), G, G, Gb, dp1, rps, GR(bp.projb),
+                                   GR(bp.n2w), GR(bp.n2b), M, Cc, dt, stream));
+      // ---- attention branch (Gb = dp1 * G) ----
+      RUN(mtus_linear_wgrad(Gb, A(ba.attn), GR(bp.projw), nullptr, M, Cc, Cc, dt, be, stream));
+      RUN(mtus_linear_dgrad(Gb, W(bp.projw), dLN, nullptr, nullptr, 1, nullptr, M, Cc, Cc, dt, be, stream));
+      RUN(mtus_window_attn_bwd(dLN, A(ba.qkv), A(ba.attn), FA(ba.lse), F(bp.table), F(bp.qkvb), dQKV, GR(bp.table), GR(bp.qkvb), GR(bp.qkvb),
+                               p.B, res, res, Cc, p.heads[i], p.win[i], p.win[i], shift, shift, dt, stream));
+      RUN(mtus_linear_wgrad(dQKV, A(ba.ln1), GR(bp.qkvw), nullptr, M, 3 * Cc, Cc, dt, be, stream));
+      RUN(mtus_linear_dgrad(dQKV, W(bp.qkvw), dLN, nullptr, nullptr, 1, nullptr, M, 3 * Cc, Cc, dt, be, stream));
+      // LN1 backward closes the block: the new Gb feeds the previous block's fc2 (its drop-path scale, its bias
+      // gradient), or -- unscaled -- the PatchMerging reduction of this stage; stage 0 / block 0 needs no copy
+      const float* dp2_prev = (j > 0 && droppath) ? droppath + (size_t)(2 * (gblk - 1) + 1) * p.B : nullptr;
+      float* cs_prev = (j > 0) ? GR(p.sp[i].blk[j - 1].fc2b) : nullptr;
+      void* lp = (j > 0 || i > 0) ? Gb : nullptr;
+      RUN(mtus_layernorm_bwd_mixed(dLN, 0, A(xin), 1, F(bp.n1w), FA(ba.mean1), FA(ba.rstd1), G, G, lp, dp2_prev, rps, cs_prev,
+                                   GR(bp.n1w), GR(bp.n1b), M, Cc, dt, stream));
     }
     gblk_end -= p.depths[i];
     if (i > 0) {
       // ---- patch merging backward: reduction wgrad/dgrad, then LN backward scattered to [B,H,W,C_{i-1}] ----
       const StageA& s = p.sa[i];
       const int Cp = p.C[i - 1], rp = p.res[i - 1];
-      RUN(mtus_linear_wgrad(G, A(s.mg_ln), GR(p.sp[i].mg_red), nullptr, M, Cc, 4 * Cp, dt, be, stream));
-      RUN(mtus_linear_dgrad(G, W(p.sp[i].mg_red), dH, nullptr, nullptr, 1, M, Cc, 4 * Cp, dt, be, stream));
-      const void* dres = nullptr;
-      if (dfeats[i - 1] && dfeats_layout == 0) { RUN(mtus_nchw_to_nhwc(dfeats[i - 1], tmpS, p.B, rp * rp, Cp, dt, dfeats_f32, stream)); dres = tmpS; }
-      else if (dfeats[i - 1]) { MTUS_CHECK_ARG(!(dfeats_f32 && dt != MTUS_F32)); dres = dfeats[i - 1]; }
-      RUN(mtus_patch_merge_ln_bwd(dH, A(p.sa[i - 1].blk.back().xout), F(p.sp[i].mg_nw), FA(s.mg_mean), FA(s.mg_rstd), dres, G,
-                                  GR(p.sp[i].mg_nw), GR(p.sp[i].mg_nb), p.B, rp, rp, Cp, dt, stream));
+      RUN(mtus_linear_wgrad(Gb, A(s.mg_ln), GR(p.sp[i].mg_red), nullptr, M, Cc, 4 * Cp, dt, be, stream));
+      RUN(mtus_linear_dgrad(Gb, W(p.sp[i].mg_red), dH, nullptr, nullptr, 1, nullptr, M, Cc, 4 * Cp, dt, be, stream));
+      const float* dres = nullptr;
+      if (dfeats[i - 1]) { RUN(load_dfeat(i - 1, tmpF)); dres = tmpF; }
+      const BlockP& bl = p.sp[i - 1].blk.back();                 // consumer of the new Gb: last block of stage i-1
+      const float* dp2 = droppath ? droppath + (size_t)(2 * (gblk_end - 1) + 1) * p.B : nullptr;
+      RUN(mtus_patch_merge_ln_bwd_mixed(dH, A(p.sa[i - 1].blk.back().xout), F(p.sp[i].mg_nw), FA(s.mg_mean), FA(s.mg_rstd), dres, G, Gb, dp2,
+                                        rp * rp, GR(bl.fc2b), GR(p.sp[i].mg_nw), GR(p.sp[i].mg_nb), p.B, rp, rp, Cp, dt, stream));
     } else {
-      // ---- patch embed backward: LN, then conv weight/bias gradients (no gradient w.r.t. the image) ----
-      RUN(mtus_layernorm_bwd(G, A(p.pe_pre), F(p.pe_nw), FA(p.pe_mean), FA(p.pe_rstd), nullptr, dLN, GR(p.pe_nw), GR(p.pe_nb), p.M[0],
-                             p.C0, dt, stream));
+      // ---- patch embed backward: LN (dy = the fp32 stream), then conv weight / bias gradients (none w.r.t. the image) ----
+      RUN(mtus_layernorm_bwd_mixed(G, 1, A(p.pe_pre), 0, F(p.pe_nw), FA(p.pe_mean), FA(p.pe_rstd), nullptr, nullptr, dLN, nullptr, 1, GR(p.pe_b),
+                                   GR(p.pe_nw), GR(p.pe_nb), p.M[0], p.C0, dt, stream));
       mtus_gemm_desc d; memset(&d, 0, sizeof(d));
       d.a = dLN; d.lda = p.C0; d.a_mn_major = 1;
       d.b = A(p.cols); d.ldb = 64; d.b_mn_major = 1;
@@ -370,7 +387,6 @@ extern "C" int mtus_swin_backward(const mtus_swin_config* cfg, const float* para
       d.split_k = 148;
       d.dtype = dt; d.backend = be;
       RUN(mtus_gemm(&d, stream));
-      RUN(mtus_colsum(dLN, GR(p.pe_b), p.M[0], p.C0, dt, stream));
     }
   }
   return MTUS_OK;

@@ -66,12 +66,92 @@ def linear_fwd(x, w, bias=None, gelu=False, res=None, rowscale=None, rows_per_sa
     return (y, pre) if gelu else y
 
 
-def linear_dgrad(dy, w, gelu_pre=None, rowscale=None, rows_per_sample=1, backend=0):
+def linear_dgrad(dy, w, gelu_pre=None, rowscale=None, rows_per_sample=1, backend=0, with_colsum=False):
     M, N = dy.shape
     K = w.shape[1]
     dx = torch.empty(M, K, dtype=dy.dtype, device=dy.device)
-    check(lib().mtus_linear_dgrad(ptr(dy), ptr(w), ptr(dx), ptr(gelu_pre), ptr(rowscale), rows_per_sample, M, N, K, _dt(dy), backend, stream_ptr()), "linear_dgrad")
-    return dx
+    colsum = torch.zeros(K, dtype=torch.float32, device=dy.device) if with_colsum else None
+    check(lib().mtus_linear_dgrad(ptr(dy), ptr(w), ptr(dx), ptr(gelu_pre), ptr(rowscale), rows_per_sample, ptr(colsum), M, N, K, _dt(dy), backend, stream_ptr()), "linear_dgrad")
+    return (dx, colsum) if with_colsum else dx
+
+
+def linear_fwd_stream(x, w, bias=None, res=None, rowscale=None, rows_per_sample=1, backend=0):
+    """y (fp32) = res (fp32) + rowscale * (x w^T + bias): the Linear layers that write the fp32 residual stream."""
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    check(lib().mtus_linear_fwd_stream(ptr(x), ptr(w), ptr(bias), ptr(y), ptr(res), ptr(rowscale), rows_per_sample, M, N, K, _dt(x), backend, stream_ptr()), "linear_fwd_stream")
+    return y
+
+
+def layernorm_fwd_mixed(x, gamma, beta, out_dtype, eps=1e-5):
+    rows, Cc = x.numel() // x.shape[-1], x.shape[-1]
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    dt = BF16 if torch.bfloat16 in (x.dtype, out_dtype) else F32
+    check(lib().mtus_layernorm_fwd_mixed(ptr(x), int(x.dtype == torch.float32), ptr(gamma), ptr(beta), ptr(y), int(out_dtype == torch.float32),
+                                         ptr(mean), ptr(rstd), rows, Cc, eps, dt, stream_ptr()), "layernorm_fwd_mixed")
+    return y, mean, rstd
+
+
+def layernorm_bwd_mixed(dy, x, gamma, mean, rstd, dres=None, lp_dtype=None, rowscale=None, rows_per_sample=1, want_dx=True):
+    """Returns (dx fp32 | None, dx_lp | None, lp_colsum | None, dgamma, dbeta)."""
+    rows, Cc = x.numel() // x.shape[-1], x.shape[-1]
+    dx = torch.empty(x.shape, dtype=torch.float32, device=x.device) if want_dx else None
+    lp = torch.empty(x.shape, dtype=lp_dtype, device=x.device) if lp_dtype is not None else None
+    cs = torch.zeros(Cc, dtype=torch.float32, device=x.device) if lp is not None else None
+    dg = torch.zeros(Cc, dtype=torch.float32, device=x.device)
+    db = torch.zeros_like(dg)
+    dt = BF16 if torch.bfloat16 in (dy.dtype, x.dtype, lp_dtype) else F32
+    check(lib().mtus_layernorm_bwd_mixed(ptr(dy), int(dy.dtype == torch.float32), ptr(x), int(x.dtype == torch.float32), ptr(gamma), ptr(mean),
+                                         ptr(rstd), ptr(dres), ptr(dx), ptr(lp), ptr(rowscale), rows_per_sample, ptr(cs), ptr(dg), ptr(db),
+                                         rows, Cc, dt, stream_ptr()), "layernorm_bwd_mixed")
+    return dx, lp, cs, dg, db
+
+
+def patch_merge_ln_fwd_mixed(x, gamma, beta, out_dtype, eps=1e-5):
+    B, H, W, Cc = x.shape
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    y = torch.empty(B, Ho, Wo, 4 * Cc, dtype=out_dtype, device=x.device)
+    mean = torch.empty(B * Ho * Wo, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    check(lib().mtus_patch_merge_ln_fwd_mixed(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), B, H, W, Cc, eps,
+                                              BF16 if out_dtype == torch.bfloat16 else F32, stream_ptr()), "patch_merge_ln_fwd_mixed")
+    return y, mean, rstd
+
+
+def patch_merge_ln_bwd_mixed(dy, x, gamma, mean, rstd, dres=None, rowscale=None):
+    """dy: [B,Ho,Wo,4C] (operand dtype), x / dres: fp32 [B,H,W,C].  Returns (dx fp32, dx_lp, lp_colsum [C], dgamma, dbeta)."""
+    B, H, W, Cc = x.shape
+    dx = torch.empty_like(x)
+    lp = torch.empty(x.shape, dtype=dy.dtype, device=x.device)
+    cs = torch.zeros(Cc, dtype=torch.float32, device=x.device)
+    dg = torch.zeros(4 * Cc, dtype=torch.float32, device=x.device)
+    db = torch.zeros_like(dg)
+    if H % 2 or W % 2:     # positions outside the gather never get written
+        dx.zero_(); lp.zero_()
+    check(lib().mtus_patch_merge_ln_bwd_mixed(ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dres), ptr(dx), ptr(lp), ptr(rowscale), H * W,
+                                              ptr(cs), ptr(dg), ptr(db), B, H, W, Cc, _dt(dy), stream_ptr()), "patch_merge_ln_bwd_mixed")
+    return dx, lp, cs, dg, db
+
+
+def scale_cast_colsum(g, out_dtype, rowscale=None, rows_per_sample=1):
+    rows, Cc = g.shape
+    y = torch.empty(rows, Cc, dtype=out_dtype, device=g.device)
+    cs = torch.zeros(Cc, dtype=torch.float32, device=g.device)
+    check(lib().mtus_scale_cast_colsum(ptr(g), ptr(rowscale), rows_per_sample, ptr(y), ptr(cs), rows, Cc,
+                                       BF16 if out_dtype == torch.bfloat16 else F32, stream_ptr()), "scale_cast_colsum")
+    return y, cs
+
+
+def convert(x, out_dtype, transpose=False):
+    """[B,R,C] -> [B,R,C] or [B,C,R] with a dtype change (fp32 <-> bf16)."""
+    B, R, Cc = x.shape
+    y = torch.empty((B, Cc, R) if transpose else (B, R, Cc), dtype=out_dtype, device=x.device)
+    dt = BF16 if torch.bfloat16 in (x.dtype, out_dtype) else F32
+    check(lib().mtus_convert(ptr(x), ptr(y), B, R, Cc, int(transpose), int(x.dtype == torch.float32), int(out_dtype == torch.float32), dt, stream_ptr()), "convert")
+    return y
 
 
 def linear_wgrad(dy, x, with_bias=True, backend=0):

@@ -48,6 +48,24 @@ int mtus_layernorm_bwd(const void* dy, const void* x, const float* gamma, const 
                        const void* dres, void* dx, float* dgamma, float* dbeta, int64_t rows, int C, int dtype,
                        void* stream);
 
+/* Mixed-precision variants (fp32 residual stream): x / y element types are fp32 when the *_f32 flag is set,
+ * `dtype` otherwise.  Backward: dx (fp32, may be NULL) = dres (fp32, may be NULL) + LN'(dy); dx_lp (dtype, may be
+ * NULL) = lp_rowscale[sample] * dx rounded to the GEMM operand type and lp_colsum [C] (may be NULL) += its column
+ * sums; dgamma / dbeta ACCUMULATED. */
+int mtus_layernorm_fwd_mixed(const void* x, int x_f32, const float* gamma, const float* beta, void* y, int y_f32,
+                             float* mean, float* rstd, int64_t rows, int C, float eps, int dtype, void* stream);
+int mtus_layernorm_bwd_mixed(const void* dy, int dy_f32, const void* x, int x_f32, const float* gamma, const float* mean,
+                             const float* rstd, const float* dres, float* dx, void* dx_lp, const float* lp_rowscale,
+                             int rows_per_sample, float* lp_colsum, float* dgamma, float* dbeta, int64_t rows, int C,
+                             int dtype, void* stream);
+/* x / dres / dx: fp32 [B,H,W,C]; y / dy: dtype [B,ceil(H/2),ceil(W/2),4C]; dx_lp: dtype [B,H,W,C]; lp_colsum [C] */
+int mtus_patch_merge_ln_fwd_mixed(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                                  float* rstd, int B, int H, int W, int C, float eps, int dtype, void* stream);
+int mtus_patch_merge_ln_bwd_mixed(const void* dy, const void* x, const float* gamma, const float* mean,
+                                  const float* rstd, const float* dres, float* dx, void* dx_lp, const float* lp_rowscale,
+                                  int rows_per_sample, float* lp_colsum, float* dgamma, float* dbeta, int B, int H, int W,
+                                  int C, int dtype, void* stream);
+
 /* ---- PatchMerging gather + LayerNorm(4C) (timm PatchMerging) ----------------- */
 int mtus_patch_merge_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
                             float* rstd, int B, int H, int W, int C, float eps, int dtype, void* stream);
@@ -71,6 +89,8 @@ typedef struct mtus_gemm_desc {
   int dtype;
   int backend;
   int res_f32;                 /* residual (and out, with out_f32) in fp32: the fp32 residual stream of the bf16 mode */
+  float* out_colsum;           /* [N] or NULL: += column sums of the stored output (the bias gradient of the Linear
+                                  that produced this GEMM's A operand in forward) */
 } mtus_gemm_desc;
 
 int mtus_gemm(const mtus_gemm_desc* desc, void* stream);
@@ -80,9 +100,15 @@ int mtus_gemm(const mtus_gemm_desc* desc, void* stream);
 int mtus_linear_fwd(const void* x, const void* w, const float* bias, void* y, void* gelu_pre, const void* res,
                     const float* rowscale, int rows_per_sample, int64_t M, int N, int K, int dtype, int backend,
                     void* stream);
-/* dx[M,K] = dy[M,N] w[N,K]  (optionally * GELU'(gelu_pre[M,K]), optionally scaled per sample) */
+/* y (fp32) = res (fp32, optional) + rowscale * (x w^T + bias): the Linear layers that write the fp32 residual
+ * stream (proj, fc2, PatchMerging reduction) */
+int mtus_linear_fwd_stream(const void* x, const void* w, const float* bias, float* y, const float* res,
+                           const float* rowscale, int rows_per_sample, int64_t M, int N, int K, int dtype, int backend,
+                           void* stream);
+/* dx[M,K] = dy[M,N] w[N,K]  (optionally * GELU'(gelu_pre[M,K]), optionally scaled per sample);
+ * dx_colsum [K] (may be NULL) += column sums of dx = the bias gradient of the Linear that produced gelu_pre */
 int mtus_linear_dgrad(const void* dy, const void* w, void* dx, const void* gelu_pre, const float* rowscale,
-                      int rows_per_sample, int64_t M, int N, int K, int dtype, int backend, void* stream);
+                      int rows_per_sample, float* dx_colsum, int64_t M, int N, int K, int dtype, int backend, void* stream);
 /* dw[N,K] += dy[M,N]^T x[M,K] (fp32, accumulated); db[N] += colsum(dy) when db != NULL */
 int mtus_linear_wgrad(const void* dy, const void* x, float* dw, float* db, int64_t M, int N, int K, int dtype,
                       int backend, void* stream);
@@ -93,6 +119,12 @@ int mtus_colsum(const void* x, float* out, int64_t rows, int C, int dtype, void*
 int mtus_scale_rows(const void* x, void* y, const float* rowscale, int rows_per_sample, int64_t rows, int C,
                     int dtype, void* stream);
 int mtus_add(const void* a, const void* b, void* y, int64_t n, int dtype, void* stream);
+/* fp32 gradient stream -> GEMM operand: y (dtype) = rowscale[row / rows_per_sample] * g, colsum [C] (may be NULL) += column sums of y */
+int mtus_scale_cast_colsum(const float* g, const float* rowscale, int rows_per_sample, void* y, float* colsum,
+                           int64_t rows, int C, int dtype, void* stream);
+/* [B][R][Cc] -> [B][R][Cc] (transpose = 0) or [B][Cc][R] (transpose = 1), element types fp32 (flag set) or dtype */
+int mtus_convert(const void* x, void* y, int B, int R, int Cc, int transpose, int in_f32, int out_f32, int dtype,
+                 void* stream);
 int mtus_nhwc_to_nchw(const void* x, void* y, int B, int HW, int C, int dtype, int out_f32, void* stream);
 int mtus_nchw_to_nhwc(const void* x, void* y, int B, int HW, int C, int dtype, int in_f32, void* stream);
 

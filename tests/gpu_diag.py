@@ -70,6 +70,67 @@ def g_elementwise():
             dx, dg, db = ops.patch_merge_ln_bwd(dy, x, g, mean, rstd)
             yr.backward(dy.float())
             ok &= report(f"merge_ln_bwd {dt} {B,H,W,Cc}", dx, xr.grad, tol)
+        # ---- mixed-precision LayerNorm family (fp32 residual stream) ----
+        for rows, Cc in ((1000, 96), (3137, 128), (300, 768), (200, 1024), (64, 3072)):
+            xs = torch.randn(rows, Cc, device=dev) * 2 + 0.5                       # fp32 stream
+            g = torch.randn(Cc, device=dev) * 0.5 + 1
+            b = torch.randn(Cc, device=dev) * 0.1
+            y, mean, rstd = ops.layernorm_fwd_mixed(xs, g, b, dt)
+            xr = xs.clone().requires_grad_(True)
+            gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+            yr = F.layer_norm(xr, (Cc,), gr, br, 1e-5)
+            ok &= report(f"lnx_fwd f32->{dt} [{rows},{Cc}]", y, yr, tol)
+            dy = torch.randn(rows, Cc, device=dev).to(dt)
+            dres = torch.randn(rows, Cc, device=dev)
+            rs = torch.rand(5, device=dev) + 0.5
+            rps = (rows + 4) // 5
+            dx, lp, cs, dg, db = ops.layernorm_bwd_mixed(dy, xs, g, mean, rstd, dres, lp_dtype=dt, rowscale=rs, rows_per_sample=rps)
+            yr.backward(dy.float())
+            ref_dx = xr.grad + dres
+            ok &= report(f"lnx_bwd dx (fp32 stream)", dx, ref_dx, 2e-5)
+            sc = rs[torch.arange(rows, device=dev) // rps][:, None]
+            ok &= report(f"lnx_bwd dx_lp (scaled operand copy)", lp, ref_dx * sc, tol)
+            ok &= report(f"lnx_bwd lp_colsum", cs, lp.float().sum(0), 2e-4)
+            ok &= report(f"lnx_bwd dgamma", dg, gr.grad, max(tol, 2e-4))
+            ok &= report(f"lnx_bwd dbeta", db, br.grad, max(tol, 2e-4))
+            # patch-embed form: low-precision input, fp32 output; backward with dy = fp32 stream, only the operand copy out
+            xl = (torch.randn(rows, Cc, device=dev) * 2).to(dt)
+            y2, mean2, rstd2 = ops.layernorm_fwd_mixed(xl, g, b, torch.float32)
+            xr2 = xl.float().requires_grad_(True)
+            yr2 = F.layer_norm(xr2, (Cc,), g, b, 1e-5)
+            ok &= report(f"lnx_fwd {dt}->f32", y2, yr2, 2e-5)
+            dyf = torch.randn(rows, Cc, device=dev)
+            _, lp2, cs2, _, _ = ops.layernorm_bwd_mixed(dyf, xl, g, mean2, rstd2, None, lp_dtype=dt, want_dx=False)
+            yr2.backward(dyf)
+            ok &= report(f"lnx_bwd (dy fp32, x {dt}) dx_lp", lp2, xr2.grad, tol)
+            ok &= report(f"lnx_bwd (dy fp32) colsum", cs2, lp2.float().sum(0), 2e-4)
+        for (B, H, W, Cc) in ((2, 8, 8, 32), (3, 7, 7, 64), (2, 14, 14, 128)):
+            xs = torch.randn(B, H, W, Cc, device=dev)
+            g = torch.randn(4 * Cc, device=dev) * 0.5 + 1
+            b = torch.randn(4 * Cc, device=dev) * 0.1
+            y, mean, rstd = ops.patch_merge_ln_fwd_mixed(xs, g, b, dt)
+            xr = xs.clone().requires_grad_(True)
+            xp = F.pad(xr, (0, 0, 0, W % 2, 0, H % 2))
+            Hp, Wp = xp.shape[1], xp.shape[2]
+            xg = xp.reshape(B, Hp // 2, 2, Wp // 2, 2, Cc).permute(0, 1, 3, 4, 2, 5).flatten(3)
+            yr = F.layer_norm(xg, (4 * Cc,), g, b, 1e-5)
+            ok &= report(f"merge_lnx_fwd f32->{dt} {B,H,W,Cc}", y, yr, tol)
+            dy = torch.randn_like(yr).to(dt)
+            dres = torch.randn(B, H, W, Cc, device=dev)
+            rs = torch.rand(B, device=dev) + 0.5
+            dx, lp, cs, dg, db = ops.patch_merge_ln_bwd_mixed(dy, xs, g, mean, rstd, dres, rowscale=rs)
+            yr.backward(dy.float())
+            ok &= report(f"merge_lnx_bwd dx", dx, xr.grad + dres, 2e-5)
+            ok &= report(f"merge_lnx_bwd dx_lp", lp, (xr.grad + dres) * rs[:, None, None, None], tol)
+            ok &= report(f"merge_lnx_bwd lp_colsum", cs, lp.float().sum((0, 1, 2)), 2e-4)
+        gs = torch.randn(777, 256, device=dev)
+        rs = torch.rand(7, device=dev) + 0.5
+        yq, cs = ops.scale_cast_colsum(gs, dt, rs, 111)
+        ok &= report(f"scale_cast_colsum {dt}", yq, gs * rs[torch.arange(777, device=dev) // 111][:, None], tol)
+        ok &= report(f"scale_cast_colsum sums", cs, yq.float().sum(0), 2e-4)
+        xc = torch.randn(3, 50, 40, device=dev)
+        ok &= report(f"convert f32->{dt} transpose", ops.convert(xc, dt, True), xc.transpose(1, 2), tol)
+        ok &= report(f"convert {dt}->f32", ops.convert(xc.to(dt), torch.float32), xc.to(dt).float(), 0)
         x = torch.randn(3, 7, 9, 40, device=dev).to(dt)
         ok &= report(f"nhwc_to_nchw {dt}", ops.nhwc_to_nchw(x), x.permute(0, 3, 1, 2), 0)
         ok &= report(f"nchw_to_nhwc {dt}", ops.nchw_to_nhwc(x.permute(0, 3, 1, 2).contiguous()), x, 0)
@@ -114,6 +175,11 @@ def _gemm_group(backend, dts):
             hpf = hp.float().requires_grad_(True)
             F.gelu(hpf).backward(dy.float() @ w.float())
             ok &= report(f"linear_dgrad*gelu'", dx2, hpf.grad, tol)
+            resf = torch.randn(M, N, device=dev)
+            ys = ops.linear_fwd_stream(x, w, bias, res=resf, rowscale=rs, rows_per_sample=rps, backend=backend)
+            ok &= report(f"linear_fwd_stream (fp32 out + fp32 residual)", ys, resf + sc * yr, max(tol * 0.05, 2e-5) if dt == torch.bfloat16 else tol)
+            dx3, cs3 = ops.linear_dgrad(dy, w, gelu_pre=hp, backend=backend, with_colsum=True)
+            ok &= report(f"linear_dgrad*gelu' + colsum", cs3, dx3.float().sum(0), 2e-4)
             dw, db = ops.linear_wgrad(dy, x, backend=backend)
             ok &= report(f"linear_wgrad dw", dw, dy.float().t() @ x.float(), max(tol, 1e-4))
             ok &= report(f"linear_wgrad db", db, dy.float().sum(0), max(tol, 1e-4))
