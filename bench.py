@@ -217,7 +217,7 @@ def _kernel_rooflines(peaks, device):
     fl = sum(g[1] for g in gemm)
     tt = sum(g[2] for g in gemm)
     ach = fl / tt / 1e12
-    res["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma + TMA + TMEM), Swin-B stage-3 forward GEMMs "
+    res["roofline"] = {"bound": "tensor", "kernel": "gemm_tc2_kernel (persistent tcgen05.mma + TMA + TMEM), Swin-B stage-3 forward GEMMs "
                        "qkv/proj/fc1/fc2 at M=6272", "achieved": round(ach, 1), "peak": peaks["tc_burst"], "unit": "TFLOP/s",
                        "frac": round(ach / peaks["tc_burst"], 4), "traffic": None,
                        "peak_source": f"{peaks['src']} (burst: kernel timed alone, L2 flushed between launches)",
@@ -386,7 +386,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--batch", type=int, default=32, help="images per GPU (the headline config uses 32)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
