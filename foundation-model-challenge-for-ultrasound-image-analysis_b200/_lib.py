@@ -88,8 +88,8 @@ SIGNATURES = {
     "mtus_groupnorm_relu_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_bilinear2x_fwd": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_bilinear2x_bwd": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
-    "mtus_fpn_merge_fwd": (i32, [_P(vp), i32, i32, vp, vp, i32, i32, i32, i32, i32, vp]),
-    "mtus_fpn_merge_bwd": (i32, [vp, i32, i32, vp, _P(vp), i32, i32, i32, i32, i32, vp]),
+    "mtus_fpn_merge_fwd": (i32, [_P(vp), i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "mtus_fpn_merge_bwd": (i32, [vp, i32, i32, vp, _P(vp), i32, i32, i32, i32, i32, i32, vp]),
     "mtus_conv3x3_repack": (i32, [vp, vp, vp, i32, i32, i32, vp]),
     "mtus_conv3x3_unpack_grad": (i32, [vp, vp, i32, i32, vp]),
     "mtus_conv3x3_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),

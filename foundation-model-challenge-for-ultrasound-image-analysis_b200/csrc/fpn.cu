@@ -463,14 +463,79 @@ __global__ void __launch_bounds__(256) merge_bwd_kernel(const TI* __restrict__ d
   }
 }
 
+// channels-last output: out[b, r, cg] = scale[b, cg] * src[s][b, r, c]  (8-wide vectors, coalesced on both sides)
+template <typename T, typename TO>
+__global__ void merge_nhwc_fwd_kernel(MergePtrs src, int nsrc, int cat, const float* __restrict__ chanscale, TO* __restrict__ out,
+                                      int64_t total, int HW, int C) {
+  const int Cout = cat ? nsrc * C : C, C8 = Cout / 8;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int cg = (int)(i % C8) * 8;
+    const int64_t pix = i / C8;                       // b*HW + r
+    const int64_t b = pix / HW;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (cat) {
+      const int s = cg / C, c = cg - s * C;
+      IO<T>::load8(reinterpret_cast<const T*>(src.p[s]) + pix * C + c, v);
+    } else {
+      for (int k = 0; k < nsrc; ++k) {
+        float t[8]; IO<T>::load8(reinterpret_cast<const T*>(src.p[k]) + pix * C + cg, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += t[j];
+      }
+    }
+    if (chanscale) {
+      float f[8]; IO<float>::load8(chanscale + b * Cout + cg, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= f[j];
+    }
+    IO<TO>::store8(out + pix * Cout + cg, v);
+  }
+}
+
+template <typename T, typename TI>
+__global__ void merge_nhwc_bwd_kernel(const TI* __restrict__ dout, int nsrc, int cat, const float* __restrict__ chanscale, MergeOutPtrs dst,
+                                      int64_t total, int HW, int C) {
+  const int Cout = cat ? nsrc * C : C, C8 = Cout / 8;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int cg = (int)(i % C8) * 8;
+    const int64_t pix = i / C8;
+    const int64_t b = pix / HW;
+    float v[8];
+    IO<TI>::load8(dout + pix * Cout + cg, v);
+    if (chanscale) {
+      float f[8]; IO<float>::load8(chanscale + b * Cout + cg, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= f[j];
+    }
+    if (cat) {
+      const int s = cg / C, c = cg - s * C;
+      IO<T>::store8(reinterpret_cast<T*>(dst.p[s]) + pix * C + c, v);
+    } else {
+      for (int k = 0; k < nsrc; ++k) IO<T>::store8(reinterpret_cast<T*>(dst.p[k]) + pix * C + cg, v);
+    }
+  }
+}
+
 extern "C" int mtus_fpn_merge_fwd(const void* const* srcs, int nsrc, int policy_cat, const float* chanscale, void* out,
-                                  int B, int HW, int C, int dtype, int out_f32, void* stream) {
+                                  int B, int HW, int C, int dtype, int out_f32, int out_nhwc, void* stream) {
   MTUS_CHECK_ARG(srcs && out && nsrc >= 1 && nsrc <= 4 && C % 32 == 0 && B <= 65535);
   if (B == 0) return MTUS_OK;
   MergePtrs mp{};
   for (int i = 0; i < nsrc; ++i) { MTUS_CHECK_ARG(srcs[i]); mp.p[i] = srcs[i]; }
   dim3 grid((policy_cat ? nsrc * C : C) / 32, ceil_div(HW, 32), B);
   cudaStream_t st = (cudaStream_t)stream;
+  if (out_nhwc) {
+    const int64_t total = (int64_t)B * HW * ((policy_cat ? nsrc * C : C) / 8);
+    const int g1 = grid_for(total, 256);
+    if (dtype == MTUS_F32) merge_nhwc_fwd_kernel<float, float><<<g1, 256, 0, st>>>(mp, nsrc, policy_cat, chanscale, (float*)out, total, HW, C);
+    else if (dtype == MTUS_BF16 && out_f32) merge_nhwc_fwd_kernel<bf16, float><<<g1, 256, 0, st>>>(mp, nsrc, policy_cat, chanscale, (float*)out, total, HW, C);
+    else if (dtype == MTUS_BF16) merge_nhwc_fwd_kernel<bf16, bf16><<<g1, 256, 0, st>>>(mp, nsrc, policy_cat, chanscale, (bf16*)out, total, HW, C);
+    else return MTUS_ERR_UNSUPPORTED;
+    MTUS_LAUNCH_STATUS();
+    return MTUS_OK;
+  }
   if (dtype == MTUS_F32) merge_fwd_kernel<float, float><<<grid, 256, 0, st>>>(mp, nsrc, policy_cat, chanscale, (float*)out, HW, C);
   else if (dtype == MTUS_BF16) {
     if (out_f32) merge_fwd_kernel<bf16, float><<<grid, 256, 0, st>>>(mp, nsrc, policy_cat, chanscale, (float*)out, HW, C);
@@ -481,13 +546,23 @@ extern "C" int mtus_fpn_merge_fwd(const void* const* srcs, int nsrc, int policy_
 }
 
 extern "C" int mtus_fpn_merge_bwd(const void* dout, int nsrc, int policy_cat, const float* chanscale, void* const* dsrcs,
-                                  int B, int HW, int C, int dtype, int in_f32, void* stream) {
+                                  int B, int HW, int C, int dtype, int in_f32, int in_nhwc, void* stream) {
   MTUS_CHECK_ARG(dout && dsrcs && nsrc >= 1 && nsrc <= 4 && C % 32 == 0 && B <= 65535);
   if (B == 0) return MTUS_OK;
   MergeOutPtrs mp{};
   for (int i = 0; i < nsrc; ++i) { MTUS_CHECK_ARG(dsrcs[i]); mp.p[i] = dsrcs[i]; }
   dim3 grid((policy_cat ? nsrc * C : C) / 32, ceil_div(HW, 32), B);
   cudaStream_t st = (cudaStream_t)stream;
+  if (in_nhwc) {
+    const int64_t total = (int64_t)B * HW * ((policy_cat ? nsrc * C : C) / 8);
+    const int g1 = grid_for(total, 256);
+    if (dtype == MTUS_F32) merge_nhwc_bwd_kernel<float, float><<<g1, 256, 0, st>>>((const float*)dout, nsrc, policy_cat, chanscale, mp, total, HW, C);
+    else if (dtype == MTUS_BF16 && in_f32) merge_nhwc_bwd_kernel<bf16, float><<<g1, 256, 0, st>>>((const float*)dout, nsrc, policy_cat, chanscale, mp, total, HW, C);
+    else if (dtype == MTUS_BF16) merge_nhwc_bwd_kernel<bf16, bf16><<<g1, 256, 0, st>>>((const bf16*)dout, nsrc, policy_cat, chanscale, mp, total, HW, C);
+    else return MTUS_ERR_UNSUPPORTED;
+    MTUS_LAUNCH_STATUS();
+    return MTUS_OK;
+  }
   if (dtype == MTUS_F32) merge_bwd_kernel<float, float><<<grid, 256, 0, st>>>((const float*)dout, nsrc, policy_cat, chanscale, mp, HW, C);
   else if (dtype == MTUS_BF16) {
     if (in_f32) merge_bwd_kernel<bf16, float><<<grid, 256, 0, st>>>((const float*)dout, nsrc, policy_cat, chanscale, mp, HW, C);

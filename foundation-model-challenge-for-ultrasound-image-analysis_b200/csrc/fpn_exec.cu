@@ -189,7 +189,7 @@ extern "C" int mtus_fpn_forward(const mtus_fpn_config* cfg, const void* const* f
     }
     merged[i] = x;
   }
-  RUN(mtus_fpn_merge_fwd(merged, 4, p.cat, chanscale, out, p.B, p.size[0] * p.size[0], p.S, dt, out_f32, stream));
+  RUN(mtus_fpn_merge_fwd(merged, 4, p.cat, chanscale, out, p.B, p.size[0] * p.size[0], p.S, dt, out_f32 & 1, (out_f32 >> 1) & 1, stream));
   return MTUS_OK;
 }
 
@@ -216,7 +216,7 @@ extern "C" int mtus_fpn_backward(const mtus_fpn_config* cfg, const void* const* 
   // merge backward: dout (NCHW) x Dropout2d scale -> four NHWC tower-output gradients
   void* dm[4];
   for (int i = 0; i < 4; ++i) dm[i] = A(p.gM[i]);
-  RUN(mtus_fpn_merge_bwd(dout, 4, p.cat, chanscale, dm, p.B, HW0, p.S, dt, dout_f32, stream));
+  RUN(mtus_fpn_merge_bwd(dout, 4, p.cat, chanscale, dm, p.B, HW0, p.S, dt, dout_f32 & 1, (dout_f32 >> 1) & 1, stream));
 
   // towers backward: leaves the gradient w.r.t. p_k in gP[k].  Buffer discipline per layer:
   //   g --bilinear'--> s1 (if upsampling) --GN/ReLU'--> dt (s2 | s1) --dgrad--> old g buffer (dead by then)

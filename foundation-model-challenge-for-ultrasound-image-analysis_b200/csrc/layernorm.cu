@@ -490,11 +490,255 @@ __global__ void __launch_bounds__(128) lnx_bwd_kernel(LnxBwdArgs a, MergeGeom g)
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// v2 kernels for C <= 1024: LPR lanes per row (a warp works on 32/LPR rows at once), NV 8-element vectors per lane,
+// U row groups in flight per iteration -- every lane is busy for narrow rows (C = 96..256) and each lane has
+// several 16/32-byte loads outstanding, which is what an HBM-bound kernel needs.
+// -------------------------------------------------------------------------------------------------
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename TX, typename TY, int LPR, int NV, int U, int MODE>
+__global__ void __launch_bounds__(128) lnv2_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, TY* __restrict__ y,
+                                                       float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                       int64_t rows, int C, float eps, MergeGeom g) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+  const int64_t gwarp = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 4;
+  const float invC = 1.0f / (float)C;
+  float gm[NV][8], bt[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = (i * LPR + sub) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { gm[i][k] = 0.f; bt[i][k] = 0.f; }
+    if (col < C) { IO<float>::load8(gamma + col, gm[i]); IO<float>::load8(beta + col, bt[i]); }
+  }
+  for (int64_t row0 = gwarp * (RPW * U); row0 < rows; row0 += nwarps * (RPW * U)) {
+    float v[U][NV][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + u * RPW + grp;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int col = (i * LPR + sub) * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[u][i][k] = 0.f;
+        if (row < rows && col < C) {
+          bool valid; const TX* p = ln_src<TX, MODE>(x, row, col, C, g, valid);
+          if (valid) IO<TX>::load8(p, v[u][i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + u * RPW + grp;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += v[u][i][k];
+      const float mean = group_sum<LPR>(s) * invC;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int col = (i * LPR + sub) * 8;
+        if (col < C) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { const float d = v[u][i][k] - mean; q += d * d; }
+        }
+      }
+      const float rstd = rsqrtf(group_sum<LPR>(q) * invC + eps);
+      if (row < rows) {
+        if (sub == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int col = (i * LPR + sub) * 8;
+          if (col < C) {
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = (v[u][i][k] - mean) * rstd * gm[i][k] + bt[i][k];
+            IO<TY>::store8(y + row * C + col, o);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <typename T, typename TDY, typename TX, int LPR, int NV, int MODE>
+__global__ void __launch_bounds__(128) lnv2_bwd_kernel(LnxBwdArgs a, MergeGeom g) {
+  constexpr int RPW = 32 / LPR;
+  extern __shared__ float acc_smem[];                         // [3][4 warps][C] partial dgamma / dbeta / colsum
+  const TDY* __restrict__ dy = reinterpret_cast<const TDY*>(a.dy);
+  const TX* __restrict__ x = reinterpret_cast<const TX*>(a.x);
+  T* __restrict__ dx_lp = reinterpret_cast<T*>(a.dx_lp);
+  const int C = a.C;
+  const int64_t rows = a.rows;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+  const int64_t gwarp = (int64_t)blockIdx.x * 4 + warp, nwarps = (int64_t)gridDim.x * 4;
+  const float invC = 1.0f / (float)C;
+  const bool want_cs = a.lp_colsum != nullptr;
+  float gm[NV][8], adg[NV][8], adb[NV][8], acs[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = (i * LPR + sub) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { gm[i][k] = 0.f; adg[i][k] = 0.f; adb[i][k] = 0.f; acs[i][k] = 0.f; }
+    if (col < C) IO<float>::load8(a.gamma + col, gm[i]);
+  }
+  for (int64_t row0 = gwarp * RPW; row0 < rows; row0 += nwarps * RPW) {
+    const int64_t row = row0 + grp;
+    const bool active = row < rows;
+    const float mean = active ? a.mean[row] : 0.f, rstd = active ? a.rstd[row] : 0.f;
+    float xh[NV][8], gy[NV][8];
+    int64_t off[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * LPR + sub) * 8;
+      off[i] = -1;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { xh[i][k] = 0.f; gy[i][k] = 0.f; }
+      if (active && col < C) {
+        float xv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dv[8];
+        bool valid; const TX* p = ln_src<TX, MODE>(x, row, col, C, g, valid);
+        if (valid) { IO<TX>::load8(p, xv); off[i] = p - x; }
+        IO<TDY>::load8(dy + row * C + col, dv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          xh[i][k] = (xv[k] - mean) * rstd;
+          gy[i][k] = dv[k] * gm[i][k];
+          s1 += gy[i][k];
+          s2 += gy[i][k] * xh[i][k];
+          adg[i][k] += dv[k] * xh[i][k];
+          adb[i][k] += dv[k];
+        }
+      }
+    }
+    s1 = group_sum<LPR>(s1) * invC; s2 = group_sum<LPR>(s2) * invC;
+    if (active) {
+      const float rsc = a.lp_rowscale ? __ldg(a.lp_rowscale + row / a.rows_per_sample) : 1.0f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (off[i] >= 0) {
+          float o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = rstd * (gy[i][k] - s1 - xh[i][k] * s2);
+          if (a.dres) {
+            float r[8]; IO<float>::load8(a.dres + off[i], r);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] += r[k];
+          }
+          if (a.dx) IO<float>::store8(a.dx + off[i], o);
+          if (dx_lp) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] *= rsc;
+            IO<T>::store8(dx_lp + off[i], o);
+            if (want_cs) {
+              float rr[8]; IO<T>::load8_reg(o, rr);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) acs[i][k] += rr[k];
+            }
+          }
+        }
+      }
+    }
+  }
+  // reduce the per-lane partials over the row groups of the warp, the warps of the block, then one atomic per column
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+      for (int o = LPR; o < 32; o <<= 1) {
+        adg[i][k] += __shfl_xor_sync(0xffffffffu, adg[i][k], o);
+        adb[i][k] += __shfl_xor_sync(0xffffffffu, adb[i][k], o);
+        acs[i][k] += __shfl_xor_sync(0xffffffffu, acs[i][k], o);
+      }
+    }
+  float* sg = acc_smem; float* sb = acc_smem + 4 * C; float* sc = acc_smem + 8 * C;
+  if (grp == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * LPR + sub) * 8;
+      if (col < C) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sg[warp * C + col + k] = adg[i][k]; sb[warp * C + col + k] = adb[i][k]; sc[warp * C + col + k] = acs[i][k]; }
+      }
+    }
+  }
+  __syncthreads();
+  const int Cc = (MODE == 0) ? C : g.C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(a.dgamma + c, sg[c] + sg[C + c] + sg[2 * C + c] + sg[3 * C + c]);
+    atomicAdd(a.dbeta + c, sb[c] + sb[C + c] + sb[2 * C + c] + sb[3 * C + c]);
+    if (want_cs) atomicAdd(a.lp_colsum + (c % Cc), sc[c] + sc[C + c] + sc[2 * C + c] + sc[3 * C + c]);
+  }
+}
+
+template <typename TX, typename TY, int MODE>
+static int lnv2_fwd_launch(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int64_t rows, int C,
+                           float eps, MergeGeom g, cudaStream_t st) {
+  const int nvec = C / 8;
+#define V2F(LPR_, NV_, U_)                                                                                               \
+  {                                                                                                                      \
+    const int rpi = (32 / LPR_) * U_ * 4;                                                                                \
+    int64_t blocks = (rows + rpi - 1) / rpi;                                                                             \
+    if (blocks > 148 * 8) blocks = 148 * 8;                                                                              \
+    lnv2_fwd_kernel<TX, TY, LPR_, NV_, U_, MODE><<<(int)blocks, 128, 0, st>>>((const TX*)x, gamma, beta, (TY*)y, mean, rstd, rows, C, eps, g); \
+  }
+  if (nvec <= 4) V2F(4, 1, 4)
+  else if (nvec <= 8) V2F(8, 1, 4)
+  else if (nvec <= 16) V2F(16, 1, 4)
+  else if (nvec <= 32) V2F(32, 1, 4)
+  else if (nvec <= 64) V2F(32, 2, 2)
+  else if (nvec <= 96) V2F(32, 3, 1)
+  else V2F(32, 4, 1)
+#undef V2F
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}
+
+template <typename T, typename TDY, typename TX, int MODE>
+static int lnv2_bwd_launch(const LnxBwdArgs& a, MergeGeom g, cudaStream_t st) {
+  const int C = a.C, nvec = C / 8;
+  const size_t sm = (size_t)12 * C * sizeof(float);
+#define V2B(LPR_, NV_)                                                                                       \
+  {                                                                                                          \
+    const int rpi = (32 / LPR_) * 4;                                                                         \
+    int64_t blocks = (a.rows + rpi - 1) / rpi;                                                               \
+    if (blocks > 148 * 6) blocks = 148 * 6;                                                                  \
+    auto kern = lnv2_bwd_kernel<T, TDY, TX, LPR_, NV_, MODE>;                                                \
+    if (sm > 48 * 1024) {                                                                                    \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);      \
+      if (e != cudaSuccess) return (int)e;                                                                   \
+    }                                                                                                        \
+    kern<<<(int)blocks, 128, sm, st>>>(a, g);                                                                \
+  }
+  if (nvec <= 4) V2B(4, 1)
+  else if (nvec <= 8) V2B(8, 1)
+  else if (nvec <= 16) V2B(16, 1)
+  else if (nvec <= 32) V2B(32, 1)
+  else if (nvec <= 64) V2B(32, 2)
+  else if (nvec <= 96) V2B(32, 3)
+  else V2B(32, 4)
+#undef V2B
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}
+
 template <typename TX, typename TY, int MODE>
 static int lnx_fwd_launch(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int64_t rows, int C,
                           float eps, MergeGeom g, cudaStream_t st) {
   if (rows == 0) return MTUS_OK;
   MTUS_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 4096);
+  if (C <= 1024) return lnv2_fwd_launch<TX, TY, MODE>(x, gamma, beta, y, mean, rstd, rows, C, eps, g, st);
   const int nvec = C / 8;
 #define LNX_CASE(NV_, WPR_)                                                                                                \
   {                                                                                                                        \
@@ -520,12 +764,13 @@ static int lnx_bwd_launch(const LnxBwdArgs& a, MergeGeom g, cudaStream_t st) {
   if (a.rows == 0) return MTUS_OK;
   const int C = a.C;
   MTUS_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 4096);
+  if (C <= 1024) return lnv2_bwd_launch<T, TDY, TX, MODE>(a, g, st);
   const int nvec = C / 8;
 #define LNX_CASE(NV_, WPR_)                                                                                  \
   {                                                                                                          \
     const int rpb = 4 / WPR_;                                                                                \
     int64_t blocks = (a.rows + rpb - 1) / rpb;                                                               \
-    if (blocks > 148 * 4) blocks = 148 * 4;                                                                  \
+    if (blocks > (WPR_ == 1 ? 148 * 4 : 148)) blocks = (WPR_ == 1 ? 148 * 4 : 148);                          \
     const size_t sm = (WPR_ == 1) ? (size_t)12 * C * sizeof(float) : 0;                                      \
     auto kern = lnx_bwd_kernel<T, TDY, TX, NV_, WPR_, MODE>;                                                 \
     if (sm > 48 * 1024) {                                                                                    \

@@ -42,7 +42,8 @@ class FPNDecoder(FlatParamModule):
     """smp ``FPNDecoder`` (constructor exactly as used at decoders.py:42-49)."""
 
     def __init__(self, encoder_channels, encoder_depth=5, pyramid_channels=256, segmentation_channels=128,
-                 dropout=0.2, merge_policy="add", precision: Optional[str] = None, output_dtype: Optional[str] = None):
+                 dropout=0.2, merge_policy="add", precision: Optional[str] = None, output_dtype: Optional[str] = None,
+                 channels_last_output: bool = True):
         super().__init__()
         if merge_policy not in ("add", "cat"):
             raise ValueError("`merge_policy` must be one of: ['add', 'cat'], got {}".format(merge_policy))
@@ -56,6 +57,9 @@ class FPNDecoder(FlatParamModule):
         self.merge_policy, self.p_drop = merge_policy, float(dropout)
         self.precision = precision or default_precision()
         self.output_dtype = output_dtype
+        # the [B, C, H, W] result is laid out channels-last in memory (what the kernels produce natively and what
+        # cuDNN wants for the heads' convolutions); shape and values are those of the reference's NCHW tensor
+        self.channels_last_output = bool(channels_last_output)
         self.backend = _lib.BACKEND_AUTO
         cfg = self._cfg(1, [8, 4, 2, 1], True)
         L = _lib.lib()
@@ -119,10 +123,14 @@ class FPNDecoder(FlatParamModule):
             keep = 1.0 - self.p_drop
             scale = ((torch.rand(B, self.out_channels, device=x0.device) < keep).float() / keep).contiguous()
         out_f32 = (self.output_dtype in ("fp32", "float32") or f32_in) and dt != _lib.F32
-        out = torch.empty(B, self.out_channels, sizes[0], sizes[0], dtype=torch.float32 if (out_f32 or dt == _lib.F32) else tdt,
-                          device=x0.device)
+        odt = torch.float32 if (out_f32 or dt == _lib.F32) else tdt
+        if self.channels_last_output:
+            out = torch.empty(B, sizes[0], sizes[0], self.out_channels, dtype=odt, device=x0.device).permute(0, 3, 1, 2)
+        else:
+            out = torch.empty(B, self.out_channels, sizes[0], sizes[0], dtype=odt, device=x0.device)
         _lib.check(L.mtus_fpn_forward(C.byref(cfg), _lib.ptr_array(feats), int(nhwc), int(f32_in), _lib.ptr(flat),
-                                      _lib.ptr(scale), _lib.ptr(ws), _lib.ptr(out), int(out_f32), _lib.stream_ptr()),
+                                      _lib.ptr(scale), _lib.ptr(ws), _lib.ptr(out), int(out_f32) | (2 if self.channels_last_output else 0),
+                                      _lib.stream_ptr()),
                    "fpn_forward")
         saved = (cfg, ws, feats, nhwc, f32_in, flat, scale, out_f32) if training_plan else None
         return out, saved
@@ -132,7 +140,10 @@ class FPNDecoder(FlatParamModule):
         L = _lib.lib()
         dt, tdt = precision_to_dtype(self.precision)
         want_out = torch.float32 if (out_f32 or dt == _lib.F32) else tdt
-        dout = dout.to(want_out).contiguous()
+        dout = dout.to(want_out)
+        dout_nhwc = is_channels_last_view(dout)
+        if not dout_nhwc:
+            dout = dout.contiguous()
         flat_grad = torch.zeros(self._n_flat, dtype=torch.float32, device=flat.device)
         dfeats = []
         for f in feats:
@@ -142,7 +153,7 @@ class FPNDecoder(FlatParamModule):
             else:
                 dfeats.append(torch.empty_like(f))
         _lib.check(L.mtus_fpn_backward(C.byref(cfg), _lib.ptr_array(feats), int(nhwc), int(f32_in), _lib.ptr(flat),
-                                       _lib.ptr(scale), _lib.ptr(ws), _lib.ptr(dout), int(want_out == torch.float32 and dt != _lib.F32),
+                                       _lib.ptr(scale), _lib.ptr(ws), _lib.ptr(dout), int(want_out == torch.float32 and dt != _lib.F32) | (2 if dout_nhwc else 0),
                                        _lib.ptr_array(dfeats), int(nhwc), int(f32_in), _lib.ptr(flat_grad), _lib.stream_ptr()),
                    "fpn_backward")
         return [g if n else None for g, n in zip(dfeats, feat_needs)], flat_grad

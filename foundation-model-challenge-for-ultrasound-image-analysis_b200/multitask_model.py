@@ -43,6 +43,8 @@ class MultiTaskModel(nn.Module):
         self.heads = build_all_heads(self.task_configs, self.fpn_out_channels, encoder_channels,
                                      config.config.get("model", {}) if hasattr(config, "config") else {})
         self.task_id_to_name = {c["task_id"]: c["task_name"] for c in self.task_configs}
+        # the FPN hands channels-last tensors to the heads: keep their conv weights in the matching memory format
+        self.heads.to(memory_format=torch.channels_last)
 
     def _head(self, task_id, x):
         # the heads are plain PyTorch modules with fp32 parameters: run them under autocast in bf16 mode

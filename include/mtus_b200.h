@@ -173,11 +173,11 @@ int mtus_groupnorm_relu_bwd(const void* dy, const void* x, const void* y, const 
 int mtus_bilinear2x_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
 int mtus_bilinear2x_bwd(const void* dy, void* dx, int B, int H, int W, int C, int dtype, void* stream);
 /* merge: nsrc NHWC maps [B,HW,C] -> NCHW out [B, nsrc*C (cat) | C (add), HW], times chanscale[b, c_out]
- * (Dropout2d mask / (1-p); NULL = identity).  out dtype fp32 when out_f32. */
+ * (Dropout2d mask / (1-p); NULL = identity).  out dtype fp32 when out_f32; out_nhwc: channels-last output. */
 int mtus_fpn_merge_fwd(const void* const* srcs, int nsrc, int policy_cat, const float* chanscale, void* out, int B,
-                       int HW, int C, int dtype, int out_f32, void* stream);
+                       int HW, int C, int dtype, int out_f32, int out_nhwc, void* stream);
 int mtus_fpn_merge_bwd(const void* dout, int nsrc, int policy_cat, const float* chanscale, void* const* dsrcs, int B,
-                       int HW, int C, int dtype, int in_f32, void* stream);
+                       int HW, int C, int dtype, int in_f32, int in_nhwc, void* stream);
 /* repack Conv2d weight [Cout,Cin,3,3] fp32 -> fwd [Cout, 9*Cin] and dgrad [Cin, 9*Cout] (taps flipped) */
 int mtus_conv3x3_repack(const float* w, void* w_fwd, void* w_dgrad, int Cout, int Cin, int dtype, void* stream);
 /* dw[Cout,Cin,3,3] (fp32, ACCUMULATED) from the packed [Cout, 9*Cin] gradient */
@@ -241,7 +241,8 @@ int64_t mtus_fpn_param_count(const mtus_fpn_config* cfg);
 int64_t mtus_fpn_workspace_bytes(const mtus_fpn_config* cfg);
 int mtus_fpn_param_info(const mtus_fpn_config* cfg, int idx, char* name, int64_t* offset, int* rank, int64_t* shape);
 /* feats[4]: encoder features c2..c5 (feats_layout 0 NCHW | 1 NHWC); chanscale: [B, out_channels]
- * Dropout2d scales or NULL; out: NCHW [B, out_channels, S2, S2]. */
+ * Dropout2d scales or NULL; out: [B, out_channels, S2, S2].  out_f32 / dout_f32 are bit flags: bit 0 = fp32
+ * elements, bit 1 = channels-last (NHWC) memory instead of NCHW. */
 int mtus_fpn_forward(const mtus_fpn_config* cfg, const void* const* feats, int feats_layout, int feats_f32,
                      const float* params, const float* chanscale, void* workspace, void* out, int out_f32,
                      void* stream);
