@@ -55,8 +55,10 @@ extern "C" int mtus_gemm(const mtus_gemm_desc* d, void* stream) {
 }
 
 static int pick_splits(int64_t tiles, int64_t k_blocks) {
-  // enough CTAs for ~2 waves of 148 SMs x 2 resident CTAs, each split keeping >= 4 k-blocks
-  int64_t want = (148 * 4 + tiles - 1) / tiles;
+  // persistent engine, 1 CTA per SM: MTUS_SPLITK_WAVES (default 4) waves of work items, each split keeping >= 4 k-blocks
+  static int waves = 0;
+  if (!waves) { const char* e = getenv("MTUS_SPLITK_WAVES"); waves = e ? atoi(e) : 4; if (waves < 1) waves = 1; }
+  int64_t want = (148 * waves + tiles - 1) / tiles;
   int64_t maxs = k_blocks / 4;
   if (maxs < 1) maxs = 1;
   if (want > maxs) want = maxs;
