@@ -18,13 +18,14 @@ from .encoders import build_encoder, SwinTransformerEncoder, SwinCore, SWIN_MODE
 from .decoders import build_fpn_decoder, build_decoders, FPNDecoder
 from .heads import build_all_heads, build_task_head
 from .losses import build_all_losses, compute_task_loss
-from .multitask_model import MultiTaskModel, build_model, build_optimizer
+from .multitask_model import MultiTaskModel, build_model, build_optimizer, build_flat_optimizer
+from .optim import FlatAdamW
 from .parallel import DistributedTaskSampler, GradAllReducer, DataParallelTrainer, synthetic_batch
 
 __all__ = [
     "build_encoder", "SwinTransformerEncoder", "SwinCore", "SWIN_MODEL_MAPPING", "SWIN_ARCHS",
     "build_fpn_decoder", "build_decoders", "FPNDecoder", "build_all_heads", "build_task_head",
-    "build_all_losses", "compute_task_loss", "MultiTaskModel", "build_model", "build_optimizer",
+    "build_all_losses", "compute_task_loss", "MultiTaskModel", "build_model", "build_optimizer", "build_flat_optimizer", "FlatAdamW",
     "Config", "make_config", "swin_b_27task", "tasks_27",
     "DistributedTaskSampler", "GradAllReducer", "DataParallelTrainer", "synthetic_batch",
 ]

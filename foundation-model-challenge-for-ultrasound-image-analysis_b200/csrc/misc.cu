@@ -329,3 +329,69 @@ extern "C" int mtus_convert(const void* x, void* y, int B, int R, int Cc, int tr
   MTUS_LAUNCH_STATUS();
   return MTUS_OK;
 }
+
+// ---- flat AdamW (decoupled weight decay) over a contiguous fp32 parameter block, with the global-norm clip
+//      coefficient read from device memory (no host sync): torch.optim.AdamW update rule (code/train.py:208,446,455) ----
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n4, float* __restrict__ out) {
+  float acc = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  acc = warp_sum(acc);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    atomicAdd(out, s);
+  }
+}
+
+extern "C" int mtus_sumsq(const float* g, int64_t n, float* out, void* stream) {
+  MTUS_CHECK_ARG(g && out && n >= 0 && n % 4 == 0 && ((uintptr_t)g & 15) == 0);
+  if (n == 0) return MTUS_OK;
+  sumsq_kernel<<<grid_for(n / 4, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(g, n / 4, out);
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}
+
+__global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                         float* __restrict__ v, int64_t n4, float lr, float beta1, float beta2, float eps,
+                                                         float wd, float bc1, float bc2_sqrt, const float* __restrict__ grad_scale) {
+  const float gs = grad_scale ? __ldg(grad_scale) : 1.0f;
+  const float decay = 1.0f - lr * wd, step = lr / bc1, inv_bc2 = 1.0f / bc2_sqrt;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    float* P = &pp.x; const float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = G[k] * gs;
+      P[k] *= decay;
+      M[k] = M[k] + (1.0f - beta1) * (gk - M[k]);          // lerp
+      V[k] = beta2 * V[k] + (1.0f - beta2) * gk * gk;
+      const float denom = sqrtf(V[k]) * inv_bc2 + eps;
+      P[k] -= step * (M[k] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+}
+
+extern "C" int mtus_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                               float weight_decay, int step, const float* grad_scale, void* stream) {
+  MTUS_CHECK_ARG(p && g && m && v && n >= 0 && n % 4 == 0 && step >= 1);
+  MTUS_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+  if (n == 0) return MTUS_OK;
+  const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+  adamw_flat_kernel<<<grid_for(n / 4, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n / 4, lr, beta1, beta2, eps, weight_decay,
+                                                                                   bc1, sqrtf(bc2), grad_scale);
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}

@@ -156,6 +156,7 @@ class FPNDecoder(FlatParamModule):
                                        _lib.ptr(scale), _lib.ptr(ws), _lib.ptr(dout), int(want_out == torch.float32 and dt != _lib.F32) | (2 if dout_nhwc else 0),
                                        _lib.ptr_array(dfeats), int(nhwc), int(f32_in), _lib.ptr(flat_grad), _lib.stream_ptr()),
                    "fpn_backward")
+        self._last_flat_grad = flat_grad
         return [g if n else None for g, n in zip(dfeats, feat_needs)], flat_grad
 
     def forward(self, features: List[torch.Tensor]) -> torch.Tensor:

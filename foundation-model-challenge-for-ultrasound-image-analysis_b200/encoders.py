@@ -224,6 +224,7 @@ class SwinCore(FlatParamModule):
                 if lo == 0:
                     s_lo = self._stage_slices[0][0]        # patch_embed gradients finish with stage 0
                 hook(flat_grad, s_lo, s_hi)
+        self._last_flat_grad = flat_grad
         return flat_grad
 
     def forward(self, x: torch.Tensor) -> List[torch.Tensor]:

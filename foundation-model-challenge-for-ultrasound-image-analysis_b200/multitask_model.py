@@ -105,6 +105,17 @@ def build_model(config, precision=None, zero_copy_features=True):
     return model
 
 
+def build_flat_optimizer(model, config):
+    """Same rule and grouping as ``build_optimizer`` + ``clip_grad_norm_(training.gradient_clip)``, but the encoder and
+    the FPN decoders are updated with one kernel per flat parameter block (optim.FlatAdamW)."""
+    from .optim import FlatAdamW
+    return FlatAdamW(model, lr=float(config.get("training.optimizer.learning_rate", 1e-4)),
+                     weight_decay=float(config.get("training.optimizer.weight_decay", 1e-4)),
+                     encoder_lr_multiplier=float(config.get("training.optimizer.encoder_lr_multiplier", 0.1)),
+                     head_lr_multiplier=float(config.get("training.optimizer.head_lr_multiplier", 1.0)),
+                     max_grad_norm=float(config.get("training.gradient_clip", 1.0)))
+
+
 def build_optimizer(model, config, fused=None):
     """AdamW with the reference's grouped learning rates (code/train.py:176-219): encoder x0.1, heads x1.0.
     ``fused=True`` selects torch's multi-tensor fused CUDA AdamW (same update rule)."""

@@ -1,0 +1,110 @@
+"""AdamW + global-norm gradient clipping over the flat parameter blocks of the native modules.
+
+Same update rule and step semantics as the reference's ``torch.optim.AdamW`` + ``clip_grad_norm_``
+(``/root/reference/code/train.py:176-219, 446, 455``): grouped learning rates (encoder x0.1, heads x1.0), decoupled
+weight decay, parameters that received no gradient this step are skipped entirely (no decay, no moment update).
+The Swin encoder and each FPN decoder own ONE contiguous fp32 parameter block and ONE gradient block, so their update is
+a single kernel each (``mtus_adamw_flat``) instead of a multi-tensor sweep over ~330 tensors; the clip coefficient
+stays on the device.  Everything that is not a flat module (the PyTorch task heads) goes through torch's own AdamW.
+"""
+
+from typing import Dict, List
+
+import torch
+
+from . import _lib
+from ._native import FlatParamModule
+
+
+class FlatAdamW:
+    def __init__(self, model, lr: float = 1e-4, weight_decay: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 encoder_lr_multiplier: float = 0.1, head_lr_multiplier: float = 1.0, max_grad_norm: float = 1.0):
+        self.model = model
+        self.betas, self.eps, self.wd = betas, float(eps), float(weight_decay)
+        self.max_norm = float(max_grad_norm)
+        enc_params, head_params = model.get_trainable_parameters()
+        enc_ids = {id(p) for p in enc_params}
+        self.flat: List[Dict] = []
+        flat_ids = set()
+        for mod in model.modules():
+            if isinstance(mod, FlatParamModule):
+                ps = mod.ordered_params()
+                if not all(p.requires_grad for p in ps):
+                    continue                                 # partially frozen block: leave it to torch
+                is_enc = all(id(p) in enc_ids for p in ps)
+                self.flat.append({"module": mod, "lr": lr * (encoder_lr_multiplier if is_enc else head_lr_multiplier),
+                                  "m": None, "v": None, "step": 0})
+                flat_ids |= {id(p) for p in ps}
+        rest_enc = [p for p in enc_params if id(p) not in flat_ids]
+        rest_head = [p for p in head_params if id(p) not in flat_ids]
+        groups = []
+        if rest_enc:
+            groups.append({"params": rest_enc, "lr": lr * encoder_lr_multiplier})
+        if rest_head:
+            groups.append({"params": rest_head, "lr": lr * head_lr_multiplier})
+        self.rest_params = rest_enc + rest_head
+        self.torch_opt = torch.optim.AdamW(groups, lr=lr, weight_decay=weight_decay, betas=betas, eps=eps,
+                                           fused=bool(groups) and all(p.is_cuda for p in self.rest_params)) if groups else None
+
+    # -- torch.optim.Optimizer-like surface used by the trainer ---------------------------------------------------
+    def zero_grad(self, set_to_none: bool = True):
+        for p in self.model.parameters():
+            p.grad = None
+        for f in self.flat:
+            f["module"]._last_flat_grad = None
+
+    def _flat_grad(self, f):
+        g = getattr(f["module"], "_last_flat_grad", None)
+        if g is None:
+            return None
+        # the module handed views of this buffer to autograd as .grad; somebody may have replaced them
+        first = f["module"].ordered_params()[0]
+        if first.grad is None or first.grad.data_ptr() < g.data_ptr() or first.grad.data_ptr() >= g.data_ptr() + g.numel() * 4:
+            return None
+        return g
+
+    def step(self):
+        L = _lib.lib()
+        dev = next(self.model.parameters()).device
+        st = _lib.stream_ptr()
+        active = [(f, self._flat_grad(f)) for f in self.flat]
+        fallback = [f for f, g in active if g is None and any(p.grad is not None for p in f["module"].ordered_params())]
+        if fallback:
+            raise RuntimeError("FlatAdamW: a flat module's gradients are not views of its gradient block")
+        active = [(f, g) for f, g in active if g is not None]
+        rest_grads = [p.grad for p in self.rest_params if p.grad is not None]
+        scale = None
+        if self.max_norm > 0:
+            sq = torch.zeros(1, dtype=torch.float32, device=dev)
+            for f, g in active:
+                _lib.check(L.mtus_sumsq(_lib.ptr(g), g.numel(), _lib.ptr(sq), st), "sumsq")
+            if rest_grads:
+                norms = torch._foreach_norm(rest_grads)
+                sq += torch.stack([n.float() for n in norms]).square().sum()
+            total = sq.sqrt()
+            scale = (self.max_norm / (total + 1e-6)).clamp(max=1.0)        # clip_grad_norm_ coefficient, on device
+            if rest_grads:
+                torch._foreach_mul_(rest_grads, scale.squeeze(0))
+        for f, g in active:
+            mod = f["module"]
+            p = mod.flat_params()
+            if f["m"] is None or f["m"].device != p.device:
+                f["m"], f["v"] = torch.zeros_like(p), torch.zeros_like(p)
+            f["step"] += 1
+            _lib.check(L.mtus_adamw_flat(_lib.ptr(p), _lib.ptr(g), _lib.ptr(f["m"]), _lib.ptr(f["v"]), p.numel(), f["lr"],
+                                         self.betas[0], self.betas[1], self.eps, self.wd, f["step"], _lib.ptr(scale), st), "adamw_flat")
+        if self.torch_opt is not None:
+            self.torch_opt.step()
+        self._clipped_externally = True
+
+    handles_clipping = True
+
+    def state_dict(self):
+        return {"flat": [{"m": f["m"], "v": f["v"], "step": f["step"]} for f in self.flat],
+                "torch": self.torch_opt.state_dict() if self.torch_opt is not None else None}
+
+    def load_state_dict(self, sd):
+        for f, s in zip(self.flat, sd["flat"]):
+            f["m"], f["v"], f["step"] = s["m"], s["v"], s["step"]
+        if self.torch_opt is not None and sd.get("torch") is not None:
+            self.torch_opt.load_state_dict(sd["torch"])

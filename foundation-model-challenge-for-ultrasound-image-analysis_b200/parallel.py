@@ -143,7 +143,7 @@ class DataParallelTrainer:
         with self.reducer:
             total.backward()
         self.reducer.finish()
-        if self.clip > 0:
+        if self.clip > 0 and not getattr(self.optimizer, "handles_clipping", False):
             torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip)
         self.optimizer.step()
         return total.detach()

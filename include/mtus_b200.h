@@ -128,6 +128,13 @@ int mtus_convert(const void* x, void* y, int B, int R, int Cc, int transpose, in
 int mtus_nhwc_to_nchw(const void* x, void* y, int B, int HW, int C, int dtype, int out_f32, void* stream);
 int mtus_nchw_to_nhwc(const void* x, void* y, int B, int HW, int C, int dtype, int in_f32, void* stream);
 
+/* ---- optimizer step over the flat parameter blocks (torch.optim.AdamW rule, code/train.py:208,455) ----------- */
+/* out += sum(g^2)  (global gradient norm for clip_grad_norm_, code/train.py:446) */
+int mtus_sumsq(const float* g, int64_t n, float* out, void* stream);
+/* p, m, v updated in place from g * (*grad_scale) (grad_scale: device scalar = clip coefficient, or NULL) */
+int mtus_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int step, const float* grad_scale, void* stream);
+
 /* ---- PatchEmbed (timm PatchEmbed; 8a a3): 4x4/4 conv as im2col (K padded 48->64) + GEMM + LN -- */
 int mtus_patch_embed_im2col(const void* x_nchw, void* cols, int B, int H, int W, int x_is_f32, int dtype,
                             void* stream);

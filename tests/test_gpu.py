@@ -157,3 +157,28 @@ def test_training_step_decreases_loss_and_keeps_idle_heads_untouched():
     assert losses[-1] < losses[0], losses
     assert torch.equal(model.heads["T2A_fetal_abdomen"].head[0].weight, idle)
     assert all(p.grad is None for p in model.fpn_decoder_seg.parameters())
+
+
+def test_flat_adamw_matches_torch_adamw_with_clipping():
+    """optim.FlatAdamW (one kernel per flat parameter block, clip coefficient on device) == torch AdamW + clip_grad_norm_."""
+    import mtus_b200 as m
+    tasks = [t for t in m.tasks_27() if t["task_id"] in ("T2A_fetal_abdomen", "T1_fetal_planes")]
+    cfg = m.make_config("swin_micro_patch4_window7_test", 64, 4, tasks=tasks, dropout=0.0)
+    models, trainers = [], []
+    for flat in (False, True):
+        torch.manual_seed(0)
+        model = m.build_model(cfg, precision="fp32").cuda().eval()     # eval: no drop-path / dropout randomness
+        opt = m.build_flat_optimizer(model, cfg) if flat else m.build_optimizer(model, cfg, fused=False)
+        fns, w = m.build_all_losses(cfg)
+        models.append(model)
+        trainers.append(m.DataParallelTrainer(model, opt, fns, w, gradient_clip=1.0))
+    gen = torch.Generator().manual_seed(3)
+    for step in range(4):
+        tcfg = tasks[step % 2]
+        x, y = m.synthetic_batch(tcfg, 4, 64, generator=gen, device="cuda")
+        la = trainers[0].step(x, y, tcfg["task_id"])
+        lb = trainers[1].step(x, y, tcfg["task_id"])
+        assert abs(float(la) - float(lb)) <= 1e-5 * max(1.0, abs(float(la)))
+    pa, pb = dict(models[0].named_parameters()), dict(models[1].named_parameters())
+    for k in pa:
+        assert torch.allclose(pa[k], pb[k], rtol=2e-4, atol=2e-6), k

@@ -19,7 +19,7 @@ def main():
     cfg = m.swin_b_27task(batch_size=B)
     torch.manual_seed(0)
     model = m.build_model(cfg, precision="bf16").to(dev).train()
-    opt = m.build_optimizer(model, cfg, fused=True)
+    opt = m.build_flat_optimizer(model, cfg)
     fns, w = m.build_all_losses(cfg)
     tr = m.DataParallelTrainer(model, opt, fns, w)
     tcfg = {t["task_id"]: t for t in cfg.get_task_configs()}
