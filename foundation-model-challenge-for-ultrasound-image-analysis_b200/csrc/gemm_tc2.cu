@@ -49,9 +49,10 @@ struct T2Smem {
   static constexpr int B_BYTES = BN * T2_BK * 2;
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int SUB_BYTES = 128 * 128;                       // epilogue sub-tile: 128 rows x 128 bytes
+  static constexpr int EPI_BUFS = 2;   // (measured: a deeper ring with a single-buffered epilogue is not faster)
   static constexpr int STAGES = (BN == 256) ? 3 : ((BN == 128) ? 4 : 6);
   static constexpr int EPI_OFF = STAGES * STAGE;
-  static constexpr int BAR_OFF = EPI_OFF + 4 * SUB_BYTES;           // X[2], D[2]
+  static constexpr int BAR_OFF = EPI_OFF + 2 * EPI_BUFS * SUB_BYTES;   // X[EPI_BUFS], D[EPI_BUFS]
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
   static constexpr int SUB_COLS = OUT_F32 ? 32 : 64;
   static constexpr int NSUB = BN / SUB_COLS;
@@ -59,7 +60,10 @@ struct T2Smem {
 
 // A_MODE: 0 K-major 2-D | 1 MN-major 2-D | 2 conv im2col (K-major, 128-pixel row tiles) | 3 conv pixel-major (wgrad)
 // B_MODE: 0 K-major 2-D | 1 MN-major 2-D | 2 conv pixel-major with tap shift (wgrad)
-template <int BN, int A_MODE, int B_MODE, bool OUT_F32>
+// CS: thread-block cluster size along M.  The CS CTAs of a cluster work on CS consecutive m-blocks of the same n-tile in
+// lock step: each loads its own A tile and 1/CS of the shared B tile, multicast into every CTA's shared memory, so
+// the L2 -> SM operand traffic (the main-loop limiter of these GEMMs) drops from A+B to A+B/CS per CTA.
+template <int BN, int A_MODE, int B_MODE, bool OUT_F32, int CS>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, int M, int N, int K,
@@ -73,7 +77,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * S::STAGES, bar_tfull = bar_empty + 8 * S::STAGES,
                  bar_tempty = bar_tfull + 16, bar_xfull = bar_tempty + 16, bar_xempty = bar_xfull + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 8);
-  const uint32_t smem_x = smem_base + S::EPI_OFF, smem_d = smem_x + 2 * S::SUB_BYTES;
+  const uint32_t smem_x = smem_base + S::EPI_OFF, smem_d = smem_x + S::EPI_BUFS * S::SUB_BYTES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool x_in = (ep.x_mode == 1 || ep.x_mode == 2);
@@ -84,8 +88,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
     if (ep.x_mode) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
   }
+  const int cl_rank = (CS > 1) ? (int)cluster_ctarank() : 0;
+  const int cl_id = blockIdx.x / CS, n_cl = gridDim.x / CS;
+  constexpr uint16_t cl_mask = (uint16_t)((1u << CS) - 1);
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < S::STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < S::STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CS); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 8);
       mbar_init(bar_xfull + 8 * b, 1); mbar_init(bar_xempty + 8 * b, 8);
@@ -95,16 +102,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();          // barrier inits visible cluster-wide before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int mn_tiles = m_tiles * n_tiles;
+  // work units enumerate (split z, m-group, n-tile), n fastest; the CTA of rank r takes m-block mg*CS + r (a block
+  // beyond m_tiles is a dummy: its loads are zero-filled and its stores clipped, it only keeps the cluster in step)
+  const int mgn_tiles = ((m_tiles + CS - 1) / CS) * n_tiles;
+#define T2_DECODE(u)                                                                                   \
+  const int z = (u) / mgn_tiles, r_ = (u) - z * mgn_tiles, m_blk = (r_ / n_tiles) * CS + cl_rank,      \
+            n_blk = r_ - (r_ / n_tiles) * n_tiles;                                                     \
+  (void)z; (void)m_blk; (void)n_blk;
 
   if (warp == 0 && lane == 0) {
     // ================================ TMA producer: A / B tiles ================================
     uint32_t it = 0;
-    for (int t = blockIdx.x; t < n_work; t += gridDim.x) {
-      const int z = t / mn_tiles, r = t - z * mn_tiles, m_blk = r / n_tiles, n_blk = r - m_blk * n_tiles;
+    for (int t = cl_id; t < n_work; t += n_cl) {
+      T2_DECODE(t)
       const int kb0 = z * kb_per_split, nkb = min(kb_per_split, total_kb - kb0);
       int cb = 0, cy0 = 0, cx0 = 0;
       if (A_MODE == 2) {
@@ -135,17 +149,33 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tma_load_4d(sa, &tmA, m_blk * T2_BM, px0, py0, pb, full);
           tma_load_4d(sa + 8192, &tmA, m_blk * T2_BM + 64, px0, py0, pb, full);
         }
-        if (B_MODE == 0) {
-          tma_load_2d(sb, &tmB, k0, n_blk * BN, full);
-        } else if (B_MODE == 1) {
+        if (CS == 1) {
+          if (B_MODE == 0) {
+            tma_load_2d(sb, &tmB, k0, n_blk * BN, full);
+          } else if (B_MODE == 1) {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, n_blk * BN + j * 64, k0, full);
-        } else {                    // x [pixels, Cin] shifted by the tap of this n-tile: N index = tap*C + c
-          const int n0 = n_blk * BN;
-          const int tap = n0 / cv.C, c0 = n0 - tap * cv.C;
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, n_blk * BN + j * 64, k0, full);
+          } else {                    // x [pixels, Cin] shifted by the tap of this n-tile: N index = tap*C + c
+            const int n0 = n_blk * BN;
+            const int tap = n0 / cv.C, c0 = n0 - tap * cv.C;
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_4d(sb + j * 8192, &tmB, c0 + j * 64, px0 + tap % 3 - 1, py0 + tap / 3 - 1, pb, full);
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_4d(sb + j * 8192, &tmB, c0 + j * 64, px0 + tap % 3 - 1, py0 + tap / 3 - 1, pb, full);
+          }
+        } else {                      // this CTA's 1/CS of the B tile, multicast to every CTA of the cluster
+          if (B_MODE == 0) {          // tmB box = (64 k, BN/CS rows)
+            tma_load_2d_mc(sb + cl_rank * (BN / CS) * 128, &tmB, k0, n_blk * BN + cl_rank * (BN / CS), full, cl_mask);
+          } else if (B_MODE == 1) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              if (j % CS == cl_rank) tma_load_2d_mc(sb + j * 8192, &tmB, n_blk * BN + j * 64, k0, full, cl_mask);
+          } else {
+            const int n0 = n_blk * BN;
+            const int tap = n0 / cv.C, c0 = n0 - tap * cv.C;
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              if (j % CS == cl_rank) tma_load_4d_mc(sb + j * 8192, &tmB, c0 + j * 64, px0 + tap % 3 - 1, py0 + tap / 3 - 1, pb, full, cl_mask);
+          }
         }
       }
     }
@@ -153,8 +183,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ================================ MMA issuer ================================
     constexpr uint32_t idesc = umma_idesc(T2_BM, BN, (A_MODE == 1 || A_MODE == 3) ? 1 : 0, B_MODE != 0 ? 1 : 0);
     uint32_t it = 0, tc = 0;
-    for (int t = blockIdx.x; t < n_work; t += gridDim.x, ++tc) {
-      const int z = t / mn_tiles;
+    for (int t = cl_id; t < n_work; t += n_cl, ++tc) {
+      T2_DECODE(t)
       const int kb0 = z * kb_per_split, nkb = min(kb_per_split, total_kb - kb0);
       const uint32_t ab = tc & 1;
       mbar_wait(bar_tempty + 8 * ab, ((tc >> 1) & 1) ^ 1);
@@ -171,7 +201,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint64_t bd = (B_MODE != 0) ? umma_smem_desc(sb + k * 2048, 8192, 1024) : umma_smem_desc(sb + k * 32, 0, 1024);
           umma_bf16(tacc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(bar_empty + 8 * s);
+        if (CS == 1) umma_commit(bar_empty + 8 * s);
+        else umma_commit_mc(bar_empty + 8 * s, cl_mask);   // the stage is free once EVERY CTA of the cluster has read it
       }
       umma_commit(bar_tfull + 8 * ab);
     }
@@ -179,11 +210,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ================================ TMA loader of the epilogue operand ================================
     if (x_in) {
       uint32_t e = 0;
-      for (int t = blockIdx.x; t < n_work; t += gridDim.x) {
-        const int z = t / mn_tiles, r = t - z * mn_tiles, m_blk = r / n_tiles, n_blk = r - m_blk * n_tiles;
+      for (int t = cl_id; t < n_work; t += n_cl) {
+        T2_DECODE(t)
         for (int sub = 0; sub < S::NSUB; ++sub, ++e) {
-          const uint32_t b = e & 1;
-          mbar_wait(bar_xempty + 8 * b, ((e >> 1) & 1) ^ 1);
+          const uint32_t b = e % S::EPI_BUFS;
+          mbar_wait(bar_xempty + 8 * b, ((e / S::EPI_BUFS) & 1) ^ 1);
           mbar_expect_tx(bar_xfull + 8 * b, S::SUB_BYTES);
           tma_load_2d(smem_x + b * S::SUB_BYTES, &tmX, n_blk * BN + sub * S::SUB_COLS, m_blk * T2_BM, bar_xfull + 8 * b);
         }
@@ -194,8 +225,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int ew = warp - 4, q = ew & 3, hf = ew >> 2, row = q * 32 + lane, etid = threadIdx.x - 128;
     constexpr int CH = OUT_F32 ? 16 : 32;     // accumulator columns per thread per sub-tile (64 bytes of output)
     uint32_t tc = 0, e = 0;
-    for (int t = blockIdx.x; t < n_work; t += gridDim.x, ++tc) {
-      const int z = t / mn_tiles, r = t - z * mn_tiles, m_blk = r / n_tiles, n_blk = r - m_blk * n_tiles;
+    for (int t = cl_id; t < n_work; t += n_cl, ++tc) {
+      T2_DECODE(t)
       const uint32_t ab = tc & 1;
       mbar_wait(bar_tfull + 8 * ab, (tc >> 1) & 1);
       tc_fence_after();
@@ -206,14 +237,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
 #pragma unroll 1
       for (int sub = 0; sub < S::NSUB; ++sub, ++e) {
-        const uint32_t b = e & 1;
+        const uint32_t b = e % S::EPI_BUFS;
         const uint32_t sx = smem_x + b * S::SUB_BYTES + row * 128, sd = smem_d + b * S::SUB_BYTES + row * 128;
         const int n_sub = n_blk * BN + sub * S::SUB_COLS;
         const int n0 = n_sub + hf * CH;
         // the TMA store that read D[b] / X[b] two sub-tiles ago must have finished reading shared memory
-        if (etid == 0) bulk_wait_read<1>();
+        if (etid == 0) bulk_wait_read<S::EPI_BUFS - 1>();
         named_bar_sync(T2_EPI_BAR, T2_EPI_THREADS);
-        if (x_in) mbar_wait(bar_xfull + 8 * b, (e >> 1) & 1);
+        if (x_in) mbar_wait(bar_xfull + 8 * b, (e / S::EPI_BUFS) & 1);
         uint32_t v[CH];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * BN + sub * S::SUB_COLS + hf * CH;
         if (OUT_F32) tmem_ld16_nowait(taddr, *reinterpret_cast<uint32_t(*)[16]>(v));
@@ -337,7 +368,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();          // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
+#undef T2_DECODE
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -368,20 +401,31 @@ static int sm_count() {
   return g_sm_count;
 }
 
-template <int BN, int A_MODE, int B_MODE, bool OUT_F32>
+template <int BN, int A_MODE, int B_MODE, bool OUT_F32, int CS>
 static int t2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tx, const CUtensorMap& td, int M,
-                     int N, int K, int kbps, int total_kb, int m_tiles, int n_tiles, int n_work, const T2Conv& cv,
+                     int N, int K, int kbps, int total_kb, int m_tiles, int n_tiles, int splits, const T2Conv& cv,
                      const T2Epi& ep, cudaStream_t st) {
-  auto kern = gemm_tc2_kernel<BN, A_MODE, B_MODE, OUT_F32>;
+  auto kern = gemm_tc2_kernel<BN, A_MODE, B_MODE, OUT_F32, CS>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Smem<BN, OUT_F32>::TOTAL);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  const int grid = n_work < sm_count() ? n_work : sm_count();
-  kern<<<grid, T2_THREADS, T2Smem<BN, OUT_F32>::TOTAL, st>>>(ta, tb, tx, td, M, N, K, kbps, total_kb, m_tiles, n_tiles,
-                                                             n_work, cv, ep);
+  const int64_t units64 = (int64_t)splits * ceil_div(m_tiles, CS) * n_tiles;
+  if (units64 > (1ll << 30)) return MTUS_ERR_UNSUPPORTED;
+  const int n_units = (int)units64;
+  const int max_cl = sm_count() / CS;
+  const int n_cl = n_units < max_cl ? n_units : max_cl;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_cl * CS); cfg.blockDim = dim3(T2_THREADS);
+  cfg.dynamicSmemBytes = T2Smem<BN, OUT_F32>::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tx, td, M, N, K, kbps, total_kb, m_tiles, n_tiles, n_units, cv, ep);
+  if (e != cudaSuccess) return (int)e;
   MTUS_LAUNCH_STATUS();
   return MTUS_OK;
 }
@@ -455,6 +499,14 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
     cv.ktw = 8; cv.kth = 8;
     cv.ktiles_x = ceil_div(cv.W, 8); cv.ktiles_y = ceil_div(cv.H, 8);
   }
+  int CS = 1;
+  {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("MTUS_CLUSTER"); forced = e ? atoi(e) : 0; }
+    CS = forced ? forced : 1;   // measured: multicasting B across a 2-CTA cluster does not speed these shapes up (not L2-bound)
+    if (CS != 1 && CS != 2) CS = 2;
+    if (m_tiles < 2 || BN < 128) CS = 1;
+  }
   int am, bm;
   if (d->a_conv) {
     const int B = M / (cv.H * cv.W);
@@ -473,7 +525,7 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
     const int B = K / (cv.H * cv.W);
     rc = make_map_conv(&tb, d->b, B, cv.H, cv.W, cv.C, cv.ktw, cv.kth);
     bm = 2;
-  } else if (!d->b_mn_major) { rc = make_map_2d(&tb, d->b, K, N, d->ldb, T2_BK, BN); bm = 0; }
+  } else if (!d->b_mn_major) { rc = make_map_2d(&tb, d->b, K, N, d->ldb, T2_BK, BN / CS); bm = 0; }
   else { rc = make_map_2d(&tb, d->b, N, K, d->ldb, 64, T2_BK); bm = 1; }
   if (rc) return rc;
   // D / X maps
@@ -498,11 +550,13 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
   if (splits > total_kb) splits = total_kb;
   const int kbps = ceil_div(total_kb, splits);
   splits = ceil_div(total_kb, kbps);
-  const int64_t n_work64 = (int64_t)splits * m_tiles * n_tiles;
-  if (n_work64 > (1ll << 30)) return MTUS_ERR_UNSUPPORTED;
-  const int n_work = (int)n_work64;
 
-#define T2_GO(BN_, AM_, BM_, F32_) return t2_launch<BN_, AM_, BM_, F32_>(ta, tb, tx, td, M, N, K, kbps, total_kb, m_tiles, n_tiles, n_work, cv, ep, st)
+#define T2_GO2(BN_, AM_, BM_, F32_)                                                                                                  \
+  {                                                                                                                                  \
+    if (CS == 2) return t2_launch<BN_, AM_, BM_, F32_, 2>(ta, tb, tx, td, M, N, K, kbps, total_kb, m_tiles, n_tiles, splits, cv, ep, st); \
+    return t2_launch<BN_, AM_, BM_, F32_, 1>(ta, tb, tx, td, M, N, K, kbps, total_kb, m_tiles, n_tiles, splits, cv, ep, st);              \
+  }
+#define T2_GO(BN_, AM_, BM_, F32_) T2_GO2(BN_, AM_, BM_, F32_)
   if (d->out_f32) {
     if (BN == 128) {
       if (am == 0 && bm == 0) T2_GO(128, 0, 0, true);
@@ -524,6 +578,7 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
     if (am == 0 && bm == 1) T2_GO(64, 0, 1, false);
     if (am == 2 && bm == 0) T2_GO(64, 2, 0, false);
   }
+#undef T2_GO2
 #undef T2_GO
   return MTUS_ERR_UNSUPPORTED;
 }
