@@ -2,19 +2,23 @@
 //
 // Same contract as attention.cu (timm _attn + WindowAttention minus the two Linear layers; SURVEY section 8a rows
 // a5, a6): the cyclic shift, zero padding, window partition / reverse, relative-position bias, shift mask,
-// softmax and P@V happen inside the kernel and nothing window-shaped touches HBM.  Differences:
-//   * one WARP owns one (window, head) item and is fully autonomous (no block-level barrier): q/k/v (and dO)
-//     tiles [64 x 32] bf16 are staged in swizzled shared memory with 16-byte cp.async, every contraction runs on
-//     the tensor cores (mma.sync m16n8k16, fp32 accumulate) in 16-token strips, the softmax works on the
-//     accumulator fragments (exp2 with log2e folded into the scale and the bias table), and outputs leave
-//     through a 1 KB staging strip as 64-byte row segments (full sectors);
-//   * forward also writes the per-(token, head) log-sum-exp, so the backward pass needs no max / sum reductions:
-//     it walks KEY strips once -- S^T and dP^T strips come straight out of the MMAs in the layout that dV and dK
-//     consume as A operands; only dS is transposed (2 KB strip through shared memory + ldmatrix.trans) to
-//     accumulate dQ in registers;
-//   * the relative-position-bias gradient is binned in shared memory over all the windows a warp processes and
-//     flushed with one atomicAdd per bin; the qkv-bias gradient (column sums of dqkv) is accumulated in registers
-//     and flushed once per warp, so no separate column-sum pass over dqkv is needed.
+// softmax and P@V happen inside the kernel and nothing window-shaped touches HBM.
+//
+// Execution model (v3, persistent): one CTA of 4 warps owns ONE head and walks a strided list of windows
+// (grid = heads x G, one wave of CTAs).  Everything that depends only on the head is set up once per CTA:
+//   * the relative-position bias is expanded once into per-thread accumulator-fragment order in shared memory
+//     (log2 domain, -inf baked in for the columns / rows beyond the window), so a score is one FMA;
+//   * the bias-table gradient is accumulated in registers over all windows of the CTA and binned once at the end
+//     (a [64 x 64] matrix in shared memory summed along its 169 diagonals -- no shared-memory atomics);
+//   * the qkv-bias gradient (column sums of dqkv) is accumulated in registers and flushed once per CTA.
+// Per window the q / k / v (/ dO / O) head slices [64 x 32] bf16 are gathered with 16-byte cp.async (zero fill for
+// absent tokens) into a 2-stage ring: the loads of window i+1 are in flight while window i is computed.  Warp w
+// owns the 16-token strip w; every contraction runs on the tensor cores (mma.sync m16n8k16, fp32 accumulate), the
+// softmax works on accumulator fragments with exp2, outputs leave through a 1 KB staging strip per warp as 64-byte
+// row segments.  Forward saves the per-(token, head) log-sum-exp; backward walks KEY strips (S^T and dP^T come out
+// of the MMAs in the layout dV and dK consume as A operands), parks dS^T (bf16, 8 KB) in shared memory and then
+// each warp contracts its own QUERY strip of dS with K for dQ.
+//
 // A stand-alone attention kernel is HBM-bound (24.5 FLOP/B at 49 tokens): algorithmic bytes per token are
 // 4*C*2 forward (q, k, v in; o out) and 8*C*2 backward (q, k, v, o, dO in; dq, dk, dv out).  The per-window
 // contractions are too small (49x32x49) for a tcgen05 tile on their own; they move to tcgen05 when this kernel is
@@ -32,7 +36,7 @@ struct AmGeom {
   float scale2;           // head_dim^-0.5 * log2(e)
   float scale;            // head_dim^-0.5
   int windows;            // B * nwy * nwx
-  int win_per_warp;       // consecutive windows (same head) handled by one CTA
+  int groups;             // G: CTAs per head; CTA (g, h) handles windows g, g + G, g + 2G, ...
 };
 
 __device__ __forceinline__ uint32_t am_off(int row, int chunk) {   // byte offset inside a [64][32] bf16 tile
@@ -145,19 +149,6 @@ __device__ __forceinline__ void am_store_strip(const float (&o)[4][4], float mul
   }
 }
 
-// loads one [N x 32] slice (64-byte row segments) of a [rows, row_stride] bf16 matrix into a swizzled tile; rows of
-// absent tokens (padding, t >= N) are zero-filled by the same cp.async (src-size 0), so the loop has no branches
-__device__ __forceinline__ void am_load_tile(uint32_t tile_s, const bf16* base, int64_t row_stride, int col0, const int* s_src, int tid) {
-#pragma unroll
-  for (int it0 = 0; it0 < 64 * 4; it0 += AM_WARPS * 32) {
-    const int it = it0 + tid;
-    const int tok = it >> 2, ch = it & 3;
-    const int src = s_src[tok];
-    const bf16* p = base + (int64_t)(src < 0 ? 0 : src) * row_stride + col0 + ch * 8;
-    cp_async16_zfill(tile_s + am_off(tok, ch), p, src < 0 ? 0 : 16);
-  }
-}
-
 // padded tokens of a window (resolution not divisible by the window): timm pads AFTER norm1, so their q / k / v are
 // the qkv bias.  Rare path (only windows on the bottom / right border of such maps): overwrite the zero-filled rows.
 __device__ __forceinline__ void am_fill_pad_rows(uint8_t* tile_g, const float* pad_bias, int col0, const int* s_src, int N, int tid) {
@@ -213,123 +204,166 @@ __device__ __forceinline__ AmWin am_window(const AmGeom& g, int w) {
 __device__ __forceinline__ bool am_has_pad(const AmGeom& g, const AmWin& w) {
   return (w.wy + 1) * g.wh > g.H || (w.wx + 1) * g.ww > g.W;
 }
-__device__ __forceinline__ void am_sources(const AmGeom& g, const AmWin& w, int tid, const int* s_pos, int* s_src) {
-  for (int t = tid; t < 64; t += AM_WARPS * 32) {
-    int src = -1;
-    if (t < g.N) {
-      const int pos = s_pos[t];
-      const int py = w.wy * g.wh + (pos & 0xff), px = w.wx * g.ww + (pos >> 8);
-      if (py < g.H && px < g.W) {
-        int y = py + g.sh, x = px + g.sw;
-        if (y >= g.H) y -= g.H;
-        if (x >= g.W) x -= g.W;
-        src = (w.b * g.H + y) * g.W + x;
-      }
-    }
-    s_src[t] = src;
-  }
+// source row of token t of window w (cyclic shift undone), or -1 for padding / t >= N
+__device__ __forceinline__ int am_source(const AmGeom& g, const AmWin& w, int t, const int* s_pos) {
+  if (t >= g.N) return -1;
+  const int pos = s_pos[t];
+  const int py = w.wy * g.wh + (pos & 0xff), px = w.wx * g.ww + (pos >> 8);
+  if (py >= g.H || px >= g.W) return -1;
+  int y = py + g.sh, x = px + g.sw;
+  if (y >= g.H) y -= g.H;
+  if (x >= g.W) x -= g.W;
+  return (w.b * g.H + y) * g.W + x;
 }
 
 __device__ __forceinline__ int am_region(const AmWin& w, int rg) {
   return (w.last_row ? (rg & 0xff) : 0) + (w.last_col ? (rg >> 8) : 0);
 }
 
-// scores of one strip in the log2 domain: s2 = acc*scale2 + tbl2[lin_q - lin_k + off] (+ mask), invalid columns -> -inf.
-// NTC column tiles; rows are queries (TRANSPOSED=false) or keys (TRANSPOSED=true).
-// lrow0/1: lin of the two rows (+off folded in by the caller for the non-transposed case: see below)
-template <int NTC, bool TRANSPOSED, bool MASKED>
-__device__ __forceinline__ void am_scores(float (&acc)[8][4], float scale2, const float* s_tbl2, int lin_off, const int (&clin)[16],
-                                          const int (&creg)[16], int lr0, int lr1, int rr0, int rr1, int n_valid_cols, int t) {
-  const float MASK2 = -100.0f * AM_LOG2E;
-#pragma unroll
-  for (int nt = 0; nt < NTC; ++nt)
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int c = nt * 2 + e;
-      const bool col_ok = (nt * 8 + 7 < n_valid_cols) || (nt * 8 + 2 * t + e < n_valid_cols);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int lr = h ? lr1 : lr0;
-        const int idx = (TRANSPOSED ? (clin[c] - lr) : (lr - clin[c])) + lin_off;
-        float s = fmaf(acc[nt][h * 2 + e], scale2, s_tbl2[idx]);
-        if (MASKED) { if (creg[c] != (h ? rr1 : rr0)) s += MASK2; }
-        acc[nt][h * 2 + e] = col_ok ? s : -INFINITY;
-      }
-    }
-}
-
-// ---- CTA-cooperative kernels: one CTA (4 warps) per (window group, head); warp w owns the 16-token strip w -------------
+// ---- persistent CTA-cooperative kernels ---------------------------------------------------------------------------
 // shared memory per CTA (bytes):
-//   fwd: tiles q,k,v [3][4096] | stage [4][1024] | table | 4 int[64] tables
-//   bwd: tiles q,k,v,dO [4][4096] | stage [4][1024] | dS strips [4][2048] | dQ slabs [4][64][AM_SLAB_LD] fp32 | table | bins |
-//        4 int[64] tables | delta[64] | lse[64]
-#define AM_SLAB_LD 40
-#ifndef AM_WAVES
-#define AM_WAVES 3
+//   fwd: ring [2][3 tiles: q,k,v][4096] | stage strips [4][1024] | bias fragments [4][8][32] float4 | int tables
+//   bwd: ring [2][5 tiles: q,k,v,dO,O][4096] | stage strips | dS^T [64 keys][64 queries] bf16 | bias fragments | int tables |
+//        lse ring [2][64] | delta[64] | column-sum scratch [4][96]
+#define AM_FRAG_BYTES (AM_WARPS * 8 * 32 * 16)
+#define AM_G_LD 68                                     // row pitch (floats) of the [64][64] dS^T-sum matrix (end of bwd)
+#ifndef AM_FWD_OCC
+#define AM_FWD_OCC 4
 #endif
-static __host__ __device__ inline int am_tab_bytes(int ntab) { return (ntab * 4 + 15) & ~15; }
-static __host__ __device__ inline int am_cta_bytes(int ntab, bool bwd) {
-  int b = (bwd ? 4 : 3) * AM_TILE_BYTES + AM_WARPS * 1024 + (bwd ? 2 : 1) * am_tab_bytes(ntab) + 4 * 256;
-  if (bwd) b += AM_WARPS * 2048 + AM_WARPS * 64 * AM_SLAB_LD * 4 + 2 * 256;
+#ifndef AM_BWD_OCC
+#define AM_BWD_OCC 3
+#endif
+static __host__ __device__ inline int am_cta_bytes(bool bwd) {
+  int b = 2 * (bwd ? 5 : 3) * AM_TILE_BYTES + AM_WARPS * 1024 + AM_FRAG_BYTES + 5 * 256;   // s_pos, s_lin, s_rg, s_src[2]
+  if (bwd) b += 64 * 128 + 2 * 256 + 256 + AM_WARPS * 96 * 4;
   return b;
 }
 
+// Relative-position bias (log2 domain) in accumulator-fragment order: entry (warp, nt, lane) holds the four values of
+// acc[nt][0..3] of strip `warp`: rows r0 = 16 warp + lane/4, r1 = r0 + 8; columns 8 nt + 2 (lane % 4) + {0, 1}.
+// Columns >= N are -inf (softmax ignores them); rows >= N are -inf in the transposed (backward, rows = keys) form
+// so that P^T is exactly zero there, and 0 in the forward form (those query rows are never stored).
+template <bool TRANSPOSED>
+__device__ __forceinline__ void am_build_bias_frags(float4* s_frag, const float* s_tbl2, const int* s_lin, const AmGeom& g, int tid) {
+  for (int e = tid; e < AM_WARPS * 8 * 32; e += AM_WARPS * 32) {
+    const int lane = e & 31, nt = (e >> 5) & 7, w = e >> 8;
+    const int r0 = w * 16 + (lane >> 2), r1 = r0 + 8, c0 = nt * 8 + 2 * (lane & 3), c1 = c0 + 1;
+    auto val = [&](int r, int c) -> float {
+      if (c >= g.N) return -INFINITY;
+      if (r >= g.N) return TRANSPOSED ? -INFINITY : 0.f;
+      return s_tbl2[(TRANSPOSED ? (s_lin[c] - s_lin[r]) : (s_lin[r] - s_lin[c])) + g.lin_off];
+    };
+    s_frag[e] = make_float4(val(r0, c0), val(r0, c1), val(r1, c0), val(r1, c1));
+  }
+}
+
+template <int NTC, bool MASKED>
+__device__ __forceinline__ void am_scores_frag(float (&acc)[8][4], float scale2, const float4* frag, const int (&creg)[16], int rr0, int rr1) {
+  const float MASK2 = -100.0f * AM_LOG2E;
+#pragma unroll
+  for (int nt = 0; nt < NTC; ++nt) {
+    const float4 b = frag[nt * 32];
+    acc[nt][0] = fmaf(acc[nt][0], scale2, b.x); acc[nt][1] = fmaf(acc[nt][1], scale2, b.y);
+    acc[nt][2] = fmaf(acc[nt][2], scale2, b.z); acc[nt][3] = fmaf(acc[nt][3], scale2, b.w);
+    if (MASKED) {
+      if (creg[nt * 2] != rr0) acc[nt][0] += MASK2;
+      if (creg[nt * 2 + 1] != rr0) acc[nt][1] += MASK2;
+      if (creg[nt * 2] != rr1) acc[nt][2] += MASK2;
+      if (creg[nt * 2 + 1] != rr1) acc[nt][3] += MASK2;
+    }
+  }
+}
+
+// Issues the gathers of one window into ring stage `ring_s` (NT tiles: q, k, v [, dO, O]); thread (tok, ch) moves the
+// 16-byte chunk ch of tokens tok and tok + 32.  Also records the source rows (s_src) and, for the backward pass,
+// prefetches the log-sum-exp of the query rows (1e30 for absent queries: P = 0).
+template <bool BWD>
+__device__ __forceinline__ void am_issue_window(const AmGeom& g, const AmWin& win, int h, uint32_t ring_s, const bf16* qkv, const bf16* dout,
+                                                const bf16* outp, const float* lse, const int* s_pos, int* s_src, float* s_lse, int tid) {
+  const int ch = tid & 3;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int tok = k * 32 + (tid >> 2);
+    const int src = am_source(g, win, tok, s_pos);
+    const int bytes = src < 0 ? 0 : 16;
+    const int64_t row = src < 0 ? 0 : src;
+    const uint32_t off = am_off(tok, ch);
+    const bf16* p = qkv + row * (3 * g.C) + h * 32 + ch * 8;
+    cp_async16_zfill(ring_s + off, p, bytes);
+    cp_async16_zfill(ring_s + AM_TILE_BYTES + off, p + g.C, bytes);
+    cp_async16_zfill(ring_s + 2 * AM_TILE_BYTES + off, p + 2 * g.C, bytes);
+    if (BWD) {
+      cp_async16_zfill(ring_s + 3 * AM_TILE_BYTES + off, dout + row * g.C + h * 32 + ch * 8, bytes);   // padded tokens: dO = 0 (cropped away)
+      cp_async16_zfill(ring_s + 4 * AM_TILE_BYTES + off, outp + row * g.C + h * 32 + ch * 8, bytes);
+    }
+    if (ch == 0) {
+      s_src[tok] = src;
+      if (BWD) {
+        if (src >= 0) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32_generic(s_lse + tok)), "l"(lse + (int64_t)src * g.heads + h) : "memory");
+        else s_lse[tok] = 1e30f;
+      }
+    }
+  }
+}
+
 template <int NTC>
-__global__ void __launch_bounds__(AM_WARPS * 32, 4) window_attn_mma_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ table,
-                                                                               const float* __restrict__ qkv_bias, bf16* __restrict__ out,
-                                                                               float* __restrict__ lse, AmGeom g) {
+__global__ void __launch_bounds__(AM_WARPS * 32, AM_FWD_OCC) window_attn_mma_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ table,
+                                                                                        const float* __restrict__ qkv_bias, bf16* __restrict__ out,
+                                                                                        float* __restrict__ lse, AmGeom g) {
   extern __shared__ __align__(128) uint8_t am_smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int h = blockIdx.x % g.heads, wg = blockIdx.x / g.heads;
-  uint8_t* tq = am_smem_raw; uint8_t* tk = tq + AM_TILE_BYTES; uint8_t* tv = tk + AM_TILE_BYTES;
-  uint8_t* stage = tv + AM_TILE_BYTES + warp * 1024;
-  float* s_tbl = reinterpret_cast<float*>(tv + AM_TILE_BYTES + AM_WARPS * 1024);
-  int* s_pos = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(s_tbl) + am_tab_bytes(g.ntab));
-  int* s_lin = s_pos + 64; int* s_rg = s_lin + 64; int* s_src = s_rg + 64;
-  const uint32_t tq_s = smem_u32_generic(tq), tk_s = smem_u32_generic(tk), tv_s = smem_u32_generic(tv), stage_s = smem_u32_generic(stage);
+  const int h = blockIdx.x % g.heads, grp = blockIdx.x / g.heads;
+  uint8_t* ring = am_smem_raw;                                             // [2][3][4096]
+  uint8_t* stage = ring + 2 * 3 * AM_TILE_BYTES + warp * 1024;
+  float4* s_frag = reinterpret_cast<float4*>(ring + 2 * 3 * AM_TILE_BYTES + AM_WARPS * 1024);
+  int* s_pos = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(s_frag) + AM_FRAG_BYTES);
+  int* s_lin = s_pos + 64; int* s_rg = s_lin + 64; int* s_src2 = s_rg + 64;   // s_src2: [2][64]
+  float* s_tbl = reinterpret_cast<float*>(ring + 3 * AM_TILE_BYTES);       // scratch inside ring stage 1 (free until the first prefetch)
+  const uint32_t ring_s = smem_u32_generic(ring), stage_s = smem_u32_generic(stage);
   for (int t = tid; t < g.ntab; t += AM_WARPS * 32) s_tbl[t] = __ldg(table + t * g.heads + h) * AM_LOG2E;
   am_init_tables(g, tid, s_pos, s_lin, s_rg);
   __syncthreads();
+  int w = grp;
+  if (w < g.windows) am_issue_window<false>(g, am_window(g, w), h, ring_s, qkv, nullptr, nullptr, nullptr, s_pos, s_src2, nullptr, tid);
+  am_build_bias_frags<false>(s_frag, s_tbl, s_lin, g, tid);
+  const float4* frag = s_frag + warp * 8 * 32 + lane;
   const int gq = lane >> 2, tq4 = lane & 3;
   const int n_mt = (g.N + 15) >> 4;
   const int mt = warp;                                  // this warp's query strip
-  int clin[16], creg[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) { const int j = (c >> 1) * 8 + 2 * tq4 + (c & 1); clin[c] = s_lin[j]; creg[c] = 0; }
   const int r0 = mt * 16 + gq, r1 = r0 + 8;
-  const int lr0 = s_lin[r0], lr1 = s_lin[r1];
-
-  for (int wi = 0; wi < g.win_per_warp; ++wi) {
-    const int w = wg * g.win_per_warp + wi;
-    if (w >= g.windows) break;
+  int creg[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) creg[c] = 0;
+  int st = 0;
+  for (; w < g.windows; w += g.groups, st ^= 1) {
     const AmWin win = am_window(g, w);
     const bool masked = win.last_row || win.last_col;
     const bool has_pad = am_has_pad(g, win);
-    __syncthreads();                                    // previous window fully consumed
-    am_sources(g, win, tid, s_pos, s_src);
-    __syncthreads();
-    am_load_tile(tq_s, qkv, 3 * g.C, h * 32, s_src, tid);
-    am_load_tile(tk_s, qkv, 3 * g.C, g.C + h * 32, s_src, tid);
-    am_load_tile(tv_s, qkv, 3 * g.C, 2 * g.C + h * 32, s_src, tid);
-    if (masked) {
-#pragma unroll
-      for (int c = 0; c < 16; ++c) { const int j = (c >> 1) * 8 + 2 * tq4 + (c & 1); creg[c] = am_region(win, s_rg[j]); }
-    }
     cp_async_wait_all();
+    __syncthreads();                                    // tiles of this window landed; every warp is done with the previous one
+    if (w + g.groups < g.windows)
+      am_issue_window<false>(g, am_window(g, w + g.groups), h, ring_s + (st ^ 1) * 3 * AM_TILE_BYTES, qkv, nullptr, nullptr, nullptr, s_pos,
+                             s_src2 + (st ^ 1) * 64, nullptr, tid);
+    uint8_t* tq = ring + st * 3 * AM_TILE_BYTES;
+    const uint32_t tq_s = ring_s + st * 3 * AM_TILE_BYTES, tk_s = tq_s + AM_TILE_BYTES, tv_s = tk_s + AM_TILE_BYTES;
+    const int* s_src = s_src2 + st * 64;
     if (has_pad) {
-      __syncthreads();
       am_fill_pad_rows(tq, qkv_bias, h * 32, s_src, g.N, tid);
-      am_fill_pad_rows(tk, qkv_bias, g.C + h * 32, s_src, g.N, tid);
-      am_fill_pad_rows(tv, qkv_bias, 2 * g.C + h * 32, s_src, g.N, tid);
+      am_fill_pad_rows(tq + AM_TILE_BYTES, qkv_bias, g.C + h * 32, s_src, g.N, tid);
+      am_fill_pad_rows(tq + 2 * AM_TILE_BYTES, qkv_bias, 2 * g.C + h * 32, s_src, g.N, tid);
+      __syncthreads();
     }
-    __syncthreads();
     if (mt < n_mt) {
+      if (masked) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { const int j = (c >> 1) * 8 + 2 * tq4 + (c & 1); creg[c] = am_region(win, s_rg[j]); }
+      }
       uint32_t a[2][4];
       am_load_a(tq_s, mt, lane, a);
       float acc[8][4];
       am_strip_nt<NTC>(acc, a, tk_s, lane);
-      if (masked) am_scores<NTC, false, true>(acc, g.scale2, s_tbl, g.lin_off, clin, creg, lr0, lr1, am_region(win, s_rg[r0]), am_region(win, s_rg[r1]), g.N, tq4);
-      else am_scores<NTC, false, false>(acc, g.scale2, s_tbl, g.lin_off, clin, creg, lr0, lr1, 0, 0, g.N, tq4);
+      if (masked) am_scores_frag<NTC, true>(acc, g.scale2, frag, creg, am_region(win, s_rg[r0]), am_region(win, s_rg[r1]));
+      else am_scores_frag<NTC, false>(acc, g.scale2, frag, creg, 0, 0);
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int nt = 0; nt < NTC; ++nt) { mx0 = fmaxf(mx0, fmaxf(acc[nt][0], acc[nt][1])); mx1 = fmaxf(mx1, fmaxf(acc[nt][2], acc[nt][3])); }
@@ -358,112 +392,100 @@ __global__ void __launch_bounds__(AM_WARPS * 32, 4) window_attn_mma_fwd_kernel(c
 }
 
 template <int NTC>
-__global__ void __launch_bounds__(AM_WARPS * 32, 3) window_attn_mma_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ qkv,
-                                                                               const bf16* __restrict__ outp, const float* __restrict__ lse,
-                                                                               const float* __restrict__ table, const float* __restrict__ qkv_bias,
-                                                                               bf16* __restrict__ dqkv, float* __restrict__ dtable,
-                                                                               float* __restrict__ dqkv_bias, float* __restrict__ dqkv_colsum,
-                                                                               AmGeom g) {
+__global__ void __launch_bounds__(AM_WARPS * 32, AM_BWD_OCC) window_attn_mma_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ qkv,
+                                                                                        const bf16* __restrict__ outp, const float* __restrict__ lse,
+                                                                                        const float* __restrict__ table, const float* __restrict__ qkv_bias,
+                                                                                        bf16* __restrict__ dqkv, float* __restrict__ dtable,
+                                                                                        float* __restrict__ dqkv_bias, float* __restrict__ dqkv_colsum,
+                                                                                        AmGeom g) {
   extern __shared__ __align__(128) uint8_t am_smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int h = blockIdx.x % g.heads, wg = blockIdx.x / g.heads;
-  uint8_t* tq = am_smem_raw; uint8_t* tk = tq + AM_TILE_BYTES; uint8_t* tv = tk + AM_TILE_BYTES; uint8_t* tdo = tv + AM_TILE_BYTES;
-  uint8_t* stage = tdo + AM_TILE_BYTES + warp * 1024;
-  uint8_t* sds = tdo + AM_TILE_BYTES + AM_WARPS * 1024 + warp * 2048;          // this warp's dS^T strip [16 keys][64 queries] bf16
-  float* slabs = reinterpret_cast<float*>(tdo + AM_TILE_BYTES + AM_WARPS * 1024 + AM_WARPS * 2048);
-  float* slab = slabs + warp * 64 * AM_SLAB_LD;                                // this warp's partial dQ [64][AM_SLAB_LD]
-  float* s_tbl = slabs + AM_WARPS * 64 * AM_SLAB_LD;
-  const int tab_bytes = am_tab_bytes(g.ntab);
-  float* s_bins = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_tbl) + tab_bytes);
-  int* s_pos = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(s_bins) + tab_bytes);
-  int* s_lin = s_pos + 64; int* s_rg = s_lin + 64; int* s_src = s_rg + 64;
-  float* s_delta = reinterpret_cast<float*>(s_src + 64);
-  float* s_lse = s_delta + 64;
-  const uint32_t tq_s = smem_u32_generic(tq), tk_s = smem_u32_generic(tk), tv_s = smem_u32_generic(tv), tdo_s = smem_u32_generic(tdo),
-                 stage_s = smem_u32_generic(stage), sds_s = smem_u32_generic(sds);
-  for (int t = tid; t < g.ntab; t += AM_WARPS * 32) { s_tbl[t] = __ldg(table + t * g.heads + h) * AM_LOG2E; s_bins[t] = 0.f; }
+  const int h = blockIdx.x % g.heads, grp = blockIdx.x / g.heads;
+  uint8_t* ring = am_smem_raw;                                             // [2][5][4096]
+  uint8_t* stage = ring + 2 * 5 * AM_TILE_BYTES + warp * 1024;
+  uint8_t* sds_all = ring + 2 * 5 * AM_TILE_BYTES + AM_WARPS * 1024;       // dS^T [64 keys][64 queries] bf16, 16-byte chunks swizzled by key row
+  float4* s_frag = reinterpret_cast<float4*>(sds_all + 64 * 128);
+  int* s_pos = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(s_frag) + AM_FRAG_BYTES);
+  int* s_lin = s_pos + 64; int* s_rg = s_lin + 64; int* s_src2 = s_rg + 64;   // s_src2: [2][64]
+  float* s_lse2 = reinterpret_cast<float*>(s_src2 + 128);                  // [2][64]
+  float* s_delta = s_lse2 + 128;
+  float* s_cs = s_delta + 64;                                              // [4 warps][3][32]
+  float* s_tbl = reinterpret_cast<float*>(ring + 5 * AM_TILE_BYTES);       // scratch inside ring stage 1 (free until the first prefetch)
+  const uint32_t ring_s = smem_u32_generic(ring), stage_s = smem_u32_generic(stage), sds_all_s = smem_u32_generic(sds_all);
+  const uint32_t sds_s = sds_all_s + warp * 2048;                          // this warp's dS^T strip [16 keys][64 queries]
+  for (int t = tid; t < g.ntab; t += AM_WARPS * 32) s_tbl[t] = __ldg(table + t * g.heads + h) * AM_LOG2E;
   am_init_tables(g, tid, s_pos, s_lin, s_rg);
   __syncthreads();
+  int w = grp;
+  if (w < g.windows) am_issue_window<true>(g, am_window(g, w), h, ring_s, qkv, dout, outp, lse, s_pos, s_src2, s_lse2, tid);
+  am_build_bias_frags<true>(s_frag, s_tbl, s_lin, g, tid);
+  const float4* frag = s_frag + warp * 8 * 32 + lane;
   const int gq = lane >> 2, tq4 = lane & 3;
   const int n_mt = (g.N + 15) >> 4;
-  const int jt = warp;                                  // this warp's key strip
-  int clin[16], creg[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) { const int j = (c >> 1) * 8 + 2 * tq4 + (c & 1); clin[c] = s_lin[j]; creg[c] = 0; }
+  const int jt = warp;                                  // this warp's key strip (and its query strip for dQ)
   const int r0 = jt * 16 + gq, r1 = r0 + 8;
-  const int lr0 = s_lin[r0], lr1 = s_lin[r1];
-  const bool row0_ok = r0 < g.N, row1_ok = r1 < g.N;
+  int creg[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) creg[c] = 0;
   float gsum[8][4];                     // dS^T of this warp's strip summed over the CTA's windows (bias-table gradient)
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) gsum[nt][0] = gsum[nt][1] = gsum[nt][2] = gsum[nt][3] = 0.f;
-  float cs_k[8], cs_v[8], cs_q[8];      // qkv-bias gradient partials
+  float cs_k[8], cs_v[8], cs_q[8];      // qkv-bias gradient partials: columns 8*nt + 2*t + {0,1} of this head
 #pragma unroll
   for (int k = 0; k < 8; ++k) cs_k[k] = cs_v[k] = cs_q[k] = 0.f;
-  const float2* lse2 = reinterpret_cast<const float2*>(s_lse) + tq4;
-  const float2* del2 = reinterpret_cast<const float2*>(s_delta) + tq4;
-
-  for (int wi = 0; wi < g.win_per_warp; ++wi) {
-    const int w = wg * g.win_per_warp + wi;
-    if (w >= g.windows) break;
+  int st = 0;
+  for (; w < g.windows; w += g.groups, st ^= 1) {
     const AmWin win = am_window(g, w);
     const bool masked = win.last_row || win.last_col;
     const bool has_pad = am_has_pad(g, win);
-    __syncthreads();                                    // previous window fully consumed (tiles, slabs, tables)
-    am_sources(g, win, tid, s_pos, s_src);
-    __syncthreads();
-    am_load_tile(tq_s, qkv, 3 * g.C, h * 32, s_src, tid);
-    am_load_tile(tk_s, qkv, 3 * g.C, g.C + h * 32, s_src, tid);
-    am_load_tile(tv_s, qkv, 3 * g.C, 2 * g.C + h * 32, s_src, tid);
-    am_load_tile(tdo_s, dout, g.C, h * 32, s_src, tid);      // padded tokens: dO = 0 (cropped away)
-    // delta_i = dO_i . O_i straight from global (4 lanes per token, 16 bytes each); log-sum-exp of the query rows
-#pragma unroll
-    for (int it0 = 0; it0 < 64 * 4; it0 += AM_WARPS * 32) {
-      const int it = it0 + tid;
-      const int tok = it >> 2, ch = it & 3;
-      float part = 0.f;
-      const int src = s_src[tok];
-      if (src >= 0) {
-        float a[8], b[8];
-        IO<bf16>::load8(dout + (int64_t)src * g.C + h * 32 + ch * 8, a);
-        IO<bf16>::load8(outp + (int64_t)src * g.C + h * 32 + ch * 8, b);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) part = fmaf(a[k], b[k], part);
-      }
-      part = quad_sum(part);
-      if (ch == 0) {
-        s_delta[tok] = part;
-        s_lse[tok] = src >= 0 ? __ldg(lse + (int64_t)src * g.heads + h) : 1e30f;   // padded / absent query: P = 0
-      }
-    }
-    if (masked) {
-#pragma unroll
-      for (int c = 0; c < 16; ++c) { const int j = (c >> 1) * 8 + 2 * tq4 + (c & 1); creg[c] = am_region(win, s_rg[j]); }
-    }
     cp_async_wait_all();
+    __syncthreads();                                    // S1: tiles of this window landed; every warp is done with the previous one
+    if (w + g.groups < g.windows)
+      am_issue_window<true>(g, am_window(g, w + g.groups), h, ring_s + (st ^ 1) * 5 * AM_TILE_BYTES, qkv, dout, outp, lse, s_pos,
+                            s_src2 + (st ^ 1) * 64, s_lse2 + (st ^ 1) * 64, tid);
+    uint8_t* tq = ring + st * 5 * AM_TILE_BYTES;
+    const uint32_t tq_s = ring_s + st * 5 * AM_TILE_BYTES, tk_s = tq_s + AM_TILE_BYTES, tv_s = tk_s + AM_TILE_BYTES, tdo_s = tv_s + AM_TILE_BYTES;
+    const int* s_src = s_src2 + st * 64;
+    const float2* lse2 = reinterpret_cast<const float2*>(s_lse2 + st * 64) + tq4;
+    const float2* del2 = reinterpret_cast<const float2*>(s_delta) + tq4;
     if (has_pad) {
-      __syncthreads();
       am_fill_pad_rows(tq, qkv_bias, h * 32, s_src, g.N, tid);
-      am_fill_pad_rows(tk, qkv_bias, g.C + h * 32, s_src, g.N, tid);
-      am_fill_pad_rows(tv, qkv_bias, 2 * g.C + h * 32, s_src, g.N, tid);
+      am_fill_pad_rows(tq + AM_TILE_BYTES, qkv_bias, g.C + h * 32, s_src, g.N, tid);
+      am_fill_pad_rows(tq + 2 * AM_TILE_BYTES, qkv_bias, 2 * g.C + h * 32, s_src, g.N, tid);
     }
-    __syncthreads();
+    // delta_i = dO_i . O_i from the shared tiles (4 lanes per token, 16 bytes each)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int tok = k * 32 + (tid >> 2), ch = tid & 3;
+      const uint4 a = *reinterpret_cast<const uint4*>(tq + 3 * AM_TILE_BYTES + am_off(tok, ch));
+      const uint4 b = *reinterpret_cast<const uint4*>(tq + 4 * AM_TILE_BYTES + am_off(tok, ch));
+      const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+      const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float2 fa = __bfloat1622float2(ha[i]), fb = __bfloat1622float2(hb[i]); part = fmaf(fa.x, fb.x, part); part = fmaf(fa.y, fb.y, part); }
+      part = quad_sum(part);
+      if (ch == 0) s_delta[tok] = part;
+    }
+    __syncthreads();                                    // S2: delta (and pad rows) visible
 
     if (jt < n_mt) {
+      if (masked) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { const int j = (c >> 1) * 8 + 2 * tq4 + (c & 1); creg[c] = am_region(win, s_rg[j]); }
+      }
       uint32_t a[2][4];
       am_load_a(tk_s, jt, lane, a);
       float acc[8][4];
       am_strip_nt<NTC>(acc, a, tq_s, lane);          // S^T[j][i] = k_j . q_i
-      if (masked) am_scores<NTC, true, true>(acc, g.scale2, s_tbl, g.lin_off, clin, creg, lr0, lr1, am_region(win, s_rg[r0]), am_region(win, s_rg[r1]), g.N, tq4);
-      else am_scores<NTC, true, false>(acc, g.scale2, s_tbl, g.lin_off, clin, creg, lr0, lr1, 0, 0, g.N, tq4);
+      if (masked) am_scores_frag<NTC, true>(acc, g.scale2, frag, creg, am_region(win, s_rg[r0]), am_region(win, s_rg[r1]));
+      else am_scores_frag<NTC, false>(acc, g.scale2, frag, creg, 0, 0);
       uint32_t pt[4][4];
 #pragma unroll
       for (int nt = 0; nt < NTC; ++nt) {
         const float2 ls = lse2[nt * 4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float pv = ex2f(acc[nt][e] - ((e & 1) ? ls.y : ls.x));   // -inf / lse 1e30 -> 0
-          acc[nt][e] = ((e >> 1) ? row1_ok : row0_ok) ? pv : 0.f;
-        }
+        for (int e = 0; e < 4; ++e) acc[nt][e] = ex2f(acc[nt][e] - ((e & 1) ? ls.y : ls.x));   // -inf / lse 1e30 -> 0
         pt[nt >> 1][(nt & 1) * 2] = pack_bf16(acc[nt][0], acc[nt][1]);
         pt[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(acc[nt][2], acc[nt][3]);
       }
@@ -491,8 +513,7 @@ __global__ void __launch_bounds__(AM_WARPS * 32, 3) window_attn_mma_bwd_kernel(c
       if (NTC == 7) { dst[3][2] = 0u; dst[3][3] = 0u; }
       am_strip_pv(o, dst, tq_s, lane);          // dK[j][d] = scale * sum_i dS[i][j] q[i][d]
       am_store_strip(o, g.scale, g.scale, stage_s, stage, lane, jt, g.N, s_src, dqkv, 3 * g.C, g.C + h * 32, has_pad ? dqkv_bias : nullptr, dqkv_colsum ? cs_k : nullptr);
-      // dS^T strip -> shared [16 keys][64 queries] (16-byte chunks swizzled by key row), then partial dQ = dS * K_strip
-      __syncwarp();
+      // dS^T strip -> shared [16 keys][64 queries] (16-byte chunks swizzled by key row)
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         const int c0 = ks * 2, c1 = ks * 2 + 1;   // 16-byte chunk index = query column / 8
@@ -501,86 +522,68 @@ __global__ void __launch_bounds__(AM_WARPS * 32, 3) window_attn_mma_bwd_kernel(c
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(sds_s + gq * 128 + ((c1 ^ (gq & 7)) << 4) + tq4 * 4), "r"(dst[ks][2]) : "memory");
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(sds_s + (gq + 8) * 128 + ((c1 ^ ((gq + 8) & 7)) << 4) + tq4 * 4), "r"(dst[ks][3]) : "memory");
       }
-      __syncwarp();
-      uint32_t kb[4][2];            // B fragments: K strip [k = 16 keys][n = 32 channels], transposed loads from the K tile
+    }
+    __syncthreads();                                    // S3: dS^T complete
+    if (jt < n_mt) {
+      // dQ strip jt = scale * dS[16 queries][keys] * K: A = transposed loads from dS^T, B = transposed loads from the K tile
+      float dq[4][4];
 #pragma unroll
-      for (int np = 0; np < 2; ++np) {
-        const int mi = lane >> 3;
-        ldsm_x4_t(tk_s + am_off(jt * 16 + (mi & 1) * 8 + (lane & 7), np * 2 + (mi >> 1)), kb[np * 2][0], kb[np * 2][1], kb[np * 2 + 1][0], kb[np * 2 + 1][1]);
-      }
+      for (int nt = 0; nt < 4; ++nt) dq[nt][0] = dq[nt][1] = dq[nt][2] = dq[nt][3] = 0.f;
+      const int mi = lane >> 3;
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {          // query strips
-        if (it < n_mt) {
-          uint32_t a0, a1, a2, a3;               // A fragment (16 queries x 16 keys) = transpose of the stored [key][query] block
-          const int mi = lane >> 3;
-          const int key = (mi >> 1) * 8 + (lane & 7), chunk = it * 2 + (mi & 1);
-          ldsm_x4_t(sds_s + key * 128 + ((chunk ^ (key & 7)) << 4), a0, a1, a2, a3);
-          float dq[4][4];
+      for (int ks = 0; ks < 4; ++ks) {
+        if (ks < n_mt) {
+          uint32_t a0, a1, a2, a3;
+          const int key = (mi >> 1) * 8 + (lane & 7), chunk = jt * 2 + (mi & 1);
+          ldsm_x4_t(sds_all_s + ks * 2048 + key * 128 + ((chunk ^ (key & 7)) << 4), a0, a1, a2, a3);
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) {
-            dq[nt][0] = dq[nt][1] = dq[nt][2] = dq[nt][3] = 0.f;
-            mma_bf16(dq[nt], a0, a1, a2, a3, kb[nt][0], kb[nt][1]);
-            float* p0 = slab + (it * 16 + gq) * AM_SLAB_LD + nt * 8 + 2 * tq4;
-            *reinterpret_cast<float2*>(p0) = make_float2(dq[nt][0], dq[nt][1]);
-            *reinterpret_cast<float2*>(p0 + 8 * AM_SLAB_LD) = make_float2(dq[nt][2], dq[nt][3]);
+          for (int np = 0; np < 2; ++np) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4_t(tk_s + am_off(ks * 16 + (mi & 1) * 8 + (lane & 7), np * 2 + (mi >> 1)), b0, b1, b2, b3);
+            mma_bf16(dq[np * 2], a0, a1, a2, a3, b0, b1);
+            mma_bf16(dq[np * 2 + 1], a0, a1, a2, a3, b2, b3);
           }
         }
       }
-    }
-    __syncthreads();
-    // dQ = scale * sum over key strips of the partial slabs -> bf16 -> global (64-byte row segments)
-#pragma unroll
-    for (int it0 = 0; it0 < 64 * 4; it0 += AM_WARPS * 32) {
-      const int it = it0 + tid;
-      const int tok = it >> 2, ch = it & 3;
-      const int src = s_src[tok];
-      float v[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = 0.f;
-      for (int sw = 0; sw < n_mt; ++sw) {
-        const float4* p = reinterpret_cast<const float4*>(slabs + (sw * 64 + tok) * AM_SLAB_LD + ch * 8);
-        const float4 x = p[0], y = p[1];
-        v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w; v[4] += y.x; v[5] += y.y; v[6] += y.z; v[7] += y.w;
-      }
-      if (src >= 0) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { v[k] *= g.scale; cs_q[k] += v[k]; }
-        IO<bf16>::store8(dqkv + (int64_t)src * 3 * g.C + h * 32 + ch * 8, v);
-      }
+      am_store_strip(dq, g.scale, g.scale, stage_s, stage, lane, jt, g.N, s_src, dqkv, 3 * g.C, h * 32, nullptr, dqkv_colsum ? cs_q : nullptr);
     }
   }
-  // ---- flush: bias-table gradient (register sums -> shared bins -> global), qkv-bias gradient ----
+  // ---- flush (once per CTA): bias-table gradient and qkv-bias gradient ----
+  __syncthreads();
+  float* Gm = reinterpret_cast<float*>(ring);           // [64 keys][AM_G_LD] sums of dS^T over this CTA's windows
   if (jt < n_mt) {
 #pragma unroll
-    for (int nt = 0; nt < NTC; ++nt)
+    for (int nt = 0; nt < NTC; ++nt) {
+      *reinterpret_cast<float2*>(Gm + r0 * AM_G_LD + nt * 8 + 2 * tq4) = make_float2(gsum[nt][0], gsum[nt][1]);
+      *reinterpret_cast<float2*>(Gm + r1 * AM_G_LD + nt * 8 + 2 * tq4) = make_float2(gsum[nt][2], gsum[nt][3]);
+    }
+  }
+  if (dqkv_colsum) {
+    // columns 8*nt + 2*t + {0,1} per lane: sum over the 8 row groups (lanes with the same t), then over the warps
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = nt * 8 + 2 * tq4 + (e & 1), row = (e >> 1) ? r1 : r0;
-        if (col < g.N && row < g.N) atomicAdd(&s_bins[clin[nt * 2 + (e & 1)] - ((e >> 1) ? lr1 : lr0) + g.lin_off], gsum[nt][e]);
+    for (int k = 0; k < 8; ++k) {
+      float q = cs_q[k], kk = cs_k[k], v = cs_v[k];
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) { q += __shfl_xor_sync(0xffffffffu, q, o); kk += __shfl_xor_sync(0xffffffffu, kk, o); v += __shfl_xor_sync(0xffffffffu, v, o); }
+      if (gq == 0) {
+        const int col = (k >> 1) * 8 + 2 * tq4 + (k & 1);
+        s_cs[warp * 96 + col] = q; s_cs[warp * 96 + 32 + col] = kk; s_cs[warp * 96 + 64 + col] = v;
       }
+    }
   }
   __syncthreads();
-  for (int t = tid; t < g.ntab; t += AM_WARPS * 32) { const float v = s_bins[t]; if (v != 0.f) atomicAdd(dtable + t * g.heads + h, v); }
-  if (dqkv_colsum) {
-    // k / v partials: columns 8*nt + 2*t + {0,1} per lane, summed over the 8 row groups (lanes with the same t)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float kk = cs_k[k], v = cs_v[k];
-#pragma unroll
-      for (int o = 4; o < 32; o <<= 1) { kk += __shfl_xor_sync(0xffffffffu, kk, o); v += __shfl_xor_sync(0xffffffffu, v, o); }
-      if (gq == 0) {
-        const int col = h * 32 + (k >> 1) * 8 + 2 * tq4 + (k & 1);
-        atomicAdd(dqkv_colsum + g.C + col, kk); atomicAdd(dqkv_colsum + 2 * g.C + col, v);
-      }
-    }
-    // q partials: thread (tok, ch) pattern -> columns ch*8 + k, summed over lanes with the same ch (lane & 3)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float q = cs_q[k];
-#pragma unroll
-      for (int o = 4; o < 32; o <<= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-      if (gq == 0) atomicAdd(dqkv_colsum + h * 32 + tq4 * 8 + k, q);
-    }
+  // bin t = (dy + wh - 1) * (2 ww - 1) + (dx + ww - 1) collects dS[i][j] over all pairs with (yi - yj, xi - xj) = (dy, dx)
+  for (int t = tid; t < g.ntab; t += AM_WARPS * 32) {
+    const int dy = t / g.lin_stride - (g.wh - 1), dx = t % g.lin_stride - (g.ww - 1);
+    float v = 0.f;
+    for (int yj = max(0, -dy); yj < min(g.wh, g.wh - dy); ++yj)
+      for (int xj = max(0, -dx); xj < min(g.ww, g.ww - dx); ++xj)
+        v += Gm[(yj * g.ww + xj) * AM_G_LD + (yj + dy) * g.ww + xj + dx];
+    if (v != 0.f) atomicAdd(dtable + t * g.heads + h, v);
+  }
+  if (dqkv_colsum && tid < 96) {
+    const float v = s_cs[tid] + s_cs[96 + tid] + s_cs[192 + tid] + s_cs[288 + tid];
+    atomicAdd(dqkv_colsum + (tid >> 5) * g.C + h * 32 + (tid & 31), v);
   }
 }
 
@@ -596,18 +599,32 @@ static int am_geom(AmGeom& g, int B, int H, int W, int C, int heads, int wh, int
   g.scale = 1.0f / sqrtf(32.0f);
   g.scale2 = g.scale * AM_LOG2E;
   g.windows = B * g.nwy * g.nwx;
+  g.groups = 1;
   return MTUS_OK;
 }
 
 bool mtus_window_attn_mma_supported(int wh, int ww, int dtype) { return dtype == MTUS_BF16 && wh * ww <= 64 && wh > 0 && ww > 0; }
 
-// windows per CTA: enough CTAs to fill the machine several times over, otherwise as many windows per CTA as possible
-// (table loads, bias-gradient flushes and launch overhead amortise over them)
-static int am_plan(AmGeom& g, int target_ctas) {
-  int wpw = 1;
-  while ((int64_t)((g.windows + wpw * 2 - 1) / (wpw * 2)) * g.heads >= target_ctas && wpw < 32) wpw *= 2;
-  g.win_per_warp = wpw;
-  return ((g.windows + wpw - 1) / wpw) * g.heads;
+static int am_sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n = v > 0 ? v : 148;
+  }
+  return n;
+}
+
+// one wave of persistent CTAs: G CTAs per head, each walking windows g, g + G, ...; G is the largest count that fits
+// the machine, then reduced to the smallest count with the same number of windows per CTA (fewer set-ups / flushes)
+static int am_plan(AmGeom& g, int ctas_per_sm) {
+  int G = (am_sm_count() * ctas_per_sm) / g.heads;
+  if (G < 1) G = 1;
+  if (G > g.windows) G = g.windows;
+  const int per = (g.windows + G - 1) / G;
+  G = (g.windows + per - 1) / per;
+  g.groups = G;
+  return G * g.heads;
 }
 
 int mtus_window_attn_mma_fwd(const void* qkv, const float* rel_table, const float* qkv_bias, void* out, float* lse, int B, int H, int W,
@@ -617,8 +634,15 @@ int mtus_window_attn_mma_fwd(const void* qkv, const float* rel_table, const floa
   if (rc) return rc;
   if ((g.Hp != H || g.Wp != W) && !qkv_bias) return MTUS_ERR_BAD_ARG;
   if (B == 0) return MTUS_OK;
-  const int blocks = am_plan(g, 148 * 4 * AM_WAVES);
-  const size_t smem = am_cta_bytes(g.ntab, false);
+  const int blocks = am_plan(g, AM_FWD_OCC);
+  const size_t smem = am_cta_bytes(false);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(window_attn_mma_fwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(window_attn_mma_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
   if (g.N <= 56) window_attn_mma_fwd_kernel<7><<<blocks, AM_WARPS * 32, smem, st>>>((const bf16*)qkv, rel_table, qkv_bias, (bf16*)out, lse, g);
   else window_attn_mma_fwd_kernel<8><<<blocks, AM_WARPS * 32, smem, st>>>((const bf16*)qkv, rel_table, qkv_bias, (bf16*)out, lse, g);
   MTUS_LAUNCH_STATUS();
@@ -634,12 +658,12 @@ int mtus_window_attn_mma_bwd(const void* dout, const void* qkv, const void* out,
   if (!lse) return MTUS_ERR_BAD_ARG;
   if ((g.Hp != H || g.Wp != W) && !(qkv_bias && dqkv_bias)) return MTUS_ERR_BAD_ARG;
   if (B == 0) return MTUS_OK;
-  const int blocks = am_plan(g, 148 * 3 * AM_WAVES);
-  const size_t smem = am_cta_bytes(g.ntab, true);
+  const int blocks = am_plan(g, AM_BWD_OCC);
+  const size_t smem = am_cta_bytes(true);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(window_attn_mma_bwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(window_attn_mma_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(window_attn_mma_bwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(window_attn_mma_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }

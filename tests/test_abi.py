@@ -36,7 +36,7 @@ def test_version_and_status_strings(lib):
 def test_null_arguments_are_rejected_without_touching_the_gpu(lib):
     # argument validation happens before any CUDA call: usable (and required to hold) on a CPU-only box
     assert lib.mtus_layernorm_fwd(None, None, None, None, None, None, 4, 32, 1e-5, 0, None) == -1
-    assert lib.mtus_window_attn_fwd(None, None, None, None, 1, 7, 7, 32, 1, 7, 7, 0, 0, 0, None) == -1
+    assert lib.mtus_window_attn_fwd(None, None, None, None, None, 1, 7, 7, 32, 1, 7, 7, 0, 0, 0, None) == -1
     assert lib.mtus_swin_forward(None, None, 1, None, None, None, None, None, 0, 0, None) == -1
 
 

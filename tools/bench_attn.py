@@ -34,10 +34,10 @@ def main():
         tab = torch.randn(169, heads, device=dev) * 0.1
         bias = torch.zeros(3 * C, device=dev)
         for shift in ((0, 3) if res > 7 else (0,)):
-            out = ops.window_attn_fwd(qkv, tab, bias, heads, 7, shift)
+            out, lse = ops.window_attn_fwd(qkv, tab, bias, heads, 7, shift, return_lse=True)
             dout = torch.randn_like(out)
             tf = timeit(lambda: ops.window_attn_fwd(qkv, tab, bias, heads, 7, shift))
-            tb = timeit(lambda: ops.window_attn_bwd(dout, qkv, out, tab, bias, heads, 7, shift))
+            tb = timeit(lambda: ops.window_attn_bwd(dout, qkv, out, tab, bias, heads, 7, shift, lse=lse, with_colsum=True))
             tokens = B * res * res
             byf, byb = 4.0 * tokens * C * 2, 8.0 * tokens * C * 2
             fl = 4.0 * 49 * 49 * 32 * (tokens / 49) * heads
