@@ -72,21 +72,55 @@ class FlatParamModule(nn.Module):
         self._flat = flat
 
     def flat_params(self) -> torch.Tensor:
-        """The flat fp32 parameter buffer; re-flattens if somebody re-pointed a parameter."""
+        """The flat fp32 parameter buffer; re-flattens if somebody re-pointed a parameter.
+
+        Whole-module moves / casts go through ``_apply`` (which re-flattens) and ``load_state_dict`` copies in
+        place, so the per-step check only probes a few parameters; ``flat_params(full_check=True)`` probes all."""
+        return self._flat_checked(False)
+
+    def _flat_checked(self, full_check: bool) -> torch.Tensor:
         base = self._flat.data_ptr()
-        for param, off, numel, shape in self._params_by_name.values():
+        entries = self._entries()
+        probe = entries if full_check else (entries[0], entries[len(entries) // 2], entries[-1])
+        for param, off, numel, shape in probe:
             if param.data_ptr() != base + 4 * off or param.dtype != torch.float32:
                 self._reflatten()
                 break
         return self._flat
 
+    def _entries(self):
+        e = getattr(self, "_entries_cache", None)
+        if e is None or len(e) != len(self._params_by_name):
+            e = self._entries_cache = list(self._params_by_name.values())
+            self._ordered_cache = [v[0] for v in e]
+            # split plan for grad_views: parameter pieces interleaved with the alignment gaps between them
+            sizes, pick, pos = [], [], 0
+            for param, off, numel, shape in e:
+                if off > pos:
+                    sizes.append(off - pos)
+                pick.append(len(sizes))
+                sizes.append(numel)
+                pos = off + numel
+            if pos < self._n_flat:
+                sizes.append(self._n_flat - pos)
+            self._split_sizes, self._split_pick = sizes, pick
+        return e
+
     def ordered_params(self):
-        return [v[0] for v in self._params_by_name.values()]
+        self._entries()
+        return self._ordered_cache
 
     def grad_views(self, flat_grad: torch.Tensor, needs):
+        """Per-parameter views of the flat gradient block (one split call + a reshape for the >1-D tensors)."""
+        entries = self._entries()
+        pieces = flat_grad.split_with_sizes(self._split_sizes)
         out = []
-        for (param, off, numel, shape), need in zip(self._params_by_name.values(), needs):
-            out.append(flat_grad[off:off + numel].view(shape) if need else None)
+        for (param, off, numel, shape), idx, need in zip(entries, self._split_pick, needs):
+            if not need:
+                out.append(None)
+            else:
+                v = pieces[idx]
+                out.append(v if len(shape) == 1 else v.view(shape))
         return out
 
 

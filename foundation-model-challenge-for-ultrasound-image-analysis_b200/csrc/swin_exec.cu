@@ -12,6 +12,7 @@
 // Activations saved for backward live in one caller-provided workspace laid out by plan().
 #include "common.cuh"
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -40,7 +41,7 @@ struct Plan {
   // activations
   size_t cols, pe_pre, pe_mean, pe_rstd, x0;
   StageA sa[4];
-  size_t G, Gb, dLN, dQKV, dH, tmpF;
+  size_t G, Gb, Gb2, dLN, dQKV, dH, tmpF;
   size_t ws_bytes;
 };
 
@@ -161,9 +162,9 @@ bool build_plan(const mtus_swin_config* c, Plan& p) {
   }
   if (p.training) {
     const size_t E0 = (size_t)p.M[0] * p.C0;            // M_i*C_i is largest at stage 0
-    p.G = a.take(E0 * 4); p.tmpF = a.take(E0 * 4); p.Gb = a.take(E0 * es); p.dLN = a.take(E0 * es);
+    p.G = a.take(E0 * 4); p.tmpF = a.take(E0 * 4); p.Gb = a.take(E0 * es); p.Gb2 = a.take(E0 * es); p.dLN = a.take(E0 * es);
     p.dQKV = a.take(3 * E0 * es); p.dH = a.take(4 * E0 * es);
-  } else p.G = p.Gb = p.dLN = p.tmpF = p.dQKV = p.dH = 0;
+  } else p.G = p.Gb = p.Gb2 = p.dLN = p.tmpF = p.dQKV = p.dH = 0;
   p.ws_bytes = a.off;
   return true;
 }
@@ -174,6 +175,41 @@ size_t block_xin(const Plan& p, int i, int j) {
 }
 
 #define RUN(expr) do { int rc__ = (expr); if (rc__ != MTUS_OK) { fprintf(stderr, "mtus swin_exec: %s -> %d (%s) at %s:%d\n", #expr, rc__, mtus_status_string(rc__), __FILE__, __LINE__); return rc__; } } while (0)
+
+
+// Weight-gradient GEMMs have no consumer inside the backward chain, so they run on a side stream and fill the SMs the
+// dependent chain (dgrad -> LayerNorm backward -> attention backward -> ...) leaves idle: tails of the persistent GEMMs,
+// the bandwidth-bound LayerNorm / attention kernels.  Fork / join is done with events only (graph-capturable):
+//   E1 (main -> side): dH ready (after dgrad fc2)           -> wgrad fc2, wgrad fc1      -> D1 (side -> main)
+//   E2 (main -> side): dQKV ready (after attention backward) -> wgrad proj, wgrad qkv     -> D2 (side -> main)
+// main waits D1 before LayerNorm-1 backward overwrites Gb (read by wgrad fc2) and, one block later, before dgrad fc2
+// overwrites dH; it waits D2 of the previous block before LayerNorm-2 backward overwrites Gb2 (read by wgrad proj) and
+// attention backward overwrites dQKV.  MTUS_WGRAD_STREAM=0 keeps everything on the caller's stream.
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t e1 = nullptr, e2 = nullptr, d1 = nullptr, d2 = nullptr;
+  int state = 0;   // 0 unknown, 1 ready, -1 disabled
+};
+SideStream g_side[16];
+
+SideStream* side_stream() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStream& ss = g_side[dev];
+  if (ss.state == 0) {
+    const char* e = getenv("MTUS_WGRAD_STREAM");
+    if (e && atoi(e) == 0) { ss.state = -1; return nullptr; }
+    bool ok = cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ss.e1, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ss.e2, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ss.d1, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ss.d2, cudaEventDisableTiming) == cudaSuccess;
+    ss.state = ok ? 1 : -1;
+  }
+  return ss.state == 1 ? &ss : nullptr;
+}
+
+#define CU(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return (int)e__; } while (0)
 
 }  // namespace
 
@@ -305,18 +341,20 @@ extern "C" int mtus_swin_backward(const mtus_swin_config* cfg, const float* para
   auto A = [&](size_t off) -> void* { return ws + off; };
   auto FA = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   float* G = FA(p.G); float* tmpF = FA(p.tmpF);
-  void* Gb = A(p.Gb); void* dLN = A(p.dLN); void* dQKV = A(p.dQKV); void* dH = A(p.dH);
-  // The gradient w.r.t. the residual stream lives in fp32 (G).  Gb is its copy in the GEMM operand dtype, already
-  // multiplied by the drop-path scale of the branch that consumes it; whoever writes Gb also adds its column sums to
-  // the bias gradient of that branch's output Linear, so no separate cast / scale / column-sum passes exist.
+  void* Gb = A(p.Gb); void* Gb2 = A(p.Gb2); void* dLN = A(p.dLN); void* dQKV = A(p.dQKV); void* dH = A(p.dH);
+  // The gradient w.r.t. the residual stream lives in fp32 (G).  Gb (MLP branch) / Gb2 (attention branch) are its copies
+  // in the GEMM operand dtype, already multiplied by the drop-path scale of the branch that consumes them; whoever
+  // writes them also adds their column sums to the bias gradient of that branch's output Linear, so no separate
+  // cast / scale / column-sum passes exist.
+  SideStream* ss = side_stream();
+  void* wst = ss ? (void*)ss->s : stream;     // stream of the weight-gradient GEMMs
+  bool d2_pending = false;
 
   // dfeat (caller layout / dtype) -> fp32 NHWC
   auto load_dfeat = [&](int i, float* dst) -> int {
-    const int64_t M = p.M[i];
     if (dfeats_layout == 0) return mtus_convert(dfeats[i], dst, p.B, p.C[i], p.res[i] * p.res[i], 1, dfeats_f32, 1, dt, stream);
     if (dfeats_f32 && dt != MTUS_F32) return MTUS_ERR_BAD_ARG;
     return mtus_convert(dfeats[i], dst, p.B, p.res[i] * p.res[i], p.C[i], 0, dt == MTUS_F32, 1, dt, stream);
-    (void)M;
   };
 
   int gblk_end = 0;
@@ -341,27 +379,35 @@ extern "C" int mtus_swin_backward(const mtus_swin_config* cfg, const float* para
       const int shift = (j % 2) ? p.shift[i] : 0;
       const float* dp1 = droppath ? droppath + (size_t)(2 * gblk) * p.B : nullptr;
       // ---- MLP branch (Gb = dp2 * G; fc2.bias gradient already accumulated by the producer of Gb) ----
-      RUN(mtus_linear_wgrad(Gb, A(ba.a), GR(bp.fc2w), nullptr, M, Cc, 4 * Cc, dt, be, stream));
       RUN(mtus_linear_dgrad(Gb, W(bp.fc2w), dH, A(ba.h), nullptr, 1, GR(bp.fc1b), M, Cc, 4 * Cc, dt, be, stream));
-      RUN(mtus_linear_wgrad(dH, A(ba.ln2), GR(bp.fc1w), nullptr, M, 4 * Cc, Cc, dt, be, stream));
+      if (ss) { CU(cudaEventRecord(ss->e1, st)); CU(cudaStreamWaitEvent(ss->s, ss->e1, 0)); }
+      RUN(mtus_linear_wgrad(Gb, A(ba.a), GR(bp.fc2w), nullptr, M, Cc, 4 * Cc, dt, be, wst));
+      RUN(mtus_linear_wgrad(dH, A(ba.ln2), GR(bp.fc1w), nullptr, M, 4 * Cc, Cc, dt, be, wst));
+      if (ss) CU(cudaEventRecord(ss->d1, ss->s));
       RUN(mtus_linear_dgrad(dH, W(bp.fc1w), dLN, nullptr, nullptr, 1, nullptr, M, 4 * Cc, Cc, dt, be, stream));
-      RUN(mtus_layernorm_bwd_mixed(dLN, 0, A(ba.xmid), 1, F(bp.n2w), FA(ba.mean2), FA(ba.rstd2), G, G, Gb, dp1, rps, GR(bp.projb),
+      if (ss && d2_pending) { CU(cudaStreamWaitEvent(st, ss->d2, 0)); d2_pending = false; }   // Gb2 / dQKV free again
+      RUN(mtus_layernorm_bwd_mixed(dLN, 0, A(ba.xmid), 1, F(bp.n2w), FA(ba.mean2), FA(ba.rstd2), G, G, Gb2, dp1, rps, GR(bp.projb),
                                    GR(bp.n2w), GR(bp.n2b), M, Cc, dt, stream));
-      // ---- attention branch (Gb = dp1 * G) ----
-      RUN(mtus_linear_wgrad(Gb, A(ba.attn), GR(bp.projw), nullptr, M, Cc, Cc, dt, be, stream));
-      RUN(mtus_linear_dgrad(Gb, W(bp.projw), dLN, nullptr, nullptr, 1, nullptr, M, Cc, Cc, dt, be, stream));
+      // ---- attention branch (Gb2 = dp1 * G) ----
+      RUN(mtus_linear_dgrad(Gb2, W(bp.projw), dLN, nullptr, nullptr, 1, nullptr, M, Cc, Cc, dt, be, stream));
       RUN(mtus_window_attn_bwd(dLN, A(ba.qkv), A(ba.attn), FA(ba.lse), F(bp.table), F(bp.qkvb), dQKV, GR(bp.table), GR(bp.qkvb), GR(bp.qkvb),
                                p.B, res, res, Cc, p.heads[i], p.win[i], p.win[i], shift, shift, dt, stream));
-      RUN(mtus_linear_wgrad(dQKV, A(ba.ln1), GR(bp.qkvw), nullptr, M, 3 * Cc, Cc, dt, be, stream));
+      if (ss) { CU(cudaEventRecord(ss->e2, st)); CU(cudaStreamWaitEvent(ss->s, ss->e2, 0)); }
+      RUN(mtus_linear_wgrad(Gb2, A(ba.attn), GR(bp.projw), nullptr, M, Cc, Cc, dt, be, wst));
+      RUN(mtus_linear_wgrad(dQKV, A(ba.ln1), GR(bp.qkvw), nullptr, M, 3 * Cc, Cc, dt, be, wst));
+      if (ss) { CU(cudaEventRecord(ss->d2, ss->s)); d2_pending = true; }
       RUN(mtus_linear_dgrad(dQKV, W(bp.qkvw), dLN, nullptr, nullptr, 1, nullptr, M, 3 * Cc, Cc, dt, be, stream));
       // LN1 backward closes the block: the new Gb feeds the previous block's fc2 (its drop-path scale, its bias
       // gradient), or -- unscaled -- the PatchMerging reduction of this stage; stage 0 / block 0 needs no copy
       const float* dp2_prev = (j > 0 && droppath) ? droppath + (size_t)(2 * (gblk - 1) + 1) * p.B : nullptr;
       float* cs_prev = (j > 0) ? GR(p.sp[i].blk[j - 1].fc2b) : nullptr;
       void* lp = (j > 0 || i > 0) ? Gb : nullptr;
+      if (ss) CU(cudaStreamWaitEvent(st, ss->d1, 0));   // wgrad fc2 / fc1 of this block have read Gb / dH
       RUN(mtus_layernorm_bwd_mixed(dLN, 0, A(xin), 1, F(bp.n1w), FA(ba.mean1), FA(ba.rstd1), G, G, lp, dp2_prev, rps, cs_prev,
                                    GR(bp.n1w), GR(bp.n1b), M, Cc, dt, stream));
     }
+    // join: the stage's weight gradients are complete on the caller's stream (its all-reduce may start right after)
+    if (ss && d2_pending) { CU(cudaStreamWaitEvent(st, ss->d2, 0)); d2_pending = false; }
     gblk_end -= p.depths[i];
     if (i > 0) {
       // ---- patch merging backward: reduction wgrad/dgrad, then LN backward scattered to [B,H,W,C_{i-1}] ----

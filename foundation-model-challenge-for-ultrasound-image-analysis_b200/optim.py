@@ -25,6 +25,7 @@ class FlatAdamW:
         enc_params, head_params = model.get_trainable_parameters()
         enc_ids = {id(p) for p in enc_params}
         self.flat: List[Dict] = []
+        self._all_params = None
         flat_ids = set()
         for mod in model.modules():
             if isinstance(mod, FlatParamModule):
@@ -48,7 +49,9 @@ class FlatAdamW:
 
     # -- torch.optim.Optimizer-like surface used by the trainer ---------------------------------------------------
     def zero_grad(self, set_to_none: bool = True):
-        for p in self.model.parameters():
+        if self._all_params is None:
+            self._all_params = list(self.model.parameters())
+        for p in self._all_params:
             p.grad = None
         for f in self.flat:
             f["module"]._last_flat_grad = None
