@@ -322,7 +322,9 @@ __global__ void __launch_bounds__(AM_WARPS * 32, AM_FWD_OCC) window_attn_mma_fwd
   const uint32_t ring_s = smem_u32_generic(ring), stage_s = smem_u32_generic(stage);
   for (int t = tid; t < g.ntab; t += AM_WARPS * 32) s_tbl[t] = __ldg(table + t * g.heads + h) * AM_LOG2E;
   am_init_tables(g, tid, s_pos, s_lin, s_rg);
+  pdl_trigger();
   __syncthreads();
+  pdl_wait();                                           // table / index set-up overlapped the previous kernel's tail
   int w = grp;
   if (w < g.windows) am_issue_window<false>(g, am_window(g, w), h, ring_s, qkv, nullptr, nullptr, nullptr, s_pos, s_src2, nullptr, tid);
   am_build_bias_frags<false>(s_frag, s_tbl, s_lin, g, tid);
@@ -415,7 +417,9 @@ __global__ void __launch_bounds__(AM_WARPS * 32, AM_BWD_OCC) window_attn_mma_bwd
   const uint32_t sds_s = sds_all_s + warp * 2048;                          // this warp's dS^T strip [16 keys][64 queries]
   for (int t = tid; t < g.ntab; t += AM_WARPS * 32) s_tbl[t] = __ldg(table + t * g.heads + h) * AM_LOG2E;
   am_init_tables(g, tid, s_pos, s_lin, s_rg);
+  pdl_trigger();
   __syncthreads();
+  pdl_wait();                                           // table / index set-up overlapped the previous kernel's tail
   int w = grp;
   if (w < g.windows) am_issue_window<true>(g, am_window(g, w), h, ring_s, qkv, dout, outp, lse, s_pos, s_src2, s_lse2, tid);
   am_build_bias_frags<true>(s_frag, s_tbl, s_lin, g, tid);
@@ -643,8 +647,10 @@ int mtus_window_attn_mma_fwd(const void* qkv, const float* rel_table, const floa
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  if (g.N <= 56) window_attn_mma_fwd_kernel<7><<<blocks, AM_WARPS * 32, smem, st>>>((const bf16*)qkv, rel_table, qkv_bias, (bf16*)out, lse, g);
-  else window_attn_mma_fwd_kernel<8><<<blocks, AM_WARPS * 32, smem, st>>>((const bf16*)qkv, rel_table, qkv_bias, (bf16*)out, lse, g);
+  cudaError_t le;
+  if (g.N <= 56) le = mtus_launch_pdl(window_attn_mma_fwd_kernel<7>, dim3(blocks), dim3(AM_WARPS * 32), smem, st, (const bf16*)qkv, rel_table, qkv_bias, (bf16*)out, lse, g);
+  else le = mtus_launch_pdl(window_attn_mma_fwd_kernel<8>, dim3(blocks), dim3(AM_WARPS * 32), smem, st, (const bf16*)qkv, rel_table, qkv_bias, (bf16*)out, lse, g);
+  if (le != cudaSuccess) return (int)le;
   MTUS_LAUNCH_STATUS();
   return MTUS_OK;
 }
@@ -667,12 +673,14 @@ int mtus_window_attn_mma_bwd(const void* dout, const void* qkv, const void* out,
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
+  cudaError_t le;
   if (g.N <= 56)
-    window_attn_mma_bwd_kernel<7><<<blocks, AM_WARPS * 32, smem, st>>>((const bf16*)dout, (const bf16*)qkv, (const bf16*)out, lse, rel_table, qkv_bias,
-                                                                       (bf16*)dqkv, drel_table, dqkv_bias, dqkv_colsum, g);
+    le = mtus_launch_pdl(window_attn_mma_bwd_kernel<7>, dim3(blocks), dim3(AM_WARPS * 32), smem, st, (const bf16*)dout, (const bf16*)qkv, (const bf16*)out, lse,
+                         rel_table, qkv_bias, (bf16*)dqkv, drel_table, dqkv_bias, dqkv_colsum, g);
   else
-    window_attn_mma_bwd_kernel<8><<<blocks, AM_WARPS * 32, smem, st>>>((const bf16*)dout, (const bf16*)qkv, (const bf16*)out, lse, rel_table, qkv_bias,
-                                                                       (bf16*)dqkv, drel_table, dqkv_bias, dqkv_colsum, g);
+    le = mtus_launch_pdl(window_attn_mma_bwd_kernel<8>, dim3(blocks), dim3(AM_WARPS * 32), smem, st, (const bf16*)dout, (const bf16*)qkv, (const bf16*)out, lse,
+                         rel_table, qkv_bias, (bf16*)dqkv, drel_table, dqkv_bias, dqkv_colsum, g);
+  if (le != cudaSuccess) return (int)le;
   MTUS_LAUNCH_STATUS();
   return MTUS_OK;
 }

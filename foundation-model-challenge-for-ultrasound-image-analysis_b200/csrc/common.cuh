@@ -17,6 +17,28 @@ extern "C" void mtus_internal_count_launches(int n);
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------
+// The kernels of the encoder chain (LayerNorm, GEMM, attention) are launched with programmatic stream serialization:
+// kernel N+1 may be scheduled while kernel N is still running, executes its prologue (barrier / TMEM set-up, table
+// loads of PARAMETERS, index tables) and then blocks in pdl_wait() until kernel N has completed and flushed.  Every
+// such kernel calls pdl_trigger() first thing (so its successor can be scheduled as soon as resources free up) and
+// pdl_wait() before its first access to memory an earlier kernel of the step may write.  Kernels that write
+// parameters (optimizer, casts) never trigger early and are launched without the attribute.  MTUS_PDL=0 disables it.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool mtus_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t mtus_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = mtus_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // ---- 8-wide vector load/store, fp32 compute -------------------------------------------------
 template <typename T> struct IO;
 

@@ -105,6 +105,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (CS > 1) cluster_sync_all();          // barrier inits visible cluster-wide before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();                              // everything above overlapped the tail of the previous kernel
 
   // work units enumerate (split z, m-group, n-tile), n fastest; the CTA of rank r takes m-block mg*CS + r (a block
   // beyond m_tiles is a dummy: its loads are zero-filled and its stores clipped, it only keeps the cluster in step)
@@ -420,10 +422,12 @@ static int t2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n_cl * CS); cfg.blockDim = dim3(T2_THREADS);
   cfg.dynamicSmemBytes = T2Smem<BN, OUT_F32>::TOTAL; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = (CS == 1 && mtus_pdl_enabled()) ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tx, td, M, N, K, kbps, total_kb, m_tiles, n_tiles, n_units, cv, ep);
   if (e != cudaSuccess) return (int)e;
   MTUS_LAUNCH_STATUS();

@@ -519,6 +519,8 @@ __global__ void __launch_bounds__(128) lnv2_fwd_kernel(const TX* __restrict__ x,
     for (int k = 0; k < 8; ++k) { gm[i][k] = 0.f; bt[i][k] = 0.f; }
     if (col < C) { IO<float>::load8(gamma + col, gm[i]); IO<float>::load8(beta + col, bt[i]); }
   }
+  pdl_trigger();
+  pdl_wait();                               // gamma / beta (parameters) were fetched while the previous kernel drained
   for (int64_t row0 = gwarp * (RPW * U); row0 < rows; row0 += nwarps * (RPW * U)) {
     float v[U][NV][8];
 #pragma unroll
@@ -592,6 +594,8 @@ __global__ void __launch_bounds__(128) lnv2_bwd_kernel(LnxBwdArgs a, MergeGeom g
     for (int k = 0; k < 8; ++k) { gm[i][k] = 0.f; adg[i][k] = 0.f; adb[i][k] = 0.f; acs[i][k] = 0.f; }
     if (col < C) IO<float>::load8(a.gamma + col, gm[i]);
   }
+  pdl_trigger();
+  pdl_wait();
   for (int64_t row0 = gwarp * RPW; row0 < rows; row0 += nwarps * RPW) {
     const int64_t row = row0 + grp;
     const bool active = row < rows;
@@ -691,7 +695,8 @@ static int lnv2_fwd_launch(const void* x, const float* gamma, const float* beta,
     const int rpi = (32 / LPR_) * U_ * 4;                                                                                \
     int64_t blocks = (rows + rpi - 1) / rpi;                                                                             \
     if (blocks > 148 * 8) blocks = 148 * 8;                                                                              \
-    lnv2_fwd_kernel<TX, TY, LPR_, NV_, U_, MODE><<<(int)blocks, 128, 0, st>>>((const TX*)x, gamma, beta, (TY*)y, mean, rstd, rows, C, eps, g); \
+    cudaError_t le = mtus_launch_pdl(lnv2_fwd_kernel<TX, TY, LPR_, NV_, U_, MODE>, dim3((int)blocks), dim3(128), 0, st, (const TX*)x, gamma, beta, (TY*)y, mean, rstd, rows, C, eps, g); \
+    if (le != cudaSuccess) return (int)le;                                                                               \
   }
   if (nvec <= 4) V2F(4, 1, 4)
   else if (nvec <= 8) V2F(8, 1, 4)
@@ -719,7 +724,8 @@ static int lnv2_bwd_launch(const LnxBwdArgs& a, MergeGeom g, cudaStream_t st) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);      \
       if (e != cudaSuccess) return (int)e;                                                                   \
     }                                                                                                        \
-    kern<<<(int)blocks, 128, sm, st>>>(a, g);                                                                \
+    cudaError_t le = mtus_launch_pdl(kern, dim3((int)blocks), dim3(128), sm, st, a, g);                      \
+    if (le != cudaSuccess) return (int)le;                                                                   \
   }
   if (nvec <= 4) V2B(4, 1)
   else if (nvec <= 8) V2B(8, 1)

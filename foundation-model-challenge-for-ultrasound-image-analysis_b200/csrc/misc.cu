@@ -3,6 +3,7 @@
 // and the PatchEmbed im2col (timm PatchEmbed.proj as a K=48 GEMM).  All are coalesced, 16-byte
 // vectorised, grid-stride kernels; HBM roofline, algorithmic bytes = one read + one write of the tensor.
 #include "common.cuh"
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -10,6 +11,12 @@ extern "C" int mtus_version(void) { return 101; }
 
 static std::atomic<int64_t> g_launches{0};
 extern "C" void mtus_internal_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool mtus_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTUS_PDL"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  return v == 1;
+}
 extern "C" int64_t mtus_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" const char* mtus_status_string(int s) {
