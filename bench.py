@@ -316,11 +316,10 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # one untimed step per task TYPE first (cuDNN autotune of the PyTorch heads, allocator growth, lazy inits);
-    # the W warm-up steps of the contract follow inside timed()
-    for k in sorted(set(key.values())):
-        tid0 = next(t for t in task_ids if key[t] == k)
-        trainer.step(devb[k][0], devb[k][1], tid0)
+    # one untimed step per task id first (cuDNN autotune of the PyTorch heads, optimizer state of every head,
+    # allocator growth, NCCL buffers for every gradient size); the W warm-up steps of the contract follow inside timed()
+    for tid0 in task_ids:
+        trainer.step(devb[key[tid0]][0], devb[key[tid0]][1], tid0)
 
     def timed(step_fn):
         """W warm-up steps, then K timed steps bracketed by barrier + synchronize; device time, max over ranks."""

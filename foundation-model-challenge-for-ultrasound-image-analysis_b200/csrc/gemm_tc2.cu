@@ -399,6 +399,8 @@ static int sm_count() {
     int dev = 0, n = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     g_sm_count = n > 0 ? n : 148;
+    const char* e = getenv("MTUS_GEMM_SMS");       // cap of the persistent grid (leaves SMs to a concurrent NCCL kernel)
+    if (e && atoi(e) > 0 && atoi(e) < g_sm_count) g_sm_count = atoi(e);
   }
   return g_sm_count;
 }

@@ -324,11 +324,23 @@ extern "C" int mtus_swin_forward(const mtus_swin_config* cfg, const void* x, int
 extern "C" int mtus_swin_backward(const mtus_swin_config* cfg, const float* params, const void* params_lp,
                                   const float* droppath, void* workspace, const void* const* dfeats, int dfeats_layout,
                                   int dfeats_f32, float* grads, int stage_hi, int stage_lo, void* stream) {
+  MTUS_CHECK_ARG(cfg && stage_hi <= 4 && stage_lo >= 0 && stage_lo < stage_hi);
+  int hi = 0, lo = 0;
+  for (int i = 0; i < stage_hi; ++i) hi += cfg->depths[i];
+  for (int i = 0; i < stage_lo; ++i) lo += cfg->depths[i];
+  return mtus_swin_backward_blocks(cfg, params, params_lp, droppath, workspace, dfeats, dfeats_layout, dfeats_f32, grads, hi, lo, stream);
+}
+
+extern "C" int mtus_swin_backward_blocks(const mtus_swin_config* cfg, const float* params, const void* params_lp,
+                                         const float* droppath, void* workspace, const void* const* dfeats,
+                                         int dfeats_layout, int dfeats_f32, float* grads, int block_hi, int block_lo,
+                                         void* stream) {
   Plan p;
   if (!build_plan(cfg, p)) return MTUS_ERR_BAD_ARG;
   MTUS_CHECK_ARG(params && workspace && dfeats && grads && p.training);
   MTUS_CHECK_ARG(p.dtype == MTUS_F32 || params_lp);
-  MTUS_CHECK_ARG(stage_hi <= 4 && stage_lo >= 0 && stage_lo < stage_hi);
+  const int n_blocks = p.depths[0] + p.depths[1] + p.depths[2] + p.depths[3];
+  MTUS_CHECK_ARG(block_hi <= n_blocks && block_lo >= 0 && block_lo < block_hi);
   if (p.B == 0) return MTUS_OK;
   char* ws = reinterpret_cast<char*>(workspace);
   const int dt = p.dtype, be = p.backend;
@@ -357,22 +369,26 @@ extern "C" int mtus_swin_backward(const mtus_swin_config* cfg, const float* para
     return mtus_convert(dfeats[i], dst, p.B, p.res[i] * p.res[i], p.C[i], 0, dt == MTUS_F32, 1, dt, stream);
   };
 
-  int gblk_end = 0;
-  for (int i = 0; i < stage_hi; ++i) gblk_end += p.depths[i];
-
-  for (int i = stage_hi - 1; i >= stage_lo; --i) {
+  // global block index g counts blocks in forward order; this call runs blocks block_hi-1 down to block_lo and, after
+  // block 0 of a stage, that stage's PatchMerging (or patch-embed) backward
+  int gblk_end = n_blocks;
+  for (int i = 3; i >= 0; --i) {
+    const int stage_first = gblk_end - p.depths[i];           // global index of this stage's block 0
+    const int j_hi = (block_hi < gblk_end ? block_hi : gblk_end) - stage_first;   // local blocks [j_lo, j_hi)
+    const int j_lo = (block_lo > stage_first ? block_lo : stage_first) - stage_first;
+    if (j_hi <= j_lo) { gblk_end = stage_first; continue; }
     const int Cc = p.C[i], res = p.res[i];
     const int64_t M = p.M[i];
     const int rps = res * res;
-    int gblk = gblk_end - 1;
-    if (i == 3) {  // top of the chain: G = NHWC(dfeat3) or zero, Gb = dp2 * G for the last block's fc2
+    int gblk = stage_first + j_hi - 1;
+    if (i == 3 && j_hi == p.depths[3]) {  // top of the chain: G = NHWC(dfeat3) or zero, Gb = dp2 * G for the last block's fc2
       if (dfeats[3]) RUN(load_dfeat(3, G));
       else { cudaError_t e = cudaMemsetAsync(G, 0, (size_t)M * Cc * 4, st); if (e != cudaSuccess) return (int)e; }
       const BlockP& bl = p.sp[3].blk.back();
       const float* dp2 = droppath ? droppath + (size_t)(2 * gblk + 1) * p.B : nullptr;
       RUN(mtus_scale_cast_colsum(G, dp2, rps, Gb, GR(bl.fc2b), M, Cc, dt, stream));
     }
-    for (int j = p.depths[i] - 1; j >= 0; --j, --gblk) {
+    for (int j = j_hi - 1; j >= j_lo; --j, --gblk) {
       const BlockP& bp = p.sp[i].blk[j];
       const BlockA& ba = p.sa[i].blk[j];
       const size_t xin = block_xin(p, i, j);
@@ -408,7 +424,8 @@ extern "C" int mtus_swin_backward(const mtus_swin_config* cfg, const float* para
     }
     // join: the stage's weight gradients are complete on the caller's stream (its all-reduce may start right after)
     if (ss && d2_pending) { CU(cudaStreamWaitEvent(st, ss->d2, 0)); d2_pending = false; }
-    gblk_end -= p.depths[i];
+    gblk_end = stage_first;
+    if (j_lo > 0) continue;                                   // the stage's first block is not part of this call
     if (i > 0) {
       // ---- patch merging backward: reduction wgrad/dgrad, then LN backward scattered to [B,H,W,C_{i-1}] ----
       const StageA& s = p.sa[i];

@@ -214,18 +214,48 @@ class SwinCore(FlatParamModule):
         nhwc = bool(layouts) and all(layouts) and not out_f32
         gs = [None if g is None else (g if (nhwc or g.is_contiguous()) else g.contiguous()) for g in gs]
         hook = _STAGE_GRAD_HOOK
-        chunks = [(4, 3), (3, 2), (2, 1), (1, 0)] if hook is not None else [(4, 0)]
-        for hi, lo in chunks:
-            _lib.check(L.mtus_swin_backward(C.byref(cfg), _lib.ptr(flat), _lib.ptr(lp), _lib.ptr(dp), _lib.ptr(ws),
-                                            _lib.ptr_array(gs), int(nhwc), int(want == torch.float32 and dt != _lib.F32),
-                                            _lib.ptr(flat_grad), hi, lo, _lib.stream_ptr()), "swin_backward")
+        nblk = sum(self.depths)
+        chunks = self._backward_chunks() if hook is not None else [(nblk, 0, 0, self._n_flat)]
+        for b_hi, b_lo, s_lo, s_hi in chunks:
+            _lib.check(L.mtus_swin_backward_blocks(C.byref(cfg), _lib.ptr(flat), _lib.ptr(lp), _lib.ptr(dp), _lib.ptr(ws),
+                                                   _lib.ptr_array(gs), int(nhwc), int(want == torch.float32 and dt != _lib.F32),
+                                                   _lib.ptr(flat_grad), b_hi, b_lo, _lib.stream_ptr()), "swin_backward")
             if hook is not None:
-                s_lo, s_hi = self._stage_slices[lo + 1]
-                if lo == 0:
-                    s_lo = self._stage_slices[0][0]        # patch_embed gradients finish with stage 0
                 hook(flat_grad, s_lo, s_hi)
         self._last_flat_grad = flat_grad
         return flat_grad
+
+    def _backward_chunks(self, blocks_per_chunk: int = 0):
+        """[(block_hi, block_lo, grad_lo, grad_hi)] in backward order: runs of ``blocks_per_chunk`` blocks that never
+        cross a stage, each with the slice of the flat gradient it completes (the chunk holding a stage's block 0 also
+        completes that stage's PatchMerging -- or, for stage 0, the patch-embed -- gradients, which precede the
+        blocks in the parameter layout).  Used by the data-parallel wrapper to start all-reducing early."""
+        k = blocks_per_chunk or int(os.environ.get("MTUS_DP_BLOCKS_PER_CHUNK", "6"))
+        cached = getattr(self, "_chunk_cache", None)
+        if cached is not None and cached[0] == k:
+            return cached[1]
+        first_off = {}
+        for name, (p, off, numel, shape) in self._params_by_name.items():
+            parts = name.split(".")
+            if parts[0].startswith("layers_") and parts[1] == "blocks":
+                key = (int(parts[0][7:]), int(parts[2]))
+                first_off[key] = min(first_off.get(key, off), off)
+        chunks, g_end = [], sum(self.depths)
+        for i in (3, 2, 1, 0):
+            d, first = self.depths[i], g_end - self.depths[i]
+            stage_lo, stage_hi = self._stage_slices[i + 1]
+            if i == 0:
+                stage_lo = self._stage_slices[0][0]           # patch_embed gradients finish with stage 0
+            j_hi = d
+            while j_hi > 0:
+                j_lo = max(0, j_hi - k)
+                lo = stage_lo if j_lo == 0 else first_off[(i, j_lo)]
+                hi = stage_hi if j_hi == d else first_off[(i, j_hi)]
+                chunks.append((first + j_hi, first + j_lo, lo, hi))
+                j_hi = j_lo
+            g_end = first
+        self._chunk_cache = (k, chunks)
+        return chunks
 
     def forward(self, x: torch.Tensor) -> List[torch.Tensor]:
         """Returns the four stage outputs as [B,C,H,W] tensors (strides 4/8/16/32)."""

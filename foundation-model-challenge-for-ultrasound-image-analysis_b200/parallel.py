@@ -70,6 +70,7 @@ class DistributedTaskSampler(torch.utils.data.Sampler):
 
 class GradAllReducer:
     """Mean all-reduce of the gradients of ``model`` over ``group`` (NCCL on GPUs, gloo in CPU tests)."""
+    _avg = None                                 # True: ReduceOp.AVG (NCCL); False: SUM then scale (gloo)
 
     def __init__(self, model: torch.nn.Module, group=None, overlap_encoder: bool = True):
         self.model, self.group = model, group
@@ -82,16 +83,29 @@ class GradAllReducer:
         if core is not None and hasattr(core, "ordered_params"):
             self._enc_params = {id(p) for p in core.ordered_params()}
         self._enc_reduced = False
+        self._avg = None
+        from ._native import FlatParamModule
+        self._flat_modules = [m for m in model.modules() if isinstance(m, FlatParamModule)]
+        self._all_params = list(model.parameters())
 
-    # called from SwinCore._run_backward after each stage chunk
+    def _avg_op(self):
+        # NCCL averages in the collective; gloo (CPU tests) has no AVG: sum, then scale
+        if self._avg is None:
+            backend = dist.get_backend(self.group) if dist.is_initialized() else "gloo"
+            self._avg = backend == "nccl"
+        return dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+
+    # called from SwinCore._run_backward after each chunk of blocks: flat_grad[lo:hi] is final
     def _stage_hook(self, flat_grad: torch.Tensor, lo: int, hi: int):
         if self.world > 1:
-            self._handles.append(dist.all_reduce(flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            op = self._avg_op()
+            self._handles.append(dist.all_reduce(flat_grad[lo:hi], op=op, group=self.group, async_op=True))
             if lo == self._first_lo:            # last chunk: the gradient views are handed to autograd next
                 for h in self._handles:
                     h.wait()                    # stream-ordered wait, not a host sync (NCCL)
                 self._handles = []
-                flat_grad.mul_(1.0 / self.world)
+                if not self._avg:
+                    flat_grad.mul_(1.0 / self.world)
         self._enc_reduced = True
 
     def __enter__(self):
@@ -107,21 +121,42 @@ class GradAllReducer:
         return False
 
     def finish(self):
-        """All-reduce what backward did not already reduce (FPN, heads; the encoder too when not overlapped)."""
+        """All-reduce what backward did not already reduce (FPN, heads; the encoder too when not overlapped).
+
+        Flat modules (FPN decoders, the encoder) are reduced in place through their one contiguous gradient block;
+        the remaining (head) gradients are coalesced into one call."""
         if self.world == 1:
             return
-        grads = [p.grad for p in self.model.parameters()
-                 if p.grad is not None and not (self._enc_reduced and id(p) in self._enc_params)]
-        if not grads:
-            return
-        flat = torch.cat([g.reshape(-1) for g in grads])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-        flat.mul_(1.0 / self.world)
-        off = 0
-        for g in grads:
-            n = g.numel()
-            g.copy_(flat[off:off + n].view_as(g))
-            off += n
+        op = self._avg_op()
+        done = set(self._enc_params) if self._enc_reduced else set()
+        handles, scale_later = [], []
+        for mod in self._flat_modules:
+            g = getattr(mod, "_last_flat_grad", None)
+            ps = mod.ordered_params()
+            if g is None or not ps or id(ps[0]) in done:
+                continue
+            first = ps[0].grad
+            if first is None:
+                continue
+            if not (g.data_ptr() <= first.data_ptr() < g.data_ptr() + g.numel() * g.element_size()):
+                continue                        # autograd copied the views: fall through to the generic path
+            handles.append(dist.all_reduce(g, op=op, group=self.group, async_op=True))
+            scale_later.append(g)
+            done |= {id(p) for p in ps}
+        grads = [p.grad for p in self._all_params if p.grad is not None and id(p) not in done]
+        flat = None
+        if grads:
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            handles.append(dist.all_reduce(flat, op=op, group=self.group, async_op=True))
+        for h in handles:
+            h.wait()
+        if not self._avg:
+            for g in scale_later:
+                g.mul_(1.0 / self.world)
+            if flat is not None:
+                flat.mul_(1.0 / self.world)
+        if flat is not None:
+            torch._foreach_copy_(grads, [v.view_as(g) for v, g in zip(flat.split_with_sizes([g.numel() for g in grads]), grads)])
 
 
 class DataParallelTrainer:

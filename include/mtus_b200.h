@@ -234,6 +234,13 @@ int mtus_swin_forward(const mtus_swin_config* cfg, const void* x, int x_is_f32, 
 int mtus_swin_backward(const mtus_swin_config* cfg, const float* params, const void* params_lp,
                        const float* droppath, void* workspace, const void* const* dfeats, int dfeats_layout,
                        int dfeats_f32, float* grads, int stage_hi, int stage_lo, void* stream);
+/* Same, at block granularity: global block indices count the blocks of all stages in forward order
+ * (Swin-B: 0..23); runs blocks block_hi-1 down to block_lo, plus the PatchMerging / patch-embed backward of every
+ * stage whose first block is in the range.  Lets the data-parallel wrapper all-reduce finished slices of the flat
+ * gradient while the long stage 3 (18 blocks, 2/3 of the parameters) is still running backward. */
+int mtus_swin_backward_blocks(const mtus_swin_config* cfg, const float* params, const void* params_lp,
+                              const float* droppath, void* workspace, const void* const* dfeats, int dfeats_layout,
+                              int dfeats_f32, float* grads, int block_hi, int block_lo, void* stream);
 
 typedef struct mtus_fpn_config {
   int batch;

@@ -145,3 +145,33 @@ def test_synthetic_batches_have_the_documented_shapes():
             assert y.shape == (3, 4) and (y[:, 2] > y[:, 0]).all() and (y[:, 3] > y[:, 1]).all()
         else:
             assert y.shape == (3, 2 * t["num_classes"])
+
+
+def test_backward_chunk_plan_tiles_the_flat_gradient():
+    """Data-parallel chunk plan (SwinCore._backward_chunks): block ranges descend from the top, never cross a stage,
+    and their gradient slices tile the flat gradient block exactly once (so every chunk can be all-reduced as soon as
+    its backward range has run)."""
+    enc = m.SwinTransformerEncoder("swin_b", pretrained=False, img_size=224, precision="fp32")
+    core = enc.model
+    for k in (1, 3, 5, 100):
+        chunks = core._backward_chunks(k)
+        nblk = sum(core.depths)
+        assert chunks[0][0] == nblk and chunks[-1][1] == 0
+        for (hi, lo, _, _), (hi2, _, _, _) in zip(chunks, chunks[1:]):
+            assert lo == hi2 and hi > lo
+        bounds, acc = [], 0
+        for d in core.depths:
+            bounds.append((acc, acc + d))
+            acc += d
+        for hi, lo, _, _ in chunks:
+            assert any(b0 <= lo and hi <= b1 for b0, b1 in bounds), "a chunk crosses a stage"
+            assert hi - lo <= k
+        spans = sorted((g_lo, g_hi) for _, _, g_lo, g_hi in chunks)
+        assert spans[0][0] == core._stage_slices[0][0]
+        for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+            assert a1 == b0, "gradient slices must be contiguous and disjoint"
+        assert spans[-1][1] == core._stage_slices[4][1]
+        # every parameter lies inside exactly one slice, together with the rest of its block
+        for name, (p, off, numel, shape) in core._params_by_name.items():
+            inside = [s for s in spans if s[0] <= off and off + numel <= s[1]]
+            assert len(inside) == 1, name
