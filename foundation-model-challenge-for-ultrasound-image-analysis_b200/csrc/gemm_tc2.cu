@@ -50,7 +50,8 @@ struct T2Smem {
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int SUB_BYTES = 128 * 128;                       // epilogue sub-tile: 128 rows x 128 bytes
   static constexpr int EPI_BUFS = 2;   // (measured: a deeper ring with a single-buffered epilogue is not faster)
-  static constexpr int STAGES = (BN == 256) ? 3 : ((BN == 128) ? 4 : 6);
+  static constexpr int STAGES = (BN == 256) ? 3 : ((BN >= 128) ? 4 : 6);
+  static constexpr int TMEM_COLS = (2 * BN > 256) ? 512 : ((2 * BN > 128) ? 256 : 128);   // two accumulators, power of two
   static constexpr int EPI_OFF = STAGES * STAGE;
   static constexpr int BAR_OFF = EPI_OFF + 2 * EPI_BUFS * SUB_BYTES;   // X[EPI_BUFS], D[EPI_BUFS]
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
@@ -99,7 +100,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), S::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   if (CS > 1) cluster_sync_all();          // barrier inits visible cluster-wide before any remote arrive / multicast
@@ -371,7 +372,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (CS > 1) cluster_sync_all();          // no CTA leaves while a peer may still multicast into it or arrive on its barriers
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, S::TMEM_COLS); }
 #undef T2_DECODE
 }
 
@@ -436,20 +437,27 @@ static int t2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   return MTUS_OK;
 }
 
-// 128x256 tiles halve the L2 -> SM operand traffic per flop (the main-loop limiter) but quantise worse on small
-// problems: pick them when the estimated time (waves x per-tile cost, L2-bound model) is lower.
-static bool t2_prefer_bn256(int M, int N, int K) {
+// Tile width: wider tiles move fewer operand bytes from L2 per flop (the main-loop limiter of these GEMMs: about
+// 42 B/clk/SM when every SM pulls), narrower ones quantise better on the 148 SMs.  Model: waves x (k-blocks x L2 time of
+// one k-block + a fixed per-tile cost), all in cycles.  128x192 is what makes N = 512 at M = 6272 (49 x 3 = 147 tiles) a
+// single full wave.
+static int t2_pick_bn(int M, int N, int K, bool allow_192_256) {
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("MTUS_BN"); forced = e ? atoi(e) : 0; }
-  if (forced == 128) return false;
-  if (forced == 256) return true;
+  if (N <= 64) return 64;
+  if (!allow_192_256 || N <= 128) return 128;
+  if (forced == 128 || forced == 192 || forced == 256) return forced;
   const int sms = sm_count();
-  const int64_t mt = ceil_div(M, T2_BM);
-  const int64_t t128 = mt * ceil_div(N, 128), t256 = mt * ceil_div(N, 256);
-  const double w128 = (double)((t128 + sms - 1) / sms), w256 = (double)((t256 + sms - 1) / sms);
-  // per-tile cost ~ max(MMA, operand bytes / L2 share) + epilogue drain; in units of "128x128 k-blocks"
-  const double c128 = 1.0 * K + 300.0, c256 = 1.55 * K + 600.0;
-  return w256 * c256 < w128 * c128;
+  const int64_t mt = ceil_div(M, T2_BM), kb = ceil_div(K, T2_BK);
+  int best = 128;
+  double best_t = 0;
+  for (int bn = 128; bn <= 256; bn += 64) {
+    const int64_t tiles = mt * ceil_div(N, bn);
+    const double waves = (double)((tiles + sms - 1) / sms);
+    const double t = waves * ((double)kb * (16384.0 + 128.0 * bn) / 42.5 + 600.0 + 3.0 * bn);
+    if (bn == 128 || t < best_t) { best = bn; best_t = t; }
+  }
+  return best;
 }
 
 bool mtus_gemm_tc2_supported(const mtus_gemm_desc* d) {
@@ -495,8 +503,9 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
   CUtensorMap ta, tb, tx, td;
   T2Conv cv{};
   int rc;
-  int BN = (N > 64) ? 128 : 64;
-  if (!d->out_f32 && !d->a_conv && !d->b_conv && N >= 256 && t2_prefer_bn256(M, N, K)) BN = 256;
+  // wide tiles: plain Linear shapes only (K-major A); fp32 output (residual stream) with K-major B
+  const bool wide_ok = !d->a_conv && !d->b_conv && !d->a_mn_major && (!d->out_f32 || !d->b_mn_major);
+  const int BN = t2_pick_bn(M, N, K, wide_ok);
   int m_tiles = ceil_div(M, T2_BM), n_tiles = ceil_div(N, BN), total_kb = ceil_div(K, T2_BK);
   if (d->a_conv || d->b_conv) {
     cv.H = d->conv_h; cv.W = d->conv_w; cv.C = d->conv_c;
@@ -564,7 +573,11 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
   }
 #define T2_GO(BN_, AM_, BM_, F32_) T2_GO2(BN_, AM_, BM_, F32_)
   if (d->out_f32) {
-    if (BN == 128) {
+    if (BN == 256) {
+      if (am == 0 && bm == 0) T2_GO(256, 0, 0, true);
+    } else if (BN == 192) {
+      if (am == 0 && bm == 0) T2_GO(192, 0, 0, true);
+    } else if (BN == 128) {
       if (am == 0 && bm == 0) T2_GO(128, 0, 0, true);
       if (am == 1 && bm == 1) T2_GO(128, 1, 1, true);
       if (am == 3 && bm == 2) T2_GO(128, 3, 2, true);
@@ -575,6 +588,9 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
   } else if (BN == 256) {
     if (am == 0 && bm == 0) T2_GO(256, 0, 0, false);
     if (am == 0 && bm == 1) T2_GO(256, 0, 1, false);
+  } else if (BN == 192) {
+    if (am == 0 && bm == 0) T2_GO(192, 0, 0, false);
+    if (am == 0 && bm == 1) T2_GO(192, 0, 1, false);
   } else if (BN == 128) {
     if (am == 0 && bm == 0) T2_GO(128, 0, 0, false);
     if (am == 0 && bm == 1) T2_GO(128, 0, 1, false);

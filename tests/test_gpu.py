@@ -184,11 +184,12 @@ def test_flat_adamw_matches_torch_adamw_with_clipping():
         assert torch.allclose(pa[k], pb[k], rtol=2e-4, atol=2e-6), k
 
 
-def test_chunked_backward_equals_one_shot_backward():
+def test_chunked_backward_equals_one_shot_backward(monkeypatch):
     """mtus_swin_backward_blocks over the data-parallel chunk plan produces the same flat gradient as one call over all
     blocks (fp32 accumulation order differs only through atomics: compared at 1e-5 of the tensor scale)."""
     import mtus_b200 as m
     from mtus_b200 import encoders as enc_mod
+    monkeypatch.setenv("MTUS_DP_BLOCKS_PER_CHUNK", "2")     # swin_t: 1 + 1 + 3 + 1 chunks
     torch.manual_seed(0)
     enc = m.SwinTransformerEncoder("swin_t", pretrained=False, img_size=224, precision="bf16", drop_path_rate=0.1).cuda().train()
     x = torch.randn(4, 3, 224, 224, generator=torch.Generator().manual_seed(3)).cuda()
