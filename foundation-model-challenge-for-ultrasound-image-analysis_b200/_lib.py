@@ -88,6 +88,8 @@ SIGNATURES = {
     "mtus_groupnorm_stats": (i32, [vp, vp, vp, i32, i32, i32, i32, f32, i32, vp]),
     "mtus_groupnorm_relu_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_groupnorm_relu_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "mtus_groupnorm_act_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "mtus_groupnorm_act_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "mtus_bilinear2x_fwd": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_bilinear2x_bwd": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_fpn_merge_fwd": (i32, [_P(vp), i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp]),

@@ -159,7 +159,10 @@ extern "C" int mtus_groupnorm_stats(const void* x, float* mean, float* rstd, int
   return MTUS_OK;
 }
 
-template <typename T>
+// ACT 0: ReLU (smp Conv3x3GNReLU) | ACT 1: SiLU (the reference's segmentation head, code/models/heads.py:16-42)
+__device__ __forceinline__ float gn_sigmoid(float z) { return 1.0f / (1.0f + __expf(-z)); }
+
+template <typename T, int ACT>
 __global__ void gn_relu_fwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ y,
                                    int64_t total, int HW, int C8, int G, int cpg) {
@@ -175,31 +178,47 @@ __global__ void gn_relu_fwd_kernel(const T* __restrict__ x, const float* __restr
     for (int k = 0; k < 8; ++k) {
       const int g = (v * 8 + k) / cpg;
       const float m = __ldg(mean + b * G + g), r = __ldg(rstd + b * G + g);
-      a[k] = fmaxf((a[k] - m) * r * gm[k] + bt[k], 0.f);
+      const float z = (a[k] - m) * r * gm[k] + bt[k];
+      a[k] = ACT == 0 ? fmaxf(z, 0.f) : z * gn_sigmoid(z);
     }
     IO<T>::store8(y + i * 8, a);
   }
 }
 
-extern "C" int mtus_groupnorm_relu_fwd(const void* x, const float* mean, const float* rstd, const float* gamma,
-                                       const float* beta, void* y, int B, int HW, int C, int G, int dtype, void* stream) {
-  MTUS_CHECK_ARG(x && mean && rstd && gamma && beta && y && C % 8 == 0 && G > 0 && C % G == 0);
+extern "C" int mtus_groupnorm_act_fwd(const void* x, const float* mean, const float* rstd, const float* gamma,
+                                      const float* beta, void* y, int B, int HW, int C, int G, int act, int dtype, void* stream) {
+  MTUS_CHECK_ARG(x && mean && rstd && gamma && beta && y && C % 8 == 0 && G > 0 && C % G == 0 && (act == 0 || act == 1));
   const int64_t total = (int64_t)B * HW * (C / 8);
   if (total == 0) return MTUS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == MTUS_F32) gn_relu_fwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, mean, rstd, gamma, beta, (float*)y, total, HW, C / 8, G, C / G);
-  else if (dtype == MTUS_BF16) gn_relu_fwd_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)x, mean, rstd, gamma, beta, (bf16*)y, total, HW, C / 8, G, C / G);
+#define GN_FWD(T_, ACT_) gn_relu_fwd_kernel<T_, ACT_><<<grid_for(total, 256), 256, 0, st>>>((const T_*)x, mean, rstd, gamma, beta, (T_*)y, total, HW, C / 8, G, C / G)
+  if (dtype == MTUS_F32) { if (act == 0) GN_FWD(float, 0); else GN_FWD(float, 1); }
+  else if (dtype == MTUS_BF16) { if (act == 0) GN_FWD(bf16, 0); else GN_FWD(bf16, 1); }
   else return MTUS_ERR_UNSUPPORTED;
+#undef GN_FWD
   MTUS_LAUNCH_STATUS();
   return MTUS_OK;
 }
 
+extern "C" int mtus_groupnorm_relu_fwd(const void* x, const float* mean, const float* rstd, const float* gamma,
+                                       const float* beta, void* y, int B, int HW, int C, int G, int dtype, void* stream) {
+  return mtus_groupnorm_act_fwd(x, mean, rstd, gamma, beta, y, B, HW, C, G, 0, dtype, stream);
+}
+
+// d act(z) / dz times dy.  ReLU: mask from the saved output y; SiLU: z recomputed from x (sigma(z) (1 + z (1 - sigma(z)))).
+template <int ACT>
+__device__ __forceinline__ float gn_act_grad(float dy, float yv, float xh, float gm, float bt) {
+  if (ACT == 0) return yv > 0.f ? dy : 0.f;
+  const float z = xh * gm + bt, sg = gn_sigmoid(z);
+  return dy * sg * (1.0f + z * (1.0f - sg));
+}
+
 // backward pass 1: per (b,g) s1 = sum dyr*gamma, s2 = sum dyr*gamma*xhat (ws[0..BG), ws[BG..2BG));
 //                  per channel dgamma += sum dyr*xhat, dbeta += sum dyr     (dyr = dy * (y > 0))
-template <typename T>
+template <typename T, int ACT>
 __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                            const float* __restrict__ gamma, float* __restrict__ ws,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ ws,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int HW,
                                                             int C, int G, int pix_per_chunk) {
   extern __shared__ float sred[];  // [4][C]: s1, s2 (per channel, folded to groups later), dgamma, dbeta
@@ -207,11 +226,11 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict_
   const int v = threadIdx.x % C8, pl = threadIdx.x / C8, npl = 256 / C8;
   const int b = blockIdx.y;
   const int p0 = blockIdx.x * pix_per_chunk, p1 = min(HW, p0 + pix_per_chunk);
-  float mu[8], rs[8], gm[8];
+  float mu[8], rs[8], gm[8], bt[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int g = (v * 8 + k) / cpg;
-    mu[k] = mean[b * G + g]; rs[k] = rstd[b * G + g]; gm[k] = gamma[v * 8 + k];
+    mu[k] = mean[b * G + g]; rs[k] = rstd[b * G + g]; gm[k] = gamma[v * 8 + k]; bt[k] = ACT == 0 ? 0.f : beta[v * 8 + k];
   }
   float a1[8], a2[8], ag[8], ab[8];
 #pragma unroll
@@ -219,12 +238,13 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict_
   if (pl < npl) {
     for (int p = p0 + pl; p < p1; p += npl) {
       const int64_t off = ((int64_t)b * HW + p) * C + v * 8;
-      float d[8], xv[8], yv[8];
-      IO<T>::load8(dy + off, d); IO<T>::load8(x + off, xv); IO<T>::load8(y + off, yv);
+      float d[8], xv[8], yv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      IO<T>::load8(dy + off, d); IO<T>::load8(x + off, xv);
+      if (ACT == 0) IO<T>::load8(y + off, yv);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float dr = (yv[k] > 0.f) ? d[k] : 0.f;
         const float xh = (xv[k] - mu[k]) * rs[k];
+        const float dr = gn_act_grad<ACT>(d[k], yv[k], xh, gm[k], bt[k]);
         a1[k] += dr * gm[k]; a2[k] += dr * gm[k] * xh; ag[k] += dr * xh; ab[k] += dr;
       }
     }
@@ -248,36 +268,38 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict_
   for (int c = threadIdx.x; c < C; c += 256) { atomicAdd(dgamma + c, sred[2 * C + c]); atomicAdd(dbeta + c, sred[3 * C + c]); }
 }
 
-template <typename T>
+template <typename T, int ACT>
 __global__ void gn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                    const float* __restrict__ ws, T* __restrict__ dx, int64_t total, int B, int HW, int C8, int G,
+                                    const float* __restrict__ beta, const float* __restrict__ ws, T* __restrict__ dx, int64_t total, int B, int HW, int C8, int G,
                                     int cpg) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const float inv_n = 1.0f / ((float)HW * cpg);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int v = (int)(i % C8);
     const int64_t b = i / ((int64_t)C8 * HW);
-    float d[8], xv[8], yv[8], gm[8], o[8];
-    IO<T>::load8(dy + i * 8, d); IO<T>::load8(x + i * 8, xv); IO<T>::load8(y + i * 8, yv);
+    float d[8], xv[8], yv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gm[8], bt[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, o[8];
+    IO<T>::load8(dy + i * 8, d); IO<T>::load8(x + i * 8, xv);
+    if (ACT == 0) IO<T>::load8(y + i * 8, yv); else IO<float>::load8(beta + v * 8, bt);
     IO<float>::load8(gamma + v * 8, gm);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int g = (v * 8 + k) / cpg;
       const float m = __ldg(mean + b * G + g), r = __ldg(rstd + b * G + g);
       const float s1 = __ldg(ws + b * G + g) * inv_n, s2 = __ldg(ws + (int64_t)B * G + b * G + g) * inv_n;
-      const float dr = (yv[k] > 0.f) ? d[k] : 0.f;
       const float xh = (xv[k] - m) * r;
+      const float dr = gn_act_grad<ACT>(d[k], yv[k], xh, gm[k], bt[k]);
       o[k] = r * (dr * gm[k] - s1 - xh * s2);
     }
     IO<T>::store8(dx + i * 8, o);
   }
 }
 
-extern "C" int mtus_groupnorm_relu_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* rstd,
-                                       const float* gamma, void* dx, float* dgamma, float* dbeta, float* ws, int B, int HW,
-                                       int C, int G, int dtype, void* stream) {
-  MTUS_CHECK_ARG(dy && x && y && mean && rstd && gamma && dx && dgamma && dbeta && ws);
+extern "C" int mtus_groupnorm_act_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* rstd,
+                                      const float* gamma, const float* beta, void* dx, float* dgamma, float* dbeta, float* ws,
+                                      int B, int HW, int C, int G, int act, int dtype, void* stream) {
+  MTUS_CHECK_ARG(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && ws && (act == 0 || act == 1));
+  MTUS_CHECK_ARG(act == 0 ? y != nullptr : beta != nullptr);
   MTUS_CHECK_ARG(C % 8 == 0 && C / 8 <= 256 && G > 0 && C % G == 0 && B <= 65535);
   if (B == 0) return MTUS_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -287,15 +309,24 @@ extern "C" int mtus_groupnorm_relu_bwd(const void* dy, const void* x, const void
   dim3 grid(chunks, B);
   const size_t sm = sizeof(float) * 4 * C;
   const int64_t total = (int64_t)B * HW * (C / 8);
-  if (dtype == MTUS_F32) {
-    gn_bwd_reduce_kernel<float><<<grid, 256, sm, st>>>((const float*)dy, (const float*)x, (const float*)y, mean, rstd, gamma, ws, dgamma, dbeta, B, HW, C, G, ppc);
-    gn_bwd_apply_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)dy, (const float*)x, (const float*)y, mean, rstd, gamma, ws, (float*)dx, total, B, HW, C / 8, G, C / G);
-  } else if (dtype == MTUS_BF16) {
-    gn_bwd_reduce_kernel<bf16><<<grid, 256, sm, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, rstd, gamma, ws, dgamma, dbeta, B, HW, C, G, ppc);
-    gn_bwd_apply_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, rstd, gamma, ws, (bf16*)dx, total, B, HW, C / 8, G, C / G);
-  } else return MTUS_ERR_UNSUPPORTED;
+#define GN_BWD(T_, ACT_)                                                                                                                  \
+  {                                                                                                                                       \
+    gn_bwd_reduce_kernel<T_, ACT_><<<grid, 256, sm, st>>>((const T_*)dy, (const T_*)x, (const T_*)y, mean, rstd, gamma, beta, ws, dgamma, dbeta, B, HW, C, G, ppc); \
+    gn_bwd_apply_kernel<T_, ACT_><<<grid_for(total, 256), 256, 0, st>>>((const T_*)dy, (const T_*)x, (const T_*)y, mean, rstd, gamma, beta, ws, (T_*)dx, total, B, HW, C / 8, G, C / G); \
+  }
+  if (dtype == MTUS_F32) { if (act == 0) GN_BWD(float, 0) else GN_BWD(float, 1) }
+  else if (dtype == MTUS_BF16) { if (act == 0) GN_BWD(bf16, 0) else GN_BWD(bf16, 1) }
+  else return MTUS_ERR_UNSUPPORTED;
+#undef GN_BWD
   MTUS_LAUNCH_STATUS_N(2);
   return MTUS_OK;
+}
+
+extern "C" int mtus_groupnorm_relu_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* rstd,
+                                       const float* gamma, void* dx, float* dgamma, float* dbeta, float* ws, int B, int HW,
+                                       int C, int G, int dtype, void* stream) {
+  MTUS_CHECK_ARG(y);
+  return mtus_groupnorm_act_bwd(dy, x, y, mean, rstd, gamma, nullptr, dx, dgamma, dbeta, ws, B, HW, C, G, 0, dtype, stream);
 }
 
 // ---- bilinear x2, align_corners=True (aten upsample_bilinear2d semantics) ------------------------

@@ -171,9 +171,14 @@ extern "C" int mtus_fpn_forward(const mtus_fpn_config* cfg, const void* const* f
     mtus_gemm_desc d; memset(&d, 0, sizeof(d));
     d.a = cin[k]; d.lda = p.cin[k]; d.b = W(p.lat_w[k]); d.ldb = p.cin[k];
     d.M = p.B * p.size[k] * p.size[k]; d.N = p.P; d.K = p.cin[k]; d.bias = F(p.lat_b[k]);
-    if (k < 3) { d.res = A(p.pl[k + 1]); d.ld_res = p.P; d.res_mode = 2; d.res_h = p.size[k]; d.res_w = p.size[k]; }
+    // bf16: the persistent TMA-in / TMA-out GEMM engine has no gathered-residual epilogue, so the nearest-x2 top-down
+    // add is one extra in-place elementwise pass (still ~4x faster than the one-tile-per-CTA engine that fuses it);
+    // fp32 (parity mode): fused in the SIMT epilogue
+    const bool split_add = (k < 3) && dt == MTUS_BF16 && be != MTUS_BACKEND_SIMT;
+    if (k < 3 && !split_add) { d.res = A(p.pl[k + 1]); d.ld_res = p.P; d.res_mode = 2; d.res_h = p.size[k]; d.res_w = p.size[k]; }
     d.out = A(p.pl[k]); d.ld_out = p.P; d.dtype = dt; d.backend = be;
     RUN(mtus_gemm(&d, stream));
+    if (split_add) RUN(mtus_upsample_add_fwd(A(p.pl[k]), A(p.pl[k + 1]), A(p.pl[k]), p.B, p.size[k], p.size[k], p.P, dt, stream));
   }
   // towers
   const void* merged[4];

@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(128) lnv2_fwd_kernel(const TX* __restrict__ x,
   }
 }
 
-template <typename T, typename TDY, typename TX, int LPR, int NV, int MODE>
+template <typename T, typename TDY, typename TX, int LPR, int NV, int U, int MODE>
 __global__ void __launch_bounds__(128) lnv2_bwd_kernel(LnxBwdArgs a, MergeGeom g) {
   constexpr int RPW = 32 / LPR;
   extern __shared__ float acc_smem[];                         // [3][4 warps][C] partial dgamma / dbeta / colsum
@@ -596,58 +596,75 @@ __global__ void __launch_bounds__(128) lnv2_bwd_kernel(LnxBwdArgs a, MergeGeom g
   }
   pdl_trigger();
   pdl_wait();
-  for (int64_t row0 = gwarp * RPW; row0 < rows; row0 += nwarps * RPW) {
-    const int64_t row = row0 + grp;
-    const bool active = row < rows;
-    const float mean = active ? a.mean[row] : 0.f, rstd = active ? a.rstd[row] : 0.f;
-    float xh[NV][8], gy[NV][8];
-    int64_t off[NV];
-    float s1 = 0.f, s2 = 0.f;
+  // U rows per warp iteration: all the loads of the U rows (x, dy and the incoming stream gradient) are issued before
+  // the first reduction, so one HBM latency is paid per iteration, not two per row
+  for (int64_t row0 = gwarp * (RPW * U); row0 < rows; row0 += nwarps * (RPW * U)) {
+    float xh[U][NV][8], gy[U][NV][8], rs[U][NV][8];
+    int64_t off[U][NV];
+    float mean[U], rstd[U], s1[U], s2[U];
+    bool active[U];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int col = (i * LPR + sub) * 8;
-      off[i] = -1;
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + u * RPW + grp;
+      active[u] = row < rows;
+      mean[u] = active[u] ? a.mean[row] : 0.f; rstd[u] = active[u] ? a.rstd[row] : 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { xh[i][k] = 0.f; gy[i][k] = 0.f; }
-      if (active && col < C) {
-        float xv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dv[8];
-        bool valid; const TX* p = ln_src<TX, MODE>(x, row, col, C, g, valid);
-        if (valid) { IO<TX>::load8(p, xv); off[i] = p - x; }
-        IO<TDY>::load8(dy + row * C + col, dv);
+      for (int i = 0; i < NV; ++i) {
+        const int col = (i * LPR + sub) * 8;
+        off[u][i] = -1;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          xh[i][k] = (xv[k] - mean) * rstd;
-          gy[i][k] = dv[k] * gm[i][k];
-          s1 += gy[i][k];
-          s2 += gy[i][k] * xh[i][k];
-          adg[i][k] += dv[k] * xh[i][k];
-          adb[i][k] += dv[k];
+        for (int k = 0; k < 8; ++k) { xh[u][i][k] = 0.f; gy[u][i][k] = 0.f; rs[u][i][k] = 0.f; }
+        if (active[u] && col < C) {
+          bool valid; const TX* p = ln_src<TX, MODE>(x, row, col, C, g, valid);
+          if (valid) { IO<TX>::load8(p, xh[u][i]); off[u][i] = p - x; if (a.dres) IO<float>::load8(a.dres + off[u][i], rs[u][i]); }
+          IO<TDY>::load8(dy + row * C + col, gy[u][i]);
         }
       }
     }
-    s1 = group_sum<LPR>(s1) * invC; s2 = group_sum<LPR>(s2) * invC;
-    if (active) {
-      const float rsc = a.lp_rowscale ? __ldg(a.lp_rowscale + row / a.rows_per_sample) : 1.0f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      s1[u] = 0.f; s2[u] = 0.f;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        if (off[i] >= 0) {
-          float o[8];
+        const int col = (i * LPR + sub) * 8;
+        if (active[u] && col < C) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] = rstd * (gy[i][k] - s1 - xh[i][k] * s2);
-          if (a.dres) {
-            float r[8]; IO<float>::load8(a.dres + off[i], r);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] += r[k];
+          for (int k = 0; k < 8; ++k) {
+            const float dv = gy[u][i][k];
+            const float xn = off[u][i] >= 0 ? (xh[u][i][k] - mean[u]) * rstd[u] : (0.f - mean[u]) * rstd[u];
+            xh[u][i][k] = xn;
+            gy[u][i][k] = dv * gm[i][k];
+            s1[u] += gy[u][i][k];
+            s2[u] += gy[u][i][k] * xn;
+            adg[i][k] += dv * xn;
+            adb[i][k] += dv;
           }
-          if (a.dx) IO<float>::store8(a.dx + off[i], o);
-          if (dx_lp) {
+        }
+      }
+    }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] *= rsc;
-            IO<T>::store8(dx_lp + off[i], o);
-            if (want_cs) {
-              float rr[8]; IO<T>::load8_reg(o, rr);
+    for (int u = 0; u < U; ++u) { s1[u] = group_sum<LPR>(s1[u]) * invC; s2[u] = group_sum<LPR>(s2[u]) * invC; }
 #pragma unroll
-              for (int k = 0; k < 8; ++k) acs[i][k] += rr[k];
+    for (int u = 0; u < U; ++u) {
+      if (active[u]) {
+        const int64_t row = row0 + u * RPW + grp;
+        const float rsc = a.lp_rowscale ? __ldg(a.lp_rowscale + row / a.rows_per_sample) : 1.0f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          if (off[u][i] >= 0) {
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = rstd[u] * (gy[u][i][k] - s1[u] - xh[u][i][k] * s2[u]) + rs[u][i][k];
+            if (a.dx) IO<float>::store8(a.dx + off[u][i], o);
+            if (dx_lp) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) o[k] *= rsc;
+              IO<T>::store8(dx_lp + off[u][i], o);
+              if (want_cs) {
+                float rr[8]; IO<T>::load8_reg(o, rr);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acs[i][k] += rr[k];
+              }
             }
           }
         }
@@ -714,12 +731,12 @@ template <typename T, typename TDY, typename TX, int MODE>
 static int lnv2_bwd_launch(const LnxBwdArgs& a, MergeGeom g, cudaStream_t st) {
   const int C = a.C, nvec = C / 8;
   const size_t sm = (size_t)12 * C * sizeof(float);
-#define V2B(LPR_, NV_)                                                                                       \
+#define V2B(LPR_, NV_, U_, BPS_)                                                                             \
   {                                                                                                          \
-    const int rpi = (32 / LPR_) * 4;                                                                         \
+    const int rpi = (32 / LPR_) * U_ * 4;                                                                    \
     int64_t blocks = (a.rows + rpi - 1) / rpi;                                                               \
-    if (blocks > 148 * 6) blocks = 148 * 6;                                                                  \
-    auto kern = lnv2_bwd_kernel<T, TDY, TX, LPR_, NV_, MODE>;                                                \
+    if (blocks > 148 * BPS_) blocks = 148 * BPS_;                                                            \
+    auto kern = lnv2_bwd_kernel<T, TDY, TX, LPR_, NV_, U_, MODE>;                                            \
     if (sm > 48 * 1024) {                                                                                    \
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);      \
       if (e != cudaSuccess) return (int)e;                                                                   \
@@ -727,13 +744,13 @@ static int lnv2_bwd_launch(const LnxBwdArgs& a, MergeGeom g, cudaStream_t st) {
     cudaError_t le = mtus_launch_pdl(kern, dim3((int)blocks), dim3(128), sm, st, a, g);                      \
     if (le != cudaSuccess) return (int)le;                                                                   \
   }
-  if (nvec <= 4) V2B(4, 1)
-  else if (nvec <= 8) V2B(8, 1)
-  else if (nvec <= 16) V2B(16, 1)
-  else if (nvec <= 32) V2B(32, 1)
-  else if (nvec <= 64) V2B(32, 2)
-  else if (nvec <= 96) V2B(32, 3)
-  else V2B(32, 4)
+  if (nvec <= 4) V2B(4, 1, 2, 6)
+  else if (nvec <= 8) V2B(8, 1, 2, 6)
+  else if (nvec <= 16) V2B(16, 1, 2, 6)
+  else if (nvec <= 32) V2B(32, 1, 2, 6)
+  else if (nvec <= 64) V2B(32, 2, 2, 3)
+  else if (nvec <= 96) V2B(32, 3, 1, 3)
+  else V2B(32, 4, 1, 3)
 #undef V2B
   MTUS_LAUNCH_STATUS();
   return MTUS_OK;

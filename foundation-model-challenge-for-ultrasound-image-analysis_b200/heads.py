@@ -36,6 +36,41 @@ class _SmpClassificationHead(nn.Sequential):
         super().__init__(nn.AdaptiveAvgPool2d(1), nn.Flatten(), drop, nn.Linear(in_channels, classes), nn.Identity())
 
 
+class _GroupNormSiLUFn(torch.autograd.Function):
+    """silu(group_norm(x)) for a channels-last CUDA tensor through the library's GroupNorm kernels (one statistics pass,
+    one fused normalise + SiLU pass; backward recomputes the pre-activation) -- replaces nn.GroupNorm + nn.SiLU, which
+    under autocast run in fp32 behind two dtype / layout copies of the [B, 128, 56, 56] activation each way."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, groups, eps):
+        from . import ops
+        xn = x.permute(0, 2, 3, 1)                       # NHWC view of a channels-last tensor
+        if not xn.is_contiguous():
+            xn = xn.contiguous()
+        w, b = weight.float().contiguous(), bias.float().contiguous()
+        y, mean, rstd = ops.groupnorm_silu_fwd(xn, w, b, groups, eps)
+        ctx.save_for_backward(xn, mean, rstd, w, b)
+        ctx.groups = groups
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import ops
+        xn, mean, rstd, w, b = ctx.saved_tensors
+        dyn = dy.permute(0, 2, 3, 1)
+        if dyn.dtype != xn.dtype:
+            dyn = dyn.to(xn.dtype)
+        if not dyn.is_contiguous():
+            dyn = dyn.contiguous()
+        dx, dg, db = ops.groupnorm_silu_bwd(dyn, xn, mean, rstd, w, b, ctx.groups)
+        return dx.permute(0, 3, 1, 2), dg, db, None, None
+
+
+def _fused_gn_silu_ok(x, gn):
+    return (x.is_cuda and x.dim() == 4 and x.dtype in (torch.bfloat16, torch.float32) and x.shape[1] % 8 == 0
+            and x.shape[1] // 8 <= 256 and gn.affine and x.shape[0] <= 65535)
+
+
 class SegmentationHead(nn.Module):
     def __init__(self, in_channels, num_classes, kernel_size=1, upsampling=4, mid_channels=None, num_layers=2):
         super().__init__()
@@ -49,6 +84,25 @@ class SegmentationHead(nn.Module):
         self.head = _SmpSegmentationHead(cur, num_classes, kernel_size=kernel_size, upsampling=upsampling)
 
     def forward(self, x):
+        # Conv -> GroupNorm -> SiLU triples: the norm + activation run as one fused library op on CUDA (same parameters,
+        # same state-dict keys); anything else (CPU, exotic shapes) takes the plain module path
+        if isinstance(self.pre_head, nn.Sequential) and x.is_cuda:
+            mods = list(self.pre_head)
+            i = 0
+            while i < len(mods):
+                if (i + 2 < len(mods) and isinstance(mods[i], nn.Conv2d) and isinstance(mods[i + 1], nn.GroupNorm)
+                        and isinstance(mods[i + 2], nn.SiLU)):
+                    x = mods[i](x)
+                    gn = mods[i + 1]
+                    if _fused_gn_silu_ok(x, gn):
+                        x = _GroupNormSiLUFn.apply(x, gn.weight, gn.bias, gn.num_groups, gn.eps)
+                    else:
+                        x = mods[i + 2](gn(x))
+                    i += 3
+                else:
+                    x = mods[i](x)
+                    i += 1
+            return self.head(x)
         return self.head(self.pre_head(x))
 
 

@@ -240,6 +240,27 @@ def groupnorm_relu_bwd(dy, x, y, mean, rstd, gamma, groups=32):
     return dx, dg, db
 
 
+def groupnorm_silu_fwd(x, gamma, beta, groups=32, eps=1e-5):
+    """y = silu(group_norm(x)) on an NHWC tensor [B,H,W,C]; returns (y, mean, rstd)."""
+    B, H, W, Cc = x.shape
+    mean = torch.empty(B * groups, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    check(lib().mtus_groupnorm_stats(ptr(x), ptr(mean), ptr(rstd), B, H * W, Cc, groups, eps, _dt(x), stream_ptr()), "groupnorm_stats")
+    y = torch.empty_like(x)
+    check(lib().mtus_groupnorm_act_fwd(ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(y), B, H * W, Cc, groups, 1, _dt(x), stream_ptr()), "groupnorm_act_fwd")
+    return y, mean, rstd
+
+
+def groupnorm_silu_bwd(dy, x, mean, rstd, gamma, beta, groups=32):
+    B, H, W, Cc = x.shape
+    dx = torch.empty_like(x)
+    dg = torch.zeros(Cc, dtype=torch.float32, device=x.device)
+    db = torch.zeros_like(dg)
+    ws = torch.empty(2 * B * groups, dtype=torch.float32, device=x.device)
+    check(lib().mtus_groupnorm_act_bwd(ptr(dy), ptr(x), None, ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(dx), ptr(dg), ptr(db), ptr(ws), B, H * W, Cc, groups, 1, _dt(x), stream_ptr()), "groupnorm_act_bwd")
+    return dx, dg, db
+
+
 def bilinear2x_fwd(x):
     B, H, W, Cc = x.shape
     y = torch.empty(B, 2 * H, 2 * W, Cc, dtype=x.dtype, device=x.device)

@@ -176,6 +176,14 @@ int mtus_groupnorm_relu_fwd(const void* x, const float* mean, const float* rstd,
 int mtus_groupnorm_relu_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* rstd,
                             const float* gamma, void* dx, float* dgamma, float* dbeta, float* ws, int B, int HW,
                             int C, int G, int dtype, void* stream);
+/* Same kernels with a selectable activation: act 0 = ReLU, 1 = SiLU (the reference's segmentation head stacks
+ * Conv3x3 -> GroupNorm -> SiLU, code/models/heads.py:16-42).  SiLU backward recomputes the
+ * pre-activation from x, so y may be NULL and beta is required; ReLU backward needs y. */
+int mtus_groupnorm_act_fwd(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                           void* y, int B, int HW, int C, int G, int act, int dtype, void* stream);
+int mtus_groupnorm_act_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* rstd,
+                           const float* gamma, const float* beta, void* dx, float* dgamma, float* dbeta, float* ws,
+                           int B, int HW, int C, int G, int act, int dtype, void* stream);
 /* bilinear x2, align_corners=True, NHWC */
 int mtus_bilinear2x_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
 int mtus_bilinear2x_bwd(const void* dy, void* dx, int B, int H, int W, int C, int dtype, void* stream);

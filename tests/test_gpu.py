@@ -216,3 +216,25 @@ def test_chunked_backward_equals_one_shot_backward(monkeypatch):
     for name, (p, off, numel, shape) in enc.model._params_by_name.items():
         a, b = ref[off:off + numel], got[off:off + numel]
         assert torch.allclose(a, b, rtol=1e-3, atol=1e-5 * scale + 1e-7), name
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_fused_groupnorm_silu_matches_pytorch(dtype, tol):
+    """silu(group_norm(x)) through mtus_groupnorm_act_{fwd,bwd} (the segmentation head's Conv -> GN -> SiLU stacks,
+    code/models/heads.py:16-42) against nn.GroupNorm + nn.SiLU in fp32: output, dx, dgamma, dbeta."""
+    from mtus_b200.heads import _GroupNormSiLUFn
+    g = torch.Generator().manual_seed(0)
+    for (B, C, H, W, groups) in ((2, 128, 56, 56, 32), (3, 64, 13, 9, 32), (1, 256, 7, 7, 32)):
+        x = (torch.randn(B, C, H, W, generator=g) * 1.5 + 0.3).cuda().to(memory_format=torch.channels_last)
+        w = (torch.rand(C, generator=g) + 0.5).cuda().requires_grad_(True)
+        b = (torch.randn(C, generator=g) * 0.2).cuda().requires_grad_(True)
+        dy = torch.randn(B, C, H, W, generator=g).cuda()
+        xr = x.clone().requires_grad_(True)
+        yr = torch.nn.functional.silu(torch.nn.functional.group_norm(xr, groups, w, b, 1e-5))
+        gx_r, gw_r, gb_r = torch.autograd.grad(yr, (xr, w, b), dy)
+        xk = x.to(dtype).requires_grad_(True)
+        yk = _GroupNormSiLUFn.apply(xk, w, b, groups, 1e-5)
+        gx_k, gw_k, gb_k = torch.autograd.grad(yk, (xk, w, b), dy.to(dtype))
+        for name, a, r in (("y", yk, yr), ("dx", gx_k, gx_r), ("dgamma", gw_k, gw_r), ("dbeta", gb_k, gb_r)):
+            err = (a.float() - r).abs().max().item() / (r.abs().max().item() + 1e-12)
+            assert err <= tol, f"{name} {dtype} {(B, C, H, W)}: rel err {err}"
