@@ -264,6 +264,27 @@ def _kernel_rooflines(peaks, device):
                   "peak": peaks["hbm"], "unit": "GB/s", "frac": round(by / t / 1e9 / peaks["hbm"], 4),
                   "attn_only_tflops": round(fl / t / 1e12, 2),
                   "attn_only_frac_of_bf16_peak": round(fl / t / 1e12 / peaks["tc_sustained"], 4)})
+    # window attention bwd, stage 1: q, k, v, o, dO in; dq, dk, dv out: 8*C*s bytes per token (+ lse, negligible)
+    def make_bwd():
+        q = torch.randn(32, 56, 56, 384, device=device).bfloat16()
+        o, l = ops.window_attn_fwd(q, tab, bias, 4, 7, 3, return_lse=True)
+        return q, o, l, torch.randn_like(o)
+    t = ring_time(make_bwd, lambda s_: ops.window_attn_bwd(s_[3], s_[0], s_[1], tab, bias, 4, 7, 3, lse=s_[2], with_colsum=True),
+                  32 * 3136 * 128 * 16, launches=24)
+    by = 8.0 * 32 * 3136 * 128 * 2
+    extra.append({"kernel": "window_attn_mma_bwd_kernel stage 1 (shifted) bf16", "bound": "hbm", "achieved": round(by / t / 1e9, 1),
+                  "peak": peaks["hbm"], "unit": "GB/s", "frac": round(by / t / 1e9 / peaks["hbm"], 4),
+                  "attn_only_tflops": round(2.5 * fl / t / 1e12, 2)})
+    # LayerNorm bwd (bf16 dy, fp32 x, fp32 stream gradient in / out, bf16 operand copy out), stage 1: rows*C*(2+4+4+4+2)
+    def make_lnb():
+        x = torch.randn(rows, C1, device=device)
+        y, mean, rstd = ops.layernorm_fwd_mixed(x, g_, b_, torch.bfloat16)
+        return torch.randn(rows, C1, device=device).bfloat16(), x, mean, rstd, torch.randn(rows, C1, device=device)
+    t = ring_time(make_lnb, lambda s_: ops.layernorm_bwd_mixed(s_[0], s_[1], g_, s_[2], s_[3], s_[4], lp_dtype=torch.bfloat16),
+                  rows * C1 * 16, launches=24)
+    by = rows * C1 * 16.0
+    extra.append({"kernel": "lnv2_bwd_kernel [100352,128] bf16 dy, fp32 stream", "bound": "hbm", "achieved": round(by / t / 1e9, 1),
+                  "peak": peaks["hbm"], "unit": "GB/s", "frac": round(by / t / 1e9 / peaks["hbm"], 4)})
     res["roofline_extra"] = extra
     return res
 
