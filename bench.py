@@ -343,15 +343,16 @@ def run_native(args):
         trainer.step(devb[key[tid0]][0], devb[key[tid0]][1], tid0)
 
     def timed(step_fn):
-        """W warm-up steps, then K timed steps bracketed by barrier + synchronize; device time, max over ranks."""
+        """W warm-up steps, then K timed steps bracketed by barrier + synchronize; device time, max over ranks.
+        step_fn(i, last): i indexes the task sequence; last marks the final step of the (warm-up or timed) run."""
         for i in range(args.warmup):
-            step_fn(seq[i])
+            step_fn(i, i == args.warmup - 1)
         barrier()
         l0 = L.mtus_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(args.warmup, n_total):
-            step_fn(seq[i])
+            step_fn(i, i == n_total - 1)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -360,7 +361,8 @@ def run_native(args):
         return float(ms.item()), L.mtus_launch_count() - l0
 
     # ---- value: inputs already resident in HBM -------------------------------------------------
-    def step_resident(tid):
+    def step_resident(i, last):
+        tid = seq[i]
         x, y = devb[key[tid]]
         trainer.step(x, y, tid)
 
@@ -371,14 +373,28 @@ def run_native(args):
 
     # ---- e2e: host inputs through the public API, loss read back every step -----------------------
     h2d = d2h = 0
+    h2d_sum = h2d_n = 0
 
-    def step_e2e(tid):
-        nonlocal h2d, d2h
+    # Every step's batch is copied from pinned host memory inside the timed region (K copies for K steps); the copy
+    # of step i+1 is issued on DevicePrefetcher's side stream right after step i is enqueued, so it runs under step
+    # i's compute instead of in front of step i+1 (the first step of a run has nothing to hide behind).
+    prefetch = m.DevicePrefetcher(dev)
+
+    def step_e2e(i, last):
+        nonlocal h2d, d2h, h2d_sum, h2d_n
+        tid = seq[i]
         x, y = host[key[tid]]
-        xd, yd = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
+        if not prefetch.pending():
+            prefetch.issue(x, y)
+        xd, yd = prefetch.take()
         loss = trainer.step(xd, yd, tid)
+        if not last:
+            prefetch.issue(*host[key[seq[i + 1]]])
         v = loss.item()                          # device -> host read of the step's result
         h2d = x.numel() * x.element_size() + y.numel() * y.element_size()
+        if i >= args.warmup:
+            h2d_sum += h2d
+            h2d_n += 1
         d2h = loss.element_size()
         return v
 
@@ -408,7 +424,7 @@ def run_native(args):
                    "l2": f"no explicit flush: each step streams a {ws_gb} GB activation workspace plus 0.35 GB of weights, "
                          "far beyond the 126 MB L2",
                    "detection_loss": "Detection (SURVEY 8d caveat: shipped YAML pairs the baseline head with the CenterNet loss)"},
-        "e2e": {"value": round(e2e, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+        "e2e": {"value": round(e2e, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d_sum / max(h2d_n, 1)), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": int(launches),
         "clocks": clocks,

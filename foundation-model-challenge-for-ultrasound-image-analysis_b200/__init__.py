@@ -9,7 +9,7 @@ Public surface (mirrors /root/reference/code/models/__init__.py:3-16 for the hot
     build_fpn_decoder, build_decoders, FPNDecoder                  (decoders.py)
     MultiTaskModel, build_model, build_optimizer                   (multitask_model.py)
     Config, swin_b_27task, make_config                             (configs.py)
-    DistributedTaskSampler, GradAllReducer, DataParallelTrainer    (parallel.py)
+    DistributedTaskSampler, GradAllReducer, DataParallelTrainer, DevicePrefetcher    (parallel.py)
 """
 
 from . import _lib
@@ -20,12 +20,12 @@ from .heads import build_all_heads, build_task_head
 from .losses import build_all_losses, compute_task_loss
 from .multitask_model import MultiTaskModel, build_model, build_optimizer, build_flat_optimizer
 from .optim import FlatAdamW
-from .parallel import DistributedTaskSampler, GradAllReducer, DataParallelTrainer, synthetic_batch
+from .parallel import DistributedTaskSampler, GradAllReducer, DataParallelTrainer, DevicePrefetcher, synthetic_batch
 
 __all__ = [
     "build_encoder", "SwinTransformerEncoder", "SwinCore", "SWIN_MODEL_MAPPING", "SWIN_ARCHS",
     "build_fpn_decoder", "build_decoders", "FPNDecoder", "build_all_heads", "build_task_head",
     "build_all_losses", "compute_task_loss", "MultiTaskModel", "build_model", "build_optimizer", "build_flat_optimizer", "FlatAdamW",
     "Config", "make_config", "swin_b_27task", "tasks_27",
-    "DistributedTaskSampler", "GradAllReducer", "DataParallelTrainer", "synthetic_batch",
+    "DistributedTaskSampler", "GradAllReducer", "DataParallelTrainer", "DevicePrefetcher", "synthetic_batch",
 ]

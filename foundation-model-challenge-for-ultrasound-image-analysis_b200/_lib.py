@@ -106,6 +106,7 @@ SIGNATURES = {
     "mtus_swin_feature_offset": (i64, [_P(SwinConfig), i32]),
     "mtus_swin_forward": (i32, [_P(SwinConfig), vp, i32, vp, vp, vp, vp, _P(vp), i32, i32, vp]),
     "mtus_swin_backward": (i32, [_P(SwinConfig), vp, vp, vp, vp, _P(vp), i32, i32, vp, i32, i32, vp]),
+    "mtus_graph_cache_stats": (None, [vp, vp, vp]),
     "mtus_swin_backward_blocks": (i32, [_P(SwinConfig), vp, vp, vp, vp, _P(vp), i32, i32, vp, i32, i32, vp]),
     "mtus_fpn_param_count": (i64, [_P(FpnConfig)]),
     "mtus_fpn_workspace_bytes": (i64, [_P(FpnConfig)]),

@@ -42,6 +42,7 @@ struct Plan {
   size_t cols, pe_pre, pe_mean, pe_rstd, x0;
   StageA sa[4];
   size_t G, Gb, Gb2, dLN, dQKV, dH, tmpF;
+  size_t dp_slot, dF[4];   // drop-path scales copied by forward; incoming feature gradients as fp32 NHWC maps
   size_t ws_bytes;
 };
 
@@ -160,6 +161,12 @@ bool build_plan(const mtus_swin_config* c, Plan& p) {
     // stage output as an NHWC map in the operand dtype (what the FPN consumes); fp32 mode: the stream itself
     s.feat = (p.dtype == MTUS_F32) ? s.blk.back().xout : a.take(MC);
   }
+  {
+    int nblk = 0;
+    for (int i = 0; i < 4; ++i) nblk += p.depths[i];
+    p.dp_slot = a.take((size_t)2 * nblk * (p.B > 0 ? p.B : 1) * 4);
+    for (int i = 0; i < 4; ++i) p.dF[i] = p.training ? a.take((size_t)p.M[i] * p.C[i] * 4) : 0;
+  }
   if (p.training) {
     const size_t E0 = (size_t)p.M[0] * p.C0;            // M_i*C_i is largest at stage 0
     p.G = a.take(E0 * 4); p.tmpF = a.take(E0 * 4); p.Gb = a.take(E0 * es); p.Gb2 = a.take(E0 * es); p.dLN = a.take(E0 * es);
@@ -209,6 +216,91 @@ SideStream* side_stream() {
   return ss.state == 1 ? &ss : nullptr;
 }
 
+
+// ---- executor-level CUDA graph cache ------------------------------------------------------------------------------
+// One executor call is 170-330 launches whose arguments are fully determined by (config, pointers, ranges).  PyTorch's
+// caching allocator hands the same blocks back step after step, so the schedule is captured once per distinct
+// argument set (stream capture, the side-stream fork / join included) and replayed with one cudaGraphLaunch: the host
+// cost of a call drops from milliseconds to microseconds and kernel-to-kernel gaps shrink.  Keys are exact (every
+// pointer / scalar that reaches a kernel); a miss costs one capture + instantiate.  MTUS_GRAPHS=0 disables the cache;
+// calls made while the stream is already being captured by the caller run the plain schedule.
+struct GraphEntry { std::vector<uint8_t> key; cudaGraphExec_t exec; int64_t launches; uint64_t stamp; };
+std::vector<GraphEntry> g_graphs;
+uint64_t g_stamp = 0;
+int64_t g_graph_hits = 0, g_graph_misses = 0;
+constexpr size_t kMaxGraphs = 48;
+
+bool graphs_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTUS_GRAPHS"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  return v == 1;
+}
+
+struct KeyBuilder {
+  std::vector<uint8_t> k;
+  template <typename T> KeyBuilder& add(const T& v) {
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(&v);
+    k.insert(k.end(), p, p + sizeof(T));
+    return *this;
+  }
+};
+
+// body(stream) enqueues the schedule on `stream`.  Capture always happens on an internal stream (the caller's stream is
+// usually PyTorch's legacy default stream, which cannot be captured); the instantiated graph is then launched into the
+// caller's stream, which orders it like any other work there.
+cudaStream_t capture_stream() {
+  static cudaStream_t s[16] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (!s[dev] && cudaStreamCreateWithFlags(&s[dev], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return s[dev];
+}
+
+template <typename F>
+int run_cached(const std::vector<uint8_t>& key, cudaStream_t st, F&& body) {
+  if (!graphs_enabled()) return body((void*)st);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return body((void*)st); }
+  for (GraphEntry& e : g_graphs) {
+    if (e.key == key) {
+      e.stamp = ++g_stamp; ++g_graph_hits;
+      cudaError_t le = cudaGraphLaunch(e.exec, st);
+      if (le != cudaSuccess) return (int)le;
+      mtus_internal_count_launches((int)e.launches);
+      return MTUS_OK;
+    }
+  }
+  ++g_graph_misses;
+  // addresses that keep changing would mean one capture + instantiate per call: stop adding graphs when the cache
+  // clearly does not pay (lookups of the graphs already built continue)
+  if (g_graph_misses >= 64 && g_graph_hits < 4 * g_graph_misses) return body((void*)st);
+  cudaStream_t cap = capture_stream();
+  if (!cap || cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return body((void*)st); }
+  const int64_t before = mtus_launch_count();
+  const int rc = body((void*)cap);
+  const int64_t launches = mtus_launch_count() - before;
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+  mtus_internal_count_launches(-(int)launches);             // nothing ran yet: counted when the graph (or the eager retry) runs
+  if (rc != MTUS_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+  if (ce != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return body((void*)st); }
+  cudaGraphExec_t exec = nullptr;
+  ce = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess || !exec) { cudaGetLastError(); return body((void*)st); }
+  if (g_graphs.size() >= kMaxGraphs) {                      // evict the least recently used entry
+    size_t lru = 0;
+    for (size_t i = 1; i < g_graphs.size(); ++i) if (g_graphs[i].stamp < g_graphs[lru].stamp) lru = i;
+    cudaGraphExecDestroy(g_graphs[lru].exec);
+    g_graphs.erase(g_graphs.begin() + lru);
+  }
+  g_graphs.push_back(GraphEntry{key, exec, launches, ++g_stamp});
+  ce = cudaGraphLaunch(exec, st);
+  if (ce != cudaSuccess) return (int)ce;
+  mtus_internal_count_launches((int)launches);
+  return MTUS_OK;
+}
+
 #define CU(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return (int)e__; } while (0)
 
 }  // namespace
@@ -251,9 +343,48 @@ extern "C" int64_t mtus_swin_param_offset(const mtus_swin_config* cfg, const cha
   return -1;
 }
 
+static int swin_forward_impl(const mtus_swin_config* cfg, const void* x, int x_is_f32, const float* params,
+                             const void* params_lp, const float* droppath, void* workspace, void* const* feats,
+                             int feats_layout, int feats_f32, void* stream);
+
+static int swin_forward_impl(const mtus_swin_config* cfg, const void* x, int x_is_f32, const float* params,
+                             const void* params_lp, const float* droppath, void* workspace, void* const* feats,
+                             int feats_layout, int feats_f32, void* stream);
+
+// Forward = eager prologue + cached body.  The prologue touches the arguments whose addresses change from step to
+// step (the image batch, the drop-path draws): patch im2col into the workspace and a copy of the drop-path scales
+// into the workspace.  Everything after that reads only the parameter blocks and the workspace, so the body's CUDA
+// graph is keyed on addresses that stay put.
 extern "C" int mtus_swin_forward(const mtus_swin_config* cfg, const void* x, int x_is_f32, const float* params,
                                  const void* params_lp, const float* droppath, void* workspace, void* const* feats,
                                  int feats_layout, int feats_f32, void* stream) {
+  Plan p;
+  if (!build_plan(cfg, p)) return MTUS_ERR_BAD_ARG;
+  MTUS_CHECK_ARG(x && params && workspace && feats);
+  MTUS_CHECK_ARG(p.dtype == MTUS_F32 || params_lp);
+  if (p.B == 0) return MTUS_OK;
+  char* ws = reinterpret_cast<char*>(workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  RUN(mtus_patch_embed_im2col(x, ws + p.cols, p.B, p.S, p.S, x_is_f32 || p.dtype == MTUS_F32, p.dtype, stream));
+  const float* dp = nullptr;
+  if (droppath) {
+    int nblk = 0;
+    for (int i = 0; i < 4; ++i) nblk += p.depths[i];
+    CU(cudaMemcpyAsync(ws + p.dp_slot, droppath, (size_t)2 * nblk * p.B * 4, cudaMemcpyDeviceToDevice, st));
+    dp = reinterpret_cast<const float*>(ws + p.dp_slot);
+  }
+  int dev = 0; cudaGetDevice(&dev);
+  KeyBuilder kb;
+  kb.add((int)1).add(dev).add(*cfg).add(params).add(params_lp).add((int)(dp != nullptr)).add(workspace)
+    .add(feats[0]).add(feats[1]).add(feats[2]).add(feats[3]).add(feats_layout).add(feats_f32);
+  return run_cached(kb.k, st, [&](void* s_) {
+    return swin_forward_impl(cfg, x, x_is_f32, params, params_lp, dp, workspace, feats, feats_layout, feats_f32, s_);
+  });
+}
+
+static int swin_forward_impl(const mtus_swin_config* cfg, const void* x, int x_is_f32, const float* params,
+                             const void* params_lp, const float* droppath, void* workspace, void* const* feats,
+                             int feats_layout, int feats_f32, void* stream) {
   Plan p;
   if (!build_plan(cfg, p)) return MTUS_ERR_BAD_ARG;
   MTUS_CHECK_ARG(x && params && workspace && feats);
@@ -269,8 +400,8 @@ extern "C" int mtus_swin_forward(const mtus_swin_config* cfg, const void* x, int
   auto A = [&](size_t off) -> void* { return ws + off; };
   auto FA = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
 
-  // ---- patch embed: im2col -> GEMM(K=48, +bias) -> LayerNorm (output: the fp32 residual stream) ----
-  RUN(mtus_patch_embed_im2col(x, A(p.cols), p.B, p.S, p.S, x_is_f32 || dt == MTUS_F32, dt, stream));
+  // ---- patch embed: (im2col done by the caller) GEMM(K=48, +bias) -> LayerNorm (output: the fp32 residual stream) ----
+  (void)x_is_f32;
   {
     mtus_gemm_desc d; memset(&d, 0, sizeof(d));
     d.a = A(p.cols); d.lda = 64; d.b = W(p.pe_w); d.ldb = 48;
@@ -331,10 +462,59 @@ extern "C" int mtus_swin_backward(const mtus_swin_config* cfg, const float* para
   return mtus_swin_backward_blocks(cfg, params, params_lp, droppath, workspace, dfeats, dfeats_layout, dfeats_f32, grads, hi, lo, stream);
 }
 
+static int swin_backward_impl(const mtus_swin_config* cfg, const float* params, const void* params_lp,
+                              const float* droppath, void* workspace, const void* const* dfeats, int dfeats_layout,
+                              int dfeats_f32, float* grads, int block_hi, int block_lo, void* stream);
+
+// Backward = eager prologue + cached body, like forward: the incoming feature gradients (fresh autograd tensors every
+// step) are converted to fp32 NHWC maps in fixed workspace slots by the call that starts at the top block; the body
+// reads only the slots, the parameter blocks, the workspace (drop-path scales included: forward left them there) and
+// the gradient block.
 extern "C" int mtus_swin_backward_blocks(const mtus_swin_config* cfg, const float* params, const void* params_lp,
                                          const float* droppath, void* workspace, const void* const* dfeats,
                                          int dfeats_layout, int dfeats_f32, float* grads, int block_hi, int block_lo,
                                          void* stream) {
+  Plan p;
+  if (!build_plan(cfg, p)) return MTUS_ERR_BAD_ARG;
+  MTUS_CHECK_ARG(params && workspace && dfeats && grads && p.training);
+  MTUS_CHECK_ARG(p.dtype == MTUS_F32 || params_lp);
+  const int n_blocks = p.depths[0] + p.depths[1] + p.depths[2] + p.depths[3];
+  MTUS_CHECK_ARG(block_hi <= n_blocks && block_lo >= 0 && block_lo < block_hi);
+  if (p.B == 0) return MTUS_OK;
+  char* ws = reinterpret_cast<char*>(workspace);
+  const int dt = p.dtype;
+  int mask = 0;
+  for (int i = 0; i < 4; ++i) if (dfeats[i]) mask |= 1 << i;
+  if (block_hi == n_blocks) {
+    for (int i = 0; i < 4; ++i) {
+      if (!dfeats[i]) continue;
+      float* dst = reinterpret_cast<float*>(ws + p.dF[i]);
+      if (dfeats_layout == 0) RUN(mtus_convert(dfeats[i], dst, p.B, p.C[i], p.res[i] * p.res[i], 1, dfeats_f32, 1, dt, stream));
+      else {
+        MTUS_CHECK_ARG(!(dfeats_f32 && dt != MTUS_F32));
+        RUN(mtus_convert(dfeats[i], dst, p.B, p.res[i] * p.res[i], p.C[i], 0, dt == MTUS_F32, 1, dt, stream));
+      }
+    }
+  }
+  const float* dp = droppath ? reinterpret_cast<const float*>(ws + p.dp_slot) : nullptr;
+  int dev = 0; cudaGetDevice(&dev);
+  KeyBuilder kb;
+  kb.add((int)2).add(dev).add(*cfg).add(params).add(params_lp).add((int)(dp != nullptr)).add(workspace).add(mask).add(grads)
+    .add(block_hi).add(block_lo);
+  return run_cached(kb.k, (cudaStream_t)stream, [&](void* s_) {
+    return swin_backward_impl(cfg, params, params_lp, dp, workspace, dfeats, dfeats_layout, dfeats_f32, grads, block_hi, block_lo, s_);
+  });
+}
+
+extern "C" void mtus_graph_cache_stats(int64_t* hits, int64_t* misses, int64_t* entries) {
+  if (hits) *hits = g_graph_hits;
+  if (misses) *misses = g_graph_misses;
+  if (entries) *entries = (int64_t)g_graphs.size();
+}
+
+static int swin_backward_impl(const mtus_swin_config* cfg, const float* params, const void* params_lp,
+                              const float* droppath, void* workspace, const void* const* dfeats, int dfeats_layout,
+                              int dfeats_f32, float* grads, int block_hi, int block_lo, void* stream) {
   Plan p;
   if (!build_plan(cfg, p)) return MTUS_ERR_BAD_ARG;
   MTUS_CHECK_ARG(params && workspace && dfeats && grads && p.training);
@@ -362,12 +542,8 @@ extern "C" int mtus_swin_backward_blocks(const mtus_swin_config* cfg, const floa
   void* wst = ss ? (void*)ss->s : stream;     // stream of the weight-gradient GEMMs
   bool d2_pending = false;
 
-  // dfeat (caller layout / dtype) -> fp32 NHWC
-  auto load_dfeat = [&](int i, float* dst) -> int {
-    if (dfeats_layout == 0) return mtus_convert(dfeats[i], dst, p.B, p.C[i], p.res[i] * p.res[i], 1, dfeats_f32, 1, dt, stream);
-    if (dfeats_f32 && dt != MTUS_F32) return MTUS_ERR_BAD_ARG;
-    return mtus_convert(dfeats[i], dst, p.B, p.res[i] * p.res[i], p.C[i], 0, dt == MTUS_F32, 1, dt, stream);
-  };
+  // incoming feature gradients: fp32 NHWC maps in the workspace slots dF[i] (written by the caller's prologue)
+  (void)dfeats_layout; (void)dfeats_f32; (void)tmpF;
 
   // global block index g counts blocks in forward order; this call runs blocks block_hi-1 down to block_lo and, after
   // block 0 of a stage, that stage's PatchMerging (or patch-embed) backward
@@ -382,7 +558,7 @@ extern "C" int mtus_swin_backward_blocks(const mtus_swin_config* cfg, const floa
     const int rps = res * res;
     int gblk = stage_first + j_hi - 1;
     if (i == 3 && j_hi == p.depths[3]) {  // top of the chain: G = NHWC(dfeat3) or zero, Gb = dp2 * G for the last block's fc2
-      if (dfeats[3]) RUN(load_dfeat(3, G));
+      if (dfeats[3]) { cudaError_t e = cudaMemcpyAsync(G, FA(p.dF[3]), (size_t)M * Cc * 4, cudaMemcpyDeviceToDevice, st); if (e != cudaSuccess) return (int)e; }
       else { cudaError_t e = cudaMemsetAsync(G, 0, (size_t)M * Cc * 4, st); if (e != cudaSuccess) return (int)e; }
       const BlockP& bl = p.sp[3].blk.back();
       const float* dp2 = droppath ? droppath + (size_t)(2 * gblk + 1) * p.B : nullptr;
@@ -433,7 +609,7 @@ extern "C" int mtus_swin_backward_blocks(const mtus_swin_config* cfg, const floa
       RUN(mtus_linear_wgrad(Gb, A(s.mg_ln), GR(p.sp[i].mg_red), nullptr, M, Cc, 4 * Cp, dt, be, stream));
       RUN(mtus_linear_dgrad(Gb, W(p.sp[i].mg_red), dH, nullptr, nullptr, 1, nullptr, M, Cc, 4 * Cp, dt, be, stream));
       const float* dres = nullptr;
-      if (dfeats[i - 1]) { RUN(load_dfeat(i - 1, tmpF)); dres = tmpF; }
+      if (dfeats[i - 1]) dres = FA(p.dF[i - 1]);
       const BlockP& bl = p.sp[i - 1].blk.back();                 // consumer of the new Gb: last block of stage i-1
       const float* dp2 = droppath ? droppath + (size_t)(2 * (gblk_end - 1) + 1) * p.B : nullptr;
       RUN(mtus_patch_merge_ln_bwd_mixed(dH, A(p.sa[i - 1].blk.back().xout), F(p.sp[i].mg_nw), FA(s.mg_mean), FA(s.mg_rstd), dres, G, Gb, dp2,

@@ -63,6 +63,7 @@ class _SwinFn(torch.autograd.Function):
     def forward(ctx, core, x, *params):
         needs_grad = any(ctx.needs_input_grad[2:])
         feats, saved = core._run_forward(x, training_plan=needs_grad)
+        ctx.set_materialize_grads(False)         # unused features arrive as None, not as zero tensors to convert
         ctx.core = core
         ctx.saved = saved
         ctx.param_needs = ctx.needs_input_grad[2:]
@@ -175,10 +176,16 @@ class SwinCore(FlatParamModule):
             x = x.to(tdt)
         x = x.contiguous()
         cfg = self._cfg(B, training_plan)
-        ws = torch.empty(L.mtus_swin_workspace_bytes(C.byref(cfg)), dtype=torch.uint8, device=x.device)
+        # Buffers the executor's CUDA-graph cache keys on live at fixed addresses: the bf16 parameter shadow is one
+        # persistent buffer; training workspaces (saved for backward) come from a small pool and go back to it when
+        # their backward has run.  Inference workspaces stay per call (the zero-copy features are views of them).
+        ws_bytes = L.mtus_swin_workspace_bytes(C.byref(cfg))
+        ws = self._take_workspace(B, ws_bytes, x.device) if training_plan else torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         lp = None
         if dt == _lib.BF16:
-            lp = torch.empty(self._n_flat, dtype=torch.bfloat16, device=x.device)
+            lp = getattr(self, "_lp_buf", None)
+            if lp is None or lp.device != x.device or lp.numel() != self._n_flat:
+                lp = self._lp_buf = torch.empty(self._n_flat, dtype=torch.bfloat16, device=x.device)
             _lib.check(L.mtus_cast_f32_to_bf16(_lib.ptr(flat), _lib.ptr(lp), self._n_flat, _lib.stream_ptr()), "cast")
         dp = self._droppath_scales(B, x.device)
         out_f32 = self.output_dtype in ("fp32", "float32") and dt != _lib.F32
@@ -203,11 +210,33 @@ class SwinCore(FlatParamModule):
         saved = (cfg, ws, lp, dp, flat, out_f32) if training_plan else None
         return feats, saved
 
+    def _take_workspace(self, batch: int, nbytes: int, device):
+        pool = self.__dict__.setdefault("_ws_pool", {})
+        free = pool.setdefault((batch, nbytes, str(device)), [])
+        return free.pop() if free else torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+    def _return_workspace(self, batch: int, ws):
+        free = self.__dict__.setdefault("_ws_pool", {}).setdefault((batch, ws.numel(), str(ws.device)), [])
+        if len(free) < 2:
+            free.append(ws)
+
+    def _grad_block(self, device):
+        """Zeroed flat gradient block.  The persistent block is reused only when no parameter still holds a gradient
+        (i.e. after zero_grad(set_to_none=True)): with gradient accumulation the previous views must stay intact."""
+        buf = getattr(self, "_grad_buf", None)
+        ps = self.ordered_params()
+        if buf is not None and buf.device == device and all(p.grad is None for p in ps):
+            return buf.zero_()
+        g = torch.zeros(self._n_flat, dtype=torch.float32, device=device)
+        if buf is None or buf.device != device:
+            self._grad_buf = g
+        return g
+
     def _run_backward(self, saved, dfeats):
         cfg, ws, lp, dp, flat, out_f32 = saved
         L = _lib.lib()
         dt, tdt = precision_to_dtype(self.precision)
-        flat_grad = torch.zeros(self._n_flat, dtype=torch.float32, device=flat.device)
+        flat_grad = self._grad_block(flat.device)
         want = torch.float32 if (out_f32 or dt == _lib.F32) else tdt
         gs = [None if g is None else g.to(want) for g in dfeats]
         layouts = [is_channels_last_view(g) for g in gs if g is not None]
@@ -223,6 +252,7 @@ class SwinCore(FlatParamModule):
             if hook is not None:
                 hook(flat_grad, s_lo, s_hi)
         self._last_flat_grad = flat_grad
+        self._return_workspace(cfg.batch, ws)
         return flat_grad
 
     def _backward_chunks(self, blocks_per_chunk: int = 0):

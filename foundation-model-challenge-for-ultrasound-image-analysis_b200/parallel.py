@@ -184,6 +184,49 @@ class DataParallelTrainer:
         return total.detach()
 
 
+class DevicePrefetcher:
+    """Host -> device copies of the NEXT batch on a side stream while the current step computes.
+
+    The reference moves every batch with a blocking ``images.to(device)`` right before the forward
+    (``code/train.py:305``); with pinned host memory the copy of batch i+1 can run under step i instead::
+
+        pf = DevicePrefetcher(device)
+        pf.issue(x0, y0)
+        for i in range(n):
+            x, y = pf.take()                 # current stream waits for the copy (no host sync)
+            if i + 1 < n: pf.issue(x_next, y_next)
+            trainer.step(x, y, task_id)
+    """
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._slot = None
+
+    def issue(self, *host_tensors):
+        if self._slot is not None:
+            raise RuntimeError("DevicePrefetcher: the previous batch was not taken")
+        with torch.cuda.stream(self.stream):
+            dev = [t.to(self.device, non_blocking=True) for t in host_tensors]
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._slot = (dev, ev)
+
+    def pending(self) -> bool:
+        return self._slot is not None
+
+    def take(self):
+        if self._slot is None:
+            raise RuntimeError("DevicePrefetcher: nothing was issued")
+        dev, ev = self._slot
+        self._slot = None
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for t in dev:
+            t.record_stream(cur)             # allocated on the copy stream, consumed on the compute stream
+        return dev
+
+
 def synthetic_batch(task_cfg, batch, image_size, generator=None, device="cpu", dtype=torch.float32):
     """Synthetic ultrasound-shaped batch for one task: N(0,1) images and labels by task type."""
     name, n = task_cfg["task_name"], task_cfg["num_classes"]

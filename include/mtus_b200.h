@@ -237,6 +237,9 @@ int mtus_swin_forward(const mtus_swin_config* cfg, const void* x, int x_is_f32, 
                       const void* params_lp, const float* droppath, void* workspace, void* const* feats,
                       int feats_layout, int feats_f32, void* stream);
 /* dfeats[4]: NCHW grads (NULL = zero); grads: flat fp32, ACCUMULATED into (caller zeroes).
+ * droppath: non-NULL iff forward ran with drop-path (the scales themselves are re-read from the workspace, where
+ * forward left a copy).  The call that starts at the top (stage_hi = 4 / block_hi = all blocks) converts dfeats
+ * into workspace slots; later partial calls of the same backward reuse them (pass the same dfeats).
  * stage_hi/stage_lo: run backward for stages stage_hi-1 down to stage_lo (4,0 = everything), so the
  * caller can interleave gradient all-reduce of finished stages with the remaining backward. */
 int mtus_swin_backward(const mtus_swin_config* cfg, const float* params, const void* params_lp,
@@ -249,6 +252,12 @@ int mtus_swin_backward(const mtus_swin_config* cfg, const float* params, const v
 int mtus_swin_backward_blocks(const mtus_swin_config* cfg, const float* params, const void* params_lp,
                               const float* droppath, void* workspace, const void* const* dfeats, int dfeats_layout,
                               int dfeats_f32, float* grads, int block_hi, int block_lo, void* stream);
+
+/* The schedule behind mtus_swin_forward / mtus_swin_backward* (everything after the input-dependent prologue) is
+ * captured into a CUDA graph per distinct (config, parameter / workspace / gradient addresses, range) and replayed
+ * on later calls; keep those buffers alive and at fixed addresses across steps to benefit (MTUS_GRAPHS=0 disables).
+ * Counters of the cache since process start. */
+void mtus_graph_cache_stats(int64_t* hits, int64_t* misses, int64_t* entries);
 
 typedef struct mtus_fpn_config {
   int batch;

@@ -53,6 +53,11 @@ def main():
         total += ms * weights[name.lower()]
         print(f"{name:15s} {tid:28s} device {ms:7.3f} ms/step   host (queue full) {(t1 - t0) * 1e3 / n:7.3f}   host (single step, empty queue) {min(hs):7.3f} ms/step")
     print(f"27-task mean: {total / 27:.3f} ms/step -> {B / (total / 27) * 1e3:.1f} img/s")
+    import ctypes as C
+    from mtus_b200 import _lib
+    h, ms_, n_ = C.c_int64(), C.c_int64(), C.c_int64()
+    _lib.lib().mtus_graph_cache_stats(C.byref(h), C.byref(ms_), C.byref(n_))
+    print(f"executor graph cache: {h.value} hits, {ms_.value} misses, {n_.value} entries")
 
 
 if __name__ == "__main__":
