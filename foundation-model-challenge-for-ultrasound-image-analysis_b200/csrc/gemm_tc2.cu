@@ -54,7 +54,8 @@ struct T2Smem {
   static constexpr int TMEM_COLS = (2 * BN > 256) ? 512 : ((2 * BN > 128) ? 256 : 128);   // two accumulators, power of two
   static constexpr int EPI_OFF = STAGES * STAGE;
   static constexpr int BAR_OFF = EPI_OFF + 2 * EPI_BUFS * SUB_BYTES;   // X[EPI_BUFS], D[EPI_BUFS]
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+  static constexpr int BIAS_OFF = BAR_OFF + 256;                       // bias of the current tile's BN columns (fp32)
+  static constexpr int TOTAL = BIAS_OFF + 1024 + 1024;
   static constexpr int SUB_COLS = OUT_F32 ? 32 : 64;
   static constexpr int NSUB = BN / SUB_COLS;
 };
@@ -79,6 +80,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                  bar_tempty = bar_tfull + 16, bar_xfull = bar_tempty + 16, bar_xempty = bar_xfull + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 8);
   const uint32_t smem_x = smem_base + S::EPI_OFF, smem_d = smem_x + S::EPI_BUFS * S::SUB_BYTES;
+  float* s_bias = reinterpret_cast<float*>(smem + S::BIAS_OFF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool x_in = (ep.x_mode == 1 || ep.x_mode == 2);
@@ -231,6 +233,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int t = cl_id; t < n_work; t += n_cl, ++tc) {
       T2_DECODE(t)
       const uint32_t ab = tc & 1;
+      // bias of this tile's columns: fetched before waiting for the accumulator, parked in shared memory at the first
+      // sub-tile barrier, then read as broadcast LDS (a per-sub-tile __ldg chain stalled every sub-tile on L1 / L2)
+      float bias_pref = 0.f;
+      if (ep.bias) { const int nb = n_blk * BN + etid; if (etid < BN && nb < N) bias_pref = __ldg(ep.bias + nb); }
       mbar_wait(bar_tfull + 8 * ab, (tc >> 1) & 1);
       tc_fence_after();
       float rs = 1.0f;
@@ -246,6 +252,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int n0 = n_sub + hf * CH;
         // the TMA store that read D[b] / X[b] two sub-tiles ago must have finished reading shared memory
         if (etid == 0) bulk_wait_read<S::EPI_BUFS - 1>();
+        if (sub == 0 && ep.bias && etid < BN) s_bias[etid] = bias_pref;
         named_bar_sync(T2_EPI_BAR, T2_EPI_THREADS);
         if (x_in) mbar_wait(bar_xfull + 8 * b, (e / S::EPI_BUFS) & 1);
         uint32_t v[CH];
@@ -270,15 +277,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[j]);
         if (ep.bias) {
-          if (n0 + CH <= N) {
+          const float4* sb4 = reinterpret_cast<const float4*>(s_bias + sub * S::SUB_COLS + hf * CH);   // zero beyond N
 #pragma unroll
-            for (int j = 0; j < CH / 4; ++j) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j);
-              f[4 * j] += bv.x; f[4 * j + 1] += bv.y; f[4 * j + 2] += bv.z; f[4 * j + 3] += bv.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < CH; ++j) if (n0 + j < N) f[j] += __ldg(ep.bias + n0 + j);
+          for (int j = 0; j < CH / 4; ++j) {
+            const float4 bv = sb4[j];
+            f[4 * j] += bv.x; f[4 * j + 1] += bv.y; f[4 * j + 2] += bv.z; f[4 * j + 3] += bv.w;
           }
         }
         if (OUT_F32) {

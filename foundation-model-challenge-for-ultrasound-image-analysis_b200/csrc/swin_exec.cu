@@ -181,7 +181,52 @@ size_t block_xin(const Plan& p, int i, int j) {
   return p.sa[i].blk[j - 1].xout;
 }
 
-#define RUN(expr) do { int rc__ = (expr); if (rc__ != MTUS_OK) { fprintf(stderr, "mtus swin_exec: %s -> %d (%s) at %s:%d\n", #expr, rc__, mtus_status_string(rc__), __FILE__, __LINE__); return rc__; } } while (0)
+// MTUS_TIME_KERNELS=1: in-situ timing of every executor step (warm caches, real operands): CUDA events around each
+// call on its own stream, printed per call site when the executor returns (graphs off; the events serialise PDL).
+struct StepTimer {
+  struct Rec { const char* what; int line; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  static bool enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MTUS_TIME_KERNELS"); v = (e && atoi(e) != 0) ? 1 : 0; }
+    return v == 1;
+  }
+  void begin(const char* what, int line, cudaStream_t st) {
+    Rec r{what, line, nullptr, nullptr};
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    recs.push_back(r);
+  }
+  void end(cudaStream_t st) { cudaEventRecord(recs.back().b, st); }
+  void report(const char* title) {
+    if (recs.empty()) return;
+    cudaDeviceSynchronize();
+    struct Agg { const char* what; int line; int n; float ms; };
+    std::vector<Agg> agg;
+    float total = 0.f;
+    for (Rec& r : recs) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, r.a, r.b);
+      cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+      total += ms;
+      bool found = false;
+      for (Agg& g : agg) if (g.line == r.line) { g.n++; g.ms += ms; found = true; break; }
+      if (!found) agg.push_back(Agg{r.what, r.line, 1, ms});
+    }
+    fprintf(stderr, "== %s: %zu timed calls, %.3f ms summed\n", title, recs.size(), total);
+    for (Agg& g : agg) fprintf(stderr, "  line %4d  n=%3d  total %8.1f us  avg %7.1f us  %.60s\n", g.line, g.n, g.ms * 1e3f, g.ms * 1e3f / g.n, g.what);
+    recs.clear();
+  }
+};
+StepTimer g_timer;
+
+#define RUN_STREAM(expr, strm) do { \
+    const bool t__ = StepTimer::enabled(); \
+    if (t__) g_timer.begin(#expr, __LINE__, (cudaStream_t)(strm)); \
+    int rc__ = (expr); \
+    if (t__) g_timer.end((cudaStream_t)(strm)); \
+    if (rc__ != MTUS_OK) { fprintf(stderr, "mtus swin_exec: %s -> %d (%s) at %s:%d\n", #expr, rc__, mtus_status_string(rc__), __FILE__, __LINE__); return rc__; } } while (0)
+#define RUN(expr) RUN_STREAM(expr, stream)
 
 
 // Weight-gradient GEMMs have no consumer inside the backward chain, so they run on a side stream and fill the SMs the
@@ -232,7 +277,7 @@ constexpr size_t kMaxGraphs = 48;
 
 bool graphs_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MTUS_GRAPHS"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  if (v < 0) { const char* e = getenv("MTUS_GRAPHS"); v = (e && atoi(e) == 0) ? 0 : 1; if (StepTimer::enabled()) v = 0; }
   return v == 1;
 }
 
@@ -377,9 +422,11 @@ extern "C" int mtus_swin_forward(const mtus_swin_config* cfg, const void* x, int
   KeyBuilder kb;
   kb.add((int)1).add(dev).add(*cfg).add(params).add(params_lp).add((int)(dp != nullptr)).add(workspace)
     .add(feats[0]).add(feats[1]).add(feats[2]).add(feats[3]).add(feats_layout).add(feats_f32);
-  return run_cached(kb.k, st, [&](void* s_) {
+  const int rc = run_cached(kb.k, st, [&](void* s_) {
     return swin_forward_impl(cfg, x, x_is_f32, params, params_lp, dp, workspace, feats, feats_layout, feats_f32, s_);
   });
+  if (StepTimer::enabled()) g_timer.report("mtus_swin_forward");
+  return rc;
 }
 
 static int swin_forward_impl(const mtus_swin_config* cfg, const void* x, int x_is_f32, const float* params,
@@ -501,9 +548,11 @@ extern "C" int mtus_swin_backward_blocks(const mtus_swin_config* cfg, const floa
   KeyBuilder kb;
   kb.add((int)2).add(dev).add(*cfg).add(params).add(params_lp).add((int)(dp != nullptr)).add(workspace).add(mask).add(grads)
     .add(block_hi).add(block_lo);
-  return run_cached(kb.k, (cudaStream_t)stream, [&](void* s_) {
+  const int rc = run_cached(kb.k, (cudaStream_t)stream, [&](void* s_) {
     return swin_backward_impl(cfg, params, params_lp, dp, workspace, dfeats, dfeats_layout, dfeats_f32, grads, block_hi, block_lo, s_);
   });
+  if (StepTimer::enabled()) g_timer.report("mtus_swin_backward");
+  return rc;
 }
 
 extern "C" void mtus_graph_cache_stats(int64_t* hits, int64_t* misses, int64_t* entries) {
@@ -573,8 +622,8 @@ static int swin_backward_impl(const mtus_swin_config* cfg, const float* params, 
       // ---- MLP branch (Gb = dp2 * G; fc2.bias gradient already accumulated by the producer of Gb) ----
       RUN(mtus_linear_dgrad(Gb, W(bp.fc2w), dH, A(ba.h), nullptr, 1, GR(bp.fc1b), M, Cc, 4 * Cc, dt, be, stream));
       if (ss) { CU(cudaEventRecord(ss->e1, st)); CU(cudaStreamWaitEvent(ss->s, ss->e1, 0)); }
-      RUN(mtus_linear_wgrad(Gb, A(ba.a), GR(bp.fc2w), nullptr, M, Cc, 4 * Cc, dt, be, wst));
-      RUN(mtus_linear_wgrad(dH, A(ba.ln2), GR(bp.fc1w), nullptr, M, 4 * Cc, Cc, dt, be, wst));
+      RUN_STREAM(mtus_linear_wgrad(Gb, A(ba.a), GR(bp.fc2w), nullptr, M, Cc, 4 * Cc, dt, be, wst), wst);
+      RUN_STREAM(mtus_linear_wgrad(dH, A(ba.ln2), GR(bp.fc1w), nullptr, M, 4 * Cc, Cc, dt, be, wst), wst);
       if (ss) CU(cudaEventRecord(ss->d1, ss->s));
       RUN(mtus_linear_dgrad(dH, W(bp.fc1w), dLN, nullptr, nullptr, 1, nullptr, M, 4 * Cc, Cc, dt, be, stream));
       if (ss && d2_pending) { CU(cudaStreamWaitEvent(st, ss->d2, 0)); d2_pending = false; }   // Gb2 / dQKV free again
@@ -585,8 +634,8 @@ static int swin_backward_impl(const mtus_swin_config* cfg, const float* params, 
       RUN(mtus_window_attn_bwd(dLN, A(ba.qkv), A(ba.attn), FA(ba.lse), F(bp.table), F(bp.qkvb), dQKV, GR(bp.table), GR(bp.qkvb), GR(bp.qkvb),
                                p.B, res, res, Cc, p.heads[i], p.win[i], p.win[i], shift, shift, dt, stream));
       if (ss) { CU(cudaEventRecord(ss->e2, st)); CU(cudaStreamWaitEvent(ss->s, ss->e2, 0)); }
-      RUN(mtus_linear_wgrad(Gb2, A(ba.attn), GR(bp.projw), nullptr, M, Cc, Cc, dt, be, wst));
-      RUN(mtus_linear_wgrad(dQKV, A(ba.ln1), GR(bp.qkvw), nullptr, M, 3 * Cc, Cc, dt, be, wst));
+      RUN_STREAM(mtus_linear_wgrad(Gb2, A(ba.attn), GR(bp.projw), nullptr, M, Cc, Cc, dt, be, wst), wst);
+      RUN_STREAM(mtus_linear_wgrad(dQKV, A(ba.ln1), GR(bp.qkvw), nullptr, M, 3 * Cc, Cc, dt, be, wst), wst);
       if (ss) { CU(cudaEventRecord(ss->d2, ss->s)); d2_pending = true; }
       RUN(mtus_linear_dgrad(dQKV, W(bp.qkvw), dLN, nullptr, nullptr, 1, nullptr, M, 3 * Cc, Cc, dt, be, stream));
       // LN1 backward closes the block: the new Gb feeds the previous block's fc2 (its drop-path scale, its bias
