@@ -54,8 +54,8 @@ struct T2Smem {
   static constexpr int TMEM_COLS = (2 * BN > 256) ? 512 : ((2 * BN > 128) ? 256 : 128);   // two accumulators, power of two
   static constexpr int EPI_OFF = STAGES * STAGE;
   static constexpr int BAR_OFF = EPI_OFF + 2 * EPI_BUFS * SUB_BYTES;   // X[EPI_BUFS], D[EPI_BUFS]
-  static constexpr int BIAS_OFF = BAR_OFF + 256;                       // bias of the current tile's BN columns (fp32)
-  static constexpr int TOTAL = BIAS_OFF + 1024 + 1024;
+  static constexpr int BIAS_OFF = BAR_OFF + 256;                       // bias of this / the next tile's BN columns (fp32) [2][BN]
+  static constexpr int TOTAL = BIAS_OFF + 2 * BN * 4 + 1024;
   static constexpr int SUB_COLS = OUT_F32 ? 32 : 64;
   static constexpr int NSUB = BN / SUB_COLS;
 };
@@ -230,13 +230,25 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int ew = warp - 4, q = ew & 3, hf = ew >> 2, row = q * 32 + lane, etid = threadIdx.x - 128;
     constexpr int CH = OUT_F32 ? 16 : 32;     // accumulator columns per thread per sub-tile (64 bytes of output)
     uint32_t tc = 0, e = 0;
+    // One named barrier per sub-tile: thread 0 waits until every TMA store issued so far has finished READING shared
+    // memory right before the barrier, so after it the other buffer (last stored one sub-tile ago) may be overwritten
+    // while the buffer just filled is handed to the TMA store.  The bias of a tile's BN columns is fetched one tile ahead
+    // and parked in shared memory ([2][BN], published by the last barrier of the previous tile), then read as broadcast LDS.
+    auto tile_bias = [&](int u) -> float {
+      if (!ep.bias || u >= n_work || etid >= BN) return 0.f;
+      const int r2 = u % mgn_tiles, nb2 = r2 - (r2 / n_tiles) * n_tiles;
+      const int nb = nb2 * BN + etid;
+      return nb < N ? __ldg(ep.bias + nb) : 0.f;
+    };
+    if (ep.bias) {
+      if (etid < BN) s_bias[etid] = tile_bias(cl_id);
+      named_bar_sync(T2_EPI_BAR, T2_EPI_THREADS);
+    }
     for (int t = cl_id; t < n_work; t += n_cl, ++tc) {
       T2_DECODE(t)
       const uint32_t ab = tc & 1;
-      // bias of this tile's columns: fetched before waiting for the accumulator, parked in shared memory at the first
-      // sub-tile barrier, then read as broadcast LDS (a per-sub-tile __ldg chain stalled every sub-tile on L1 / L2)
-      float bias_pref = 0.f;
-      if (ep.bias) { const int nb = n_blk * BN + etid; if (etid < BN && nb < N) bias_pref = __ldg(ep.bias + nb); }
+      const float* sb_cur = s_bias + (tc & 1) * BN;
+      const float bias_next = tile_bias(t + n_cl);
       mbar_wait(bar_tfull + 8 * ab, (tc >> 1) & 1);
       tc_fence_after();
       float rs = 1.0f;
@@ -250,10 +262,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t sx = smem_x + b * S::SUB_BYTES + row * 128, sd = smem_d + b * S::SUB_BYTES + row * 128;
         const int n_sub = n_blk * BN + sub * S::SUB_COLS;
         const int n0 = n_sub + hf * CH;
-        // the TMA store that read D[b] / X[b] two sub-tiles ago must have finished reading shared memory
-        if (etid == 0) bulk_wait_read<S::EPI_BUFS - 1>();
-        if (sub == 0 && ep.bias && etid < BN) s_bias[etid] = bias_pref;
-        named_bar_sync(T2_EPI_BAR, T2_EPI_THREADS);
         if (x_in) mbar_wait(bar_xfull + 8 * b, (e / S::EPI_BUFS) & 1);
         uint32_t v[CH];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * BN + sub * S::SUB_COLS + hf * CH;
@@ -277,7 +285,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[j]);
         if (ep.bias) {
-          const float4* sb4 = reinterpret_cast<const float4*>(s_bias + sub * S::SUB_COLS + hf * CH);   // zero beyond N
+          const float4* sb4 = reinterpret_cast<const float4*>(sb_cur + sub * S::SUB_COLS + hf * CH);   // zero beyond N
 #pragma unroll
           for (int j = 0; j < CH / 4; ++j) {
             const float4 bv = sb4[j];
@@ -354,7 +362,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
         if (x_in) { __syncwarp(); if (lane == 0) mbar_arrive(bar_xempty + 8 * b); }
+        if (sub == S::NSUB - 1 && ep.bias && etid < BN) s_bias[((tc & 1) ^ 1) * BN + etid] = bias_next;
         fence_proxy_async();
+        if (etid == 0) bulk_wait_read<0>();
         named_bar_sync(T2_EPI_BAR, T2_EPI_THREADS);
         if (etid == 0) {
           if (A_MODE == 2) {
