@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(128) lnv2_fwd_kernel(const TX* __restrict__ x,
 template <typename T, typename TDY, typename TX, int LPR, int NV, int U, int MODE>
 __global__ void __launch_bounds__(128) lnv2_bwd_kernel(LnxBwdArgs a, MergeGeom g) {
   constexpr int RPW = 32 / LPR;
-  extern __shared__ float acc_smem[];                         // [3][4 warps][C] partial dgamma / dbeta / colsum
+  extern __shared__ __align__(16) float acc_smem[];           // [4 warps][C] partials of one of dgamma / dbeta / colsum at a time
   const TDY* __restrict__ dy = reinterpret_cast<const TDY*>(a.dy);
   const TX* __restrict__ x = reinterpret_cast<const TX*>(a.x);
   T* __restrict__ dx_lp = reinterpret_cast<T*>(a.dx_lp);
@@ -683,23 +683,31 @@ __global__ void __launch_bounds__(128) lnv2_bwd_kernel(LnxBwdArgs a, MergeGeom g
         acs[i][k] += __shfl_xor_sync(0xffffffffu, acs[i][k], o);
       }
     }
-  float* sg = acc_smem; float* sb = acc_smem + 4 * C; float* sc = acc_smem + 8 * C;
-  if (grp == 0) {
+  // one quantity at a time through a [4 warps][C] buffer (16 C bytes instead of 48 C): with 8 KB per CTA at C = 512 three
+  // of these CTAs still fit next to a resident persistent-GEMM CTA (200 KB) when the weight-gradient stream overlaps
+  const int Cc = (MODE == 0) ? C : g.C;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int col = (i * LPR + sub) * 8;
-      if (col < C) {
+  for (int qn = 0; qn < 3; ++qn) {
+    if (qn == 2 && !want_cs) break;
+    if (qn > 0) __syncthreads();
+    if (grp == 0) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { sg[warp * C + col + k] = adg[i][k]; sb[warp * C + col + k] = adb[i][k]; sc[warp * C + col + k] = acs[i][k]; }
+      for (int i = 0; i < NV; ++i) {
+        const int col = (i * LPR + sub) * 8;
+        if (col < C) {
+          float* dst = acc_smem + warp * C + col;
+          const float* src = qn == 0 ? adg[i] : (qn == 1 ? adb[i] : acs[i]);
+          *reinterpret_cast<float4*>(dst) = make_float4(src[0], src[1], src[2], src[3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(src[4], src[5], src[6], src[7]);
+        }
       }
     }
-  }
-  __syncthreads();
-  const int Cc = (MODE == 0) ? C : g.C;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    atomicAdd(a.dgamma + c, sg[c] + sg[C + c] + sg[2 * C + c] + sg[3 * C + c]);
-    atomicAdd(a.dbeta + c, sb[c] + sb[C + c] + sb[2 * C + c] + sb[3 * C + c]);
-    if (want_cs) atomicAdd(a.lp_colsum + (c % Cc), sc[c] + sc[C + c] + sc[2 * C + c] + sc[3 * C + c]);
+    __syncthreads();
+    float* out = qn == 0 ? a.dgamma : (qn == 1 ? a.dbeta : a.lp_colsum);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float v = acc_smem[c] + acc_smem[C + c] + acc_smem[2 * C + c] + acc_smem[3 * C + c];
+      atomicAdd(out + (qn == 2 ? (c % Cc) : c), v);
+    }
   }
 }
 
@@ -730,7 +738,7 @@ static int lnv2_fwd_launch(const void* x, const float* gamma, const float* beta,
 template <typename T, typename TDY, typename TX, int MODE>
 static int lnv2_bwd_launch(const LnxBwdArgs& a, MergeGeom g, cudaStream_t st) {
   const int C = a.C, nvec = C / 8;
-  const size_t sm = (size_t)12 * C * sizeof(float);
+  const size_t sm = (size_t)4 * C * sizeof(float);
 #define V2B(LPR_, NV_, U_, BPS_)                                                                             \
   {                                                                                                          \
     const int rpi = (32 / LPR_) * U_ * 4;                                                                    \
