@@ -110,6 +110,29 @@ class FlatParamModule(nn.Module):
         self._entries()
         return self._ordered_cache
 
+    # ---- buffers that stay at fixed addresses across steps (the executors' CUDA-graph cache keys on them) ----
+    def _take_workspace(self, batch: int, nbytes: int, device):
+        pool = self.__dict__.setdefault("_ws_pool", {})
+        free = pool.setdefault((batch, nbytes, str(device)), [])
+        return free.pop() if free else torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+    def _return_workspace(self, batch: int, ws):
+        free = self.__dict__.setdefault("_ws_pool", {}).setdefault((batch, ws.numel(), str(ws.device)), [])
+        if len(free) < 2:
+            free.append(ws)
+
+    def _grad_block(self, device):
+        """Zeroed flat gradient block.  The persistent block is reused only when no parameter still holds a gradient
+        (i.e. after zero_grad(set_to_none=True)): with gradient accumulation the previous views must stay intact."""
+        buf = getattr(self, "_grad_buf", None)
+        ps = self.ordered_params()
+        if buf is not None and buf.device == device and all(p.grad is None for p in ps):
+            return buf.zero_()
+        g = torch.zeros(self._n_flat, dtype=torch.float32, device=device)
+        if buf is None or buf.device != device:
+            self._grad_buf = g
+        return g
+
     def grad_views(self, flat_grad: torch.Tensor, needs):
         """Per-parameter views of the flat gradient block (one split call + a reshape for the >1-D tensors)."""
         entries = self._entries()

@@ -5,6 +5,7 @@
 // Replaces segmentation_models_pytorch.decoders.fpn.decoder.FPNDecoder.forward as called from
 // /root/reference/code/models/multitask_model.py:211,221 (constructed at decoders.py:42-49).
 #include "common.cuh"
+#include "graph_cache.cuh"
 #include <stdio.h>
 #include <string.h>
 #include <string>
@@ -33,6 +34,7 @@ struct Plan {
   size_t cin_nhwc[4];     // NHWC copies of the inputs when the caller passes NCHW
   size_t pl[4];           // p2..p5
   size_t gM[4], s1, s2, gP[4], tmpL, dwp, gnws;   // backward scratch
+  size_t cs_slot;         // Dropout2d channel scales copied by forward (the caller's tensor is new every step)
   size_t ws_bytes;
   int out_channels;
 };
@@ -91,6 +93,7 @@ bool build_plan(const mtus_fpn_config* c, Plan& p) {
   Arena a;
   const size_t es = p.es;
   p.lp = p.dtype == MTUS_BF16 ? a.take((size_t)p.n_params * 2) : 0;
+  p.cs_slot = a.take((size_t)(p.B > 0 ? p.B : 1) * (p.cat ? 4 * p.S : p.S) * 4);
   for (int k = 0; k < 4; ++k) p.cin_nhwc[k] = a.take((size_t)p.B * p.size[k] * p.size[k] * p.cin[k] * es);
   for (int k = 0; k < 4; ++k) p.pl[k] = a.take((size_t)p.B * p.size[k] * p.size[k] * p.P * es);
   for (int i = 0; i < 4; ++i)
@@ -142,6 +145,12 @@ extern "C" int mtus_fpn_param_info(const mtus_fpn_config* cfg, int idx, char* na
   return 0;
 }
 
+// Like the encoder executor, each direction is an eager part that touches the tensors whose addresses change every
+// step (Dropout2d scales, the output, the incoming gradient) plus a body that only touches the features, the parameter
+// block and the workspace; the body is captured into a CUDA graph keyed on those addresses and replayed (graph_cache.cuh).
+static int fpn_forward_body(const mtus_fpn_config* cfg, const void* const* feats, int feats_layout, int feats_f32,
+                            const float* params, void* workspace, const void** merged, void* stream);
+
 extern "C" int mtus_fpn_forward(const mtus_fpn_config* cfg, const void* const* feats, int feats_layout, int feats_f32,
                                 const float* params, const float* chanscale, void* workspace, void* out, int out_f32,
                                 void* stream) {
@@ -149,6 +158,34 @@ extern "C" int mtus_fpn_forward(const mtus_fpn_config* cfg, const void* const* f
   if (!build_plan(cfg, p)) return MTUS_ERR_BAD_ARG;
   MTUS_CHECK_ARG(feats && params && workspace && out);
   if (p.B == 0) return MTUS_OK;
+  for (int k = 0; k < 4; ++k) MTUS_CHECK_ARG(feats[k]);
+  char* wsb = reinterpret_cast<char*>(workspace);
+  const float* cs = nullptr;
+  if (chanscale) {
+    cudaError_t e = cudaMemcpyAsync(wsb + p.cs_slot, chanscale, (size_t)p.B * p.out_channels * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    cs = reinterpret_cast<const float*>(wsb + p.cs_slot);
+  }
+  const void* merged[4] = {nullptr, nullptr, nullptr, nullptr};
+  int dev = 0; cudaGetDevice(&dev);
+  mtus_graphs::KeyBuilder kb;
+  kb.add((int)3).add(dev).add(*cfg).add(feats[0]).add(feats[1]).add(feats[2]).add(feats[3]).add(feats_layout).add(feats_f32)
+    .add(params).add(workspace);
+  int rc = mtus_graphs::run_cached(kb.k, (cudaStream_t)stream, [&](void* s_) {
+    return fpn_forward_body(cfg, feats, feats_layout, feats_f32, params, workspace, merged, s_);
+  });
+  if (rc != MTUS_OK) return rc;
+  if (!merged[0]) {   // graph replay: the body did not run on the host; the tower outputs are fixed workspace slots
+    for (int i = 0; i < 4; ++i) merged[i] = wsb + p.tower[i].back().v;
+  }
+  RUN(mtus_fpn_merge_fwd(merged, 4, p.cat, cs, out, p.B, p.size[0] * p.size[0], p.S, p.dtype, out_f32 & 1, (out_f32 >> 1) & 1, stream));
+  return MTUS_OK;
+}
+
+static int fpn_forward_body(const mtus_fpn_config* cfg, const void* const* feats, int feats_layout, int feats_f32,
+                            const float* params, void* workspace, const void** merged_out, void* stream) {
+  Plan p;
+  if (!build_plan(cfg, p)) return MTUS_ERR_BAD_ARG;
   char* ws = reinterpret_cast<char*>(workspace);
   const int dt = p.dtype, be = p.backend;
   auto A = [&](size_t off) -> void* { return ws + off; };
@@ -194,9 +231,13 @@ extern "C" int mtus_fpn_forward(const mtus_fpn_config* cfg, const void* const* f
     }
     merged[i] = x;
   }
-  RUN(mtus_fpn_merge_fwd(merged, 4, p.cat, chanscale, out, p.B, p.size[0] * p.size[0], p.S, dt, out_f32 & 1, (out_f32 >> 1) & 1, stream));
+  for (int i = 0; i < 4; ++i) merged_out[i] = merged[i];
   return MTUS_OK;
 }
+
+static int fpn_backward_body(const mtus_fpn_config* cfg, const void* const* feats, int feats_layout, int feats_f32,
+                             const float* params, void* workspace, void* const* dfeats, int dfeats_layout, int dfeats_f32,
+                             float* grads, void* stream);
 
 extern "C" int mtus_fpn_backward(const mtus_fpn_config* cfg, const void* const* feats, int feats_layout, int feats_f32,
                                  const float* params, const float* chanscale, void* workspace, const void* dout,
@@ -204,8 +245,32 @@ extern "C" int mtus_fpn_backward(const mtus_fpn_config* cfg, const void* const* 
                                  void* stream) {
   Plan p;
   if (!build_plan(cfg, p)) return MTUS_ERR_BAD_ARG;
-  MTUS_CHECK_ARG(params && workspace && dout && dfeats && grads && p.training);
+  MTUS_CHECK_ARG(params && workspace && dout && dfeats && grads && p.training && feats);
   if (p.B == 0) return MTUS_OK;
+  for (int k = 0; k < 4; ++k) MTUS_CHECK_ARG(dfeats[k] && (feats_layout == 0 || feats[k]));
+  char* wsb = reinterpret_cast<char*>(workspace);
+  // eager: merge backward reads the incoming gradient (a fresh autograd tensor); the Dropout2d scales are the copy
+  // forward left in the workspace (chanscale only says whether dropout was active)
+  {
+    void* dm[4];
+    for (int i = 0; i < 4; ++i) dm[i] = wsb + p.gM[i];
+    const float* cs = chanscale ? reinterpret_cast<const float*>(wsb + p.cs_slot) : nullptr;
+    RUN(mtus_fpn_merge_bwd(dout, 4, p.cat, cs, dm, p.B, p.size[0] * p.size[0], p.S, p.dtype, dout_f32 & 1, (dout_f32 >> 1) & 1, stream));
+  }
+  int dev = 0; cudaGetDevice(&dev);
+  mtus_graphs::KeyBuilder kb;
+  kb.add((int)4).add(dev).add(*cfg).add(feats[0]).add(feats[1]).add(feats[2]).add(feats[3]).add(feats_layout).add(feats_f32)
+    .add(params).add(workspace).add(dfeats[0]).add(dfeats[1]).add(dfeats[2]).add(dfeats[3]).add(dfeats_layout).add(dfeats_f32).add(grads);
+  return mtus_graphs::run_cached(kb.k, (cudaStream_t)stream, [&](void* s_) {
+    return fpn_backward_body(cfg, feats, feats_layout, feats_f32, params, workspace, dfeats, dfeats_layout, dfeats_f32, grads, s_);
+  });
+}
+
+static int fpn_backward_body(const mtus_fpn_config* cfg, const void* const* feats, int feats_layout, int feats_f32,
+                             const float* params, void* workspace, void* const* dfeats, int dfeats_layout, int dfeats_f32,
+                             float* grads, void* stream) {
+  Plan p;
+  if (!build_plan(cfg, p)) return MTUS_ERR_BAD_ARG;
   (void)feats_f32;
   char* ws = reinterpret_cast<char*>(workspace);
   const int dt = p.dtype, be = p.backend;
@@ -217,11 +282,9 @@ extern "C" int mtus_fpn_backward(const mtus_fpn_config* cfg, const void* const* 
   auto W = [&](int64_t off) -> const void* {
     return dt == MTUS_BF16 ? (const void*)(reinterpret_cast<const bf16*>(ws + p.lp) + off) : (const void*)(params + off);
   };
-  const int HW0 = p.size[0] * p.size[0];
-  // merge backward: dout (NCHW) x Dropout2d scale -> four NHWC tower-output gradients
+  // (merge backward ran eagerly in the caller: the four NHWC tower-output gradients are in gM[i])
   void* dm[4];
   for (int i = 0; i < 4; ++i) dm[i] = A(p.gM[i]);
-  RUN(mtus_fpn_merge_bwd(dout, 4, p.cat, chanscale, dm, p.B, HW0, p.S, dt, dout_f32 & 1, (dout_f32 >> 1) & 1, stream));
 
   // towers backward: leaves the gradient w.r.t. p_k in gP[k].  Buffer discipline per layer:
   //   g --bilinear'--> s1 (if upsampling) --GN/ReLU'--> dt (s2 | s1) --dgrad--> old g buffer (dead by then)

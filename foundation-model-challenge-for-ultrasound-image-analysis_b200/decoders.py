@@ -117,7 +117,9 @@ class FPNDecoder(FlatParamModule):
         nbytes = L.mtus_fpn_workspace_bytes(C.byref(cfg))
         if nbytes < 0:
             raise ValueError("mtus_b200: unsupported FPN geometry (each level must be exactly 2x the next)")
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=x0.device)
+        # training workspaces come from a pool and return to it when their backward has run (fixed addresses for
+        # the executor's graph cache); inference workspaces stay per call
+        ws = self._take_workspace(B, nbytes, x0.device) if training_plan else torch.empty(nbytes, dtype=torch.uint8, device=x0.device)
         scale = None
         if self.training and self.p_drop > 0.0:     # Dropout2d: whole channels, scaled by 1/(1-p)
             keep = 1.0 - self.p_drop
@@ -144,19 +146,28 @@ class FPNDecoder(FlatParamModule):
         dout_nhwc = is_channels_last_view(dout)
         if not dout_nhwc:
             dout = dout.contiguous()
-        flat_grad = torch.zeros(self._n_flat, dtype=torch.float32, device=flat.device)
+        flat_grad = self._grad_block(flat.device)
+        # feature gradients live in persistent buffers: the encoder's backward converts them into its own workspace
+        # right away (stream-ordered before the next step can overwrite them)
+        bufs = self.__dict__.setdefault("_dfeat_bufs", {})
         dfeats = []
-        for f in feats:
-            if nhwc:   # gradients come back channels-last, like the features
-                B, Cc, H, W = f.shape
-                dfeats.append(torch.empty(B, H, W, Cc, dtype=f.dtype, device=f.device).permute(0, 3, 1, 2))
-            else:
-                dfeats.append(torch.empty_like(f))
+        for i, f in enumerate(feats):
+            key = (i, tuple(f.shape), f.dtype, str(f.device), bool(nhwc))
+            g = bufs.get(key)
+            if g is None:
+                if nhwc:   # gradients come back channels-last, like the features
+                    B, Cc, H, W = f.shape
+                    g = torch.empty(B, H, W, Cc, dtype=f.dtype, device=f.device).permute(0, 3, 1, 2)
+                else:
+                    g = torch.empty_like(f)
+                bufs[key] = g
+            dfeats.append(g)
         _lib.check(L.mtus_fpn_backward(C.byref(cfg), _lib.ptr_array(feats), int(nhwc), int(f32_in), _lib.ptr(flat),
                                        _lib.ptr(scale), _lib.ptr(ws), _lib.ptr(dout), int(want_out == torch.float32 and dt != _lib.F32) | (2 if dout_nhwc else 0),
                                        _lib.ptr_array(dfeats), int(nhwc), int(f32_in), _lib.ptr(flat_grad), _lib.stream_ptr()),
                    "fpn_backward")
         self._last_flat_grad = flat_grad
+        self._return_workspace(cfg.batch, ws)
         return [g if n else None for g, n in zip(dfeats, feat_needs)], flat_grad
 
     def forward(self, features: List[torch.Tensor]) -> torch.Tensor:
