@@ -169,9 +169,9 @@ extern "C" int mtus_fpn_forward(const mtus_fpn_config* cfg, const void* const* f
   const void* merged[4] = {nullptr, nullptr, nullptr, nullptr};
   int dev = 0; cudaGetDevice(&dev);
   mtus_graphs::KeyBuilder kb;
-  kb.add((int)3).add(dev).add(*cfg).add(feats[0]).add(feats[1]).add(feats[2]).add(feats[3]).add(feats_layout).add(feats_f32)
-    .add(params).add(workspace);
-  int rc = mtus_graphs::run_cached(kb.k, (cudaStream_t)stream, [&](void* s_) {
+  kb.add((int)3).add(dev).add(*cfg).add(feats_layout).add(feats_f32).end_shape()
+    .add(feats[0]).add(feats[1]).add(feats[2]).add(feats[3]).add(params).add(workspace);
+  int rc = mtus_graphs::run_cached(kb, (cudaStream_t)stream, [&](void* s_) {
     return fpn_forward_body(cfg, feats, feats_layout, feats_f32, params, workspace, merged, s_);
   });
   if (rc != MTUS_OK) return rc;
@@ -259,9 +259,10 @@ extern "C" int mtus_fpn_backward(const mtus_fpn_config* cfg, const void* const* 
   }
   int dev = 0; cudaGetDevice(&dev);
   mtus_graphs::KeyBuilder kb;
-  kb.add((int)4).add(dev).add(*cfg).add(feats[0]).add(feats[1]).add(feats[2]).add(feats[3]).add(feats_layout).add(feats_f32)
-    .add(params).add(workspace).add(dfeats[0]).add(dfeats[1]).add(dfeats[2]).add(dfeats[3]).add(dfeats_layout).add(dfeats_f32).add(grads);
-  return mtus_graphs::run_cached(kb.k, (cudaStream_t)stream, [&](void* s_) {
+  kb.add((int)4).add(dev).add(*cfg).add(feats_layout).add(feats_f32).add(dfeats_layout).add(dfeats_f32).end_shape()
+    .add(feats[0]).add(feats[1]).add(feats[2]).add(feats[3]).add(params).add(workspace)
+    .add(dfeats[0]).add(dfeats[1]).add(dfeats[2]).add(dfeats[3]).add(grads);
+  return mtus_graphs::run_cached(kb, (cudaStream_t)stream, [&](void* s_) {
     return fpn_backward_body(cfg, feats, feats_layout, feats_f32, params, workspace, dfeats, dfeats_layout, dfeats_f32, grads, s_);
   });
 }

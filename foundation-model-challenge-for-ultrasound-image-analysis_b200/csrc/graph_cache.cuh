@@ -1,7 +1,9 @@
 // Executor-level CUDA graph cache shared by the encoder and decoder executors (swin_exec.cu, fpn_exec.cu).
 #pragma once
 #include "common.cuh"
+#include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <vector>
 
 namespace mtus_graphs {
@@ -25,8 +27,14 @@ inline bool graphs_enabled() {
   return v == 1;
 }
 
+// per configuration (the key minus its address fields): how often its graphs were reused / had to be rebuilt
+struct ShapeStat { std::vector<uint8_t> shape; int64_t hits, misses; };
+inline std::vector<ShapeStat> g_shapes;
+
 struct KeyBuilder {
   std::vector<uint8_t> k;
+  size_t shape_len = 0;                    // leading bytes that describe the configuration, not addresses
+  KeyBuilder& end_shape() { shape_len = k.size(); return *this; }
   template <typename T> KeyBuilder& add(const T& v) {
     const uint8_t* p = reinterpret_cast<const uint8_t*>(&v);
     k.insert(k.end(), p, p + sizeof(T));
@@ -45,14 +53,23 @@ inline cudaStream_t capture_stream() {
   return s[dev];
 }
 
+inline ShapeStat& shape_stat(const std::vector<uint8_t>& key, size_t shape_len) {
+  if (shape_len == 0 || shape_len > key.size()) shape_len = key.size();
+  for (ShapeStat& s : g_shapes)
+    if (s.shape.size() == shape_len && memcmp(s.shape.data(), key.data(), shape_len) == 0) return s;
+  if (g_shapes.size() >= 256) g_shapes.clear();
+  g_shapes.push_back(ShapeStat{std::vector<uint8_t>(key.begin(), key.begin() + shape_len), 0, 0});
+  return g_shapes.back();
+}
+
 template <typename F>
-int run_cached(const std::vector<uint8_t>& key, cudaStream_t st, F&& body) {
+int run_cached(const std::vector<uint8_t>& key, cudaStream_t st, F&& body, size_t shape_len = 0) {
   if (!graphs_enabled()) return body((void*)st);
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return body((void*)st); }
   for (GraphEntry& e : g_graphs) {
     if (e.key == key) {
-      e.stamp = ++g_stamp; ++g_graph_hits;
+      e.stamp = ++g_stamp; ++g_graph_hits; ++shape_stat(key, shape_len).hits;
       cudaError_t le = cudaGraphLaunch(e.exec, st);
       if (le != cudaSuccess) return (int)le;
       mtus_internal_count_launches((int)e.launches);
@@ -60,9 +77,13 @@ int run_cached(const std::vector<uint8_t>& key, cudaStream_t st, F&& body) {
     }
   }
   ++g_graph_misses;
-  // addresses that keep changing would mean one capture + instantiate per call: stop adding graphs when the cache
-  // clearly does not pay (lookups of the graphs already built continue)
-  if (g_graph_misses >= 64 && g_graph_hits < 4 * g_graph_misses) return body((void*)st);
+  // addresses that keep changing would mean one capture + instantiate per call: stop adding graphs for a configuration
+  // whose graphs clearly are not reused (lookups of the graphs already built continue)
+  {
+    ShapeStat& ss = shape_stat(key, shape_len);
+    ++ss.misses;
+    if (ss.misses > 8 && ss.hits < 4 * ss.misses) return body((void*)st);
+  }
   cudaStream_t cap = capture_stream();
   if (!cap || cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return body((void*)st); }
   const int64_t before = mtus_launch_count();
@@ -72,11 +93,20 @@ int run_cached(const std::vector<uint8_t>& key, cudaStream_t st, F&& body) {
   cudaError_t ce = cudaStreamEndCapture(cap, &graph);
   mtus_internal_count_launches(-(int)launches);             // nothing ran yet: counted when the graph (or the eager retry) runs
   if (rc != MTUS_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
-  if (ce != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return body((void*)st); }
+  if (ce != cudaSuccess || !graph) {
+    if (getenv("MTUS_GRAPH_DEBUG")) fprintf(stderr, "mtus graph cache: capture failed (%s), running the plain schedule\n", cudaGetErrorString(ce));
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return body((void*)st);
+  }
   cudaGraphExec_t exec = nullptr;
   ce = cudaGraphInstantiate(&exec, graph, 0);
   cudaGraphDestroy(graph);
-  if (ce != cudaSuccess || !exec) { cudaGetLastError(); return body((void*)st); }
+  if (ce != cudaSuccess || !exec) {
+    if (getenv("MTUS_GRAPH_DEBUG")) fprintf(stderr, "mtus graph cache: instantiate failed (%s), running the plain schedule\n", cudaGetErrorString(ce));
+    cudaGetLastError();
+    return body((void*)st);
+  }
   if (g_graphs.size() >= kMaxGraphs) {                      // evict the least recently used entry
     size_t lru = 0;
     for (size_t i = 1; i < g_graphs.size(); ++i) if (g_graphs[i].stamp < g_graphs[lru].stamp) lru = i;
@@ -90,5 +120,8 @@ int run_cached(const std::vector<uint8_t>& key, cudaStream_t st, F&& body) {
   return MTUS_OK;
 }
 
+
+template <typename F>
+int run_cached(const KeyBuilder& kb, cudaStream_t st, F&& body) { return run_cached(kb.k, st, body, kb.shape_len); }
 
 }  // namespace mtus_graphs

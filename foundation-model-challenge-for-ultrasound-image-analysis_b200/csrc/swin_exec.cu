@@ -339,13 +339,21 @@ extern "C" int mtus_swin_forward(const mtus_swin_config* cfg, const void* x, int
   }
   int dev = 0; cudaGetDevice(&dev);
   KeyBuilder kb;
-  kb.add((int)1).add(dev).add(*cfg).add(params).add(params_lp).add((int)(dp != nullptr)).add(workspace)
-    .add(feats[0]).add(feats[1]).add(feats[2]).add(feats[3]).add(feats_layout).add(feats_f32);
-  const int rc = run_cached(kb.k, st, [&](void* s_) {
+  int fmask = 0;
+  for (int i = 0; i < 4; ++i) if (feats[i]) fmask |= 1 << i;
+  kb.add((int)1).add(dev).add(*cfg).add((int)(dp != nullptr)).add(fmask).end_shape().add(params).add(params_lp).add(workspace);
+  const int rc = run_cached(kb, st, [&](void* s_) {
     return swin_forward_impl(cfg, x, x_is_f32, params, params_lp, dp, workspace, feats, feats_layout, feats_f32, s_);
   });
+  if (rc != MTUS_OK) return rc;
+  // eager epilogue: features materialised in the caller's own (fresh) tensors
+  for (int i = 0; i < 4; ++i) {
+    if (!feats[i]) continue;
+    MTUS_CHECK_ARG(!(feats_f32 && feats_layout != 0 && p.dtype != MTUS_F32));
+    RUN(mtus_convert(ws + p.sa[i].blk.back().xout, feats[i], p.B, p.res[i] * p.res[i], p.C[i], feats_layout == 0 ? 1 : 0, 1, feats_f32, p.dtype, stream));
+  }
   if (StepTimer::enabled()) g_timer.report("mtus_swin_forward");
-  return rc;
+  return MTUS_OK;
 }
 
 static int swin_forward_impl(const mtus_swin_config* cfg, const void* x, int x_is_f32, const float* params,
@@ -406,15 +414,12 @@ static int swin_forward_impl(const mtus_swin_config* cfg, const void* x, int x_i
       RUN(mtus_linear_fwd(A(ba.ln2), W(bp.fc1w), F(bp.fc1b), A(ba.a), A(ba.h), nullptr, nullptr, 1, M, 4 * Cc, Cc, dt, be, stream));
       RUN(mtus_linear_fwd_stream(A(ba.a), W(bp.fc2w), F(bp.fc2b), FA(ba.xout), FA(ba.xmid), dp2, rps, M, Cc, 4 * Cc, dt, be, stream));
     }
-    // stage output (fp32 stream) -> caller's feature tensor, or the in-workspace NHWC copy for zero-copy consumers
+    // stage output (fp32 stream) -> in-workspace NHWC copy in the operand dtype for zero-copy consumers; features the
+    // caller wants materialised in its own tensors are converted by the (eager) epilogue of mtus_swin_forward
     const size_t xo = p.sa[i].blk.back().xout;
-    if (feats[i]) {
-      MTUS_CHECK_ARG(!(feats_f32 && feats_layout != 0 && dt != MTUS_F32));
-      RUN(mtus_convert(A(xo), feats[i], p.B, res * res, Cc, feats_layout == 0 ? 1 : 0, 1, feats_f32, dt, stream));
-    } else if (dt != MTUS_F32) {
-      RUN(mtus_convert(A(xo), A(p.sa[i].feat), p.B, res * res, Cc, 0, 1, 0, dt, stream));
-    }
+    if (!feats[i] && dt != MTUS_F32) RUN(mtus_convert(A(xo), A(p.sa[i].feat), p.B, res * res, Cc, 0, 1, 0, dt, stream));
   }
+  (void)feats_layout; (void)feats_f32;
   return MTUS_OK;
 }
 
@@ -465,9 +470,9 @@ extern "C" int mtus_swin_backward_blocks(const mtus_swin_config* cfg, const floa
   const float* dp = droppath ? reinterpret_cast<const float*>(ws + p.dp_slot) : nullptr;
   int dev = 0; cudaGetDevice(&dev);
   KeyBuilder kb;
-  kb.add((int)2).add(dev).add(*cfg).add(params).add(params_lp).add((int)(dp != nullptr)).add(workspace).add(mask).add(grads)
-    .add(block_hi).add(block_lo);
-  const int rc = run_cached(kb.k, (cudaStream_t)stream, [&](void* s_) {
+  kb.add((int)2).add(dev).add(*cfg).add((int)(dp != nullptr)).add(mask).add(block_hi).add(block_lo).end_shape()
+    .add(params).add(params_lp).add(workspace).add(grads);
+  const int rc = run_cached(kb, (cudaStream_t)stream, [&](void* s_) {
     return swin_backward_impl(cfg, params, params_lp, dp, workspace, dfeats, dfeats_layout, dfeats_f32, grads, block_hi, block_lo, s_);
   });
   if (StepTimer::enabled()) g_timer.report("mtus_swin_backward");

@@ -238,3 +238,58 @@ def test_fused_groupnorm_silu_matches_pytorch(dtype, tol):
         for name, a, r in (("y", yk, yr), ("dx", gx_k, gx_r), ("dgamma", gw_k, gw_r), ("dbeta", gb_k, gb_r)):
             err = (a.float() - r).abs().max().item() / (r.abs().max().item() + 1e-12)
             assert err <= tol, f"{name} {dtype} {(B, C, H, W)}: rel err {err}"
+
+
+def test_graph_replay_reproduces_the_captured_step():
+    """The executors capture their schedule into a CUDA graph on the first call with a given set of addresses and
+    replay it afterwards: the replayed forward must reproduce the captured one bit for bit, replayed backward passes
+    must agree with the first one up to fp32 atomics order, and the cache must actually be hit."""
+    import ctypes as C
+    import mtus_b200 as m
+    from mtus_b200 import _lib
+    if os.environ.get("MTUS_GRAPHS", "1") == "0":
+        pytest.skip("graph cache disabled by MTUS_GRAPHS=0")
+
+    def stats():
+        h, ms, n = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.lib().mtus_graph_cache_stats(C.byref(h), C.byref(ms), C.byref(n))
+        return h.value, ms.value, n.value
+
+    torch.manual_seed(0)
+    enc = m.SwinTransformerEncoder("swin_t", pretrained=False, img_size=224, precision="bf16", drop_path_rate=0.0).cuda().train()
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(3)).cuda()
+    gs = None
+    outs, grads = [], []
+    h0 = stats()[0]
+    for it in range(4):
+        for p in enc.parameters():
+            p.grad = None
+        feats = enc(x)
+        if gs is None:
+            gs = [torch.randn_like(f) for f in feats]
+        outs.append([f.clone() for f in feats])
+        torch.autograd.backward(feats, gs)
+        grads.append(enc.model._last_flat_grad.clone())
+    assert stats()[0] - h0 >= 4, "the executor graph cache was never hit"
+    for it in range(1, 4):
+        for a, b in zip(outs[0], outs[it]):
+            assert torch.equal(a, b)
+        scale = grads[0].abs().max().item()
+        assert (grads[it] - grads[0]).abs().max().item() <= 1e-5 * scale + 1e-7
+
+
+def test_device_prefetcher_delivers_the_issued_batch():
+    import mtus_b200 as m
+    pf = m.DevicePrefetcher("cuda:0")
+    x = torch.randn(4, 3, 32, 32).pin_memory()
+    y = torch.randint(0, 5, (4,)).pin_memory()
+    pf.issue(x, y)
+    assert pf.pending()
+    with pytest.raises(RuntimeError):
+        pf.issue(x, y)
+    xd, yd = pf.take()
+    assert not pf.pending()
+    torch.cuda.synchronize()
+    assert torch.equal(xd.cpu(), x) and torch.equal(yd.cpu(), y)
+    with pytest.raises(RuntimeError):
+        pf.take()
