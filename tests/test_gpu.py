@@ -114,7 +114,10 @@ def test_full_size_swin_b_against_oracle_on_gpu():
         assert rel <= 2e-2, f"{tid}: rel {rel}"
         yo.square().mean().backward()
         ym.float().square().mean().backward()
-        assert gpu_diag._compare_grads(f"swin_b@224 bf16 {tid}", model, oracle, 0.99)
+        # encoder-only task types (classification, regression): every tensor meets the 0.999 target of the north star;
+        # through the FPN, bf16 forward arithmetic alone limits a few tensors to 0.9976-0.999
+        enc_only = model.task_id_to_name[tid] in ("classification", "Regression")
+        assert gpu_diag._compare_grads(f"swin_b@224 bf16 {tid}", model, oracle, 0.999 if enc_only else 0.99)
 
 
 def test_full_size_properties_batch_32():
