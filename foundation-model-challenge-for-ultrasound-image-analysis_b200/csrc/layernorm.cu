@@ -756,7 +756,7 @@ static int lnv2_bwd_launch(const LnxBwdArgs& a, MergeGeom g, cudaStream_t st) {
   else if (nvec <= 8) V2B(8, 1, 2, 6)
   else if (nvec <= 16) V2B(16, 1, 2, 6)
   else if (nvec <= 32) V2B(32, 1, 2, 6)
-  else if (nvec <= 64) V2B(32, 2, 2, 3)
+  else if (nvec <= 64) V2B(32, 2, 2, 2)      // 2 CTAs per SM fit (registers): one resident wave
   else if (nvec <= 96) V2B(32, 3, 1, 3)
   else V2B(32, 4, 1, 3)
 #undef V2B
