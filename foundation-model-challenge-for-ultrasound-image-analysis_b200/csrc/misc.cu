@@ -68,7 +68,17 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, fl
   const int64_t r1 = min(rows, r0 + rows_per_chunk);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (col < C) {
-    for (int64_t r = r0 + ty; r < r1; r += 8) {
+    int64_t r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {            // four independent 16-byte loads in flight per thread
+      float v0[8], v1[8], v2[8], v3[8];
+      IO<T>::load8(x + r * C + col, v0);
+      IO<T>::load8(x + (r + 8) * C + col, v1);
+      IO<T>::load8(x + (r + 16) * C + col, v2);
+      IO<T>::load8(x + (r + 24) * C + col, v3);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += (v0[k] + v1[k]) + (v2[k] + v3[k]);
+    }
+    for (; r < r1; r += 8) {
       float v[8];
       IO<T>::load8(x + r * C + col, v);
 #pragma unroll

@@ -175,3 +175,30 @@ def test_backward_chunk_plan_tiles_the_flat_gradient():
         for name, (p, off, numel, shape) in core._params_by_name.items():
             inside = [s for s in spans if s[0] <= off and off + numel <= s[1]]
             assert len(inside) == 1, name
+
+
+def test_persistent_buffers_keep_autograd_semantics():
+    """Buffers the executors' CUDA-graph cache keys on (FlatParamModule): the gradient block is reused only when no
+    parameter still holds a gradient (so gradient accumulation never sees its views overwritten), and training
+    workspaces cycle through a pool keyed by (batch, size, device)."""
+    enc = m.SwinTransformerEncoder("swin_t", pretrained=False, img_size=224, precision="fp32")
+    core = enc.model
+    dev = torch.device("cpu")
+    g1 = core._grad_block(dev)
+    assert g1.numel() == core._n_flat and float(g1.abs().sum()) == 0.0
+    g1.add_(1.0)
+    g2 = core._grad_block(dev)                      # no parameter holds a gradient: same block, zeroed again
+    assert g2.data_ptr() == g1.data_ptr() and float(g2.abs().sum()) == 0.0
+    p0 = core.ordered_params()[0]
+    p0.grad = g2[:p0.numel()].view_as(p0)           # a backward handed out views: accumulation must not clobber them
+    g3 = core._grad_block(dev)
+    assert g3.data_ptr() != g2.data_ptr()
+    p0.grad = None
+    assert core._grad_block(dev).data_ptr() == g2.data_ptr()
+    # workspace pool
+    w1 = core._take_workspace(4, 1024, dev)
+    w2 = core._take_workspace(4, 1024, dev)         # two forwards before a backward: two distinct workspaces
+    assert w1.data_ptr() != w2.data_ptr()
+    core._return_workspace(4, w1)
+    assert core._take_workspace(4, 1024, dev).data_ptr() == w1.data_ptr()
+    assert core._take_workspace(8, 1024, dev).data_ptr() != w1.data_ptr()
