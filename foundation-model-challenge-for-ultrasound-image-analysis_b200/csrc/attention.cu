@@ -207,6 +207,20 @@ int mtus_window_attn_mma_fwd(const void* qkv, const float* rel_table, const floa
 int mtus_window_attn_mma_bwd(const void* dout, const void* qkv, const void* out, const float* lse, const float* rel_table,
                              const float* qkv_bias, void* dqkv, float* drel_table, float* dqkv_bias, float* dqkv_colsum, int B, int H,
                              int W, int C, int heads, int win_h, int win_w, int shift_h, int shift_w, cudaStream_t st);
+// 65..144-token windows (window 12): attention_mma144.cu
+bool mtus_window_attn_mma144_supported(int wh, int ww, int dtype);
+int mtus_window_attn_mma144_fwd(const void* qkv, const float* rel_table, const float* qkv_bias, void* out, float* lse, int B, int H, int W,
+                                int C, int heads, int win_h, int win_w, int shift_h, int shift_w, cudaStream_t st);
+int mtus_window_attn_mma144_bwd(const void* dout, const void* qkv, const void* out, const float* lse, const float* rel_table,
+                                const float* qkv_bias, void* dqkv, float* drel_table, float* dqkv_bias, float* dqkv_colsum, int B, int H,
+                                int W, int C, int heads, int win_h, int win_w, int shift_h, int shift_w, cudaStream_t st);
+static bool att_forced_simt() {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("MTUS_ATTN"); forced = (e && !strcmp(e, "simt")) ? 1 : 0; }
+  return forced == 1;
+}
+static bool att_use_mma144(int wh, int ww, int dtype) { return !att_forced_simt() && mtus_window_attn_mma144_supported(wh, ww, dtype); }
+
 static bool att_use_mma(int wh, int ww, int dtype) {
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("MTUS_ATTN"); forced = (e && !strcmp(e, "simt")) ? 1 : 0; }
@@ -229,6 +243,8 @@ extern "C" int mtus_window_attn_fwd(const void* qkv, const float* rel_table, con
   MTUS_CHECK_ARG(qkv && rel_table && out);
   if (att_use_mma(win_h, win_w, dtype))
     return mtus_window_attn_mma_fwd(qkv, rel_table, qkv_bias, out, lse, B, H, W, C, heads, win_h, win_w, shift_h, shift_w, (cudaStream_t)stream);
+  if (att_use_mma144(win_h, win_w, dtype) && lse)
+    return mtus_window_attn_mma144_fwd(qkv, rel_table, qkv_bias, out, lse, B, H, W, C, heads, win_h, win_w, shift_h, shift_w, (cudaStream_t)stream);
   AttGeom g;
   int rc = att_geom(g, B, H, W, C, heads, win_h, win_w, shift_h, shift_w);
   if (rc) return rc;
@@ -260,6 +276,9 @@ extern "C" int mtus_window_attn_bwd(const void* dout, const void* qkv, const voi
   if (att_use_mma(win_h, win_w, dtype))
     return mtus_window_attn_mma_bwd(dout, qkv, out, lse, rel_table, qkv_bias, dqkv, drel_table, dqkv_bias, dqkv_colsum, B, H, W, C, heads,
                                     win_h, win_w, shift_h, shift_w, (cudaStream_t)stream);
+  if (att_use_mma144(win_h, win_w, dtype) && lse)
+    return mtus_window_attn_mma144_bwd(dout, qkv, out, lse, rel_table, qkv_bias, dqkv, drel_table, dqkv_bias, dqkv_colsum, B, H, W, C, heads,
+                                       win_h, win_w, shift_h, shift_w, (cudaStream_t)stream);
   AttGeom g;
   int rc = att_geom(g, B, H, W, C, heads, win_h, win_w, shift_h, shift_w);
   if (rc) return rc;

@@ -252,7 +252,9 @@ def g_attention():
     ok = True
     dev = "cuda"
     cases = [(2, 14, 14, 2, 7, 0), (2, 14, 14, 2, 7, 3), (1, 56, 56, 4, 7, 3), (2, 7, 7, 8, 7, 0), (2, 4, 4, 1, 4, 0),
-             (1, 24, 24, 3, 12, 6), (2, 16, 16, 2, 7, 3), (1, 9, 9, 1, 7, 3)]
+             (1, 24, 24, 3, 12, 6), (2, 16, 16, 2, 7, 3), (1, 9, 9, 1, 7, 3),
+             # 65..144-token windows (attention_mma144.cu in bf16): padded map, 81-token windows, one unshifted window
+             (2, 20, 20, 2, 12, 6), (1, 36, 36, 2, 9, 4), (2, 12, 12, 3, 12, 0), (1, 48, 48, 1, 12, 6)]
     for dt, tol in ((torch.float32, 5e-5), (torch.bfloat16, 3e-2)):
         for (B, H, W, heads, win, shift) in cases:
             Cc = heads * 32
