@@ -158,9 +158,17 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """Current torch stream of ``device`` (default: the current device).  The executors key their side streams and graph
+    caches on cudaGetDevice(), so callers that take a tensor's device also make it current (``device_guard``)."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def device_guard(t):
+    """Context manager making ``t.device`` the current CUDA device for the enclosed C-ABI calls."""
+    import torch
+    return torch.cuda.device(t.device)
 
 
 def ptr_array(tensors):

@@ -25,7 +25,10 @@ class _FpnFn(torch.autograd.Function):
     def forward(ctx, dec, nfeat, *args):
         feats, params = args[:nfeat], args[nfeat:]
         needs_grad = any(ctx.needs_input_grad[2:])
-        out, saved = dec._run_forward(list(feats), training_plan=needs_grad)
+        if not feats[0].is_cuda:
+            raise RuntimeError("mtus_b200: the FPN decoder runs only on CUDA (sm_100a); there is no CPU fallback")
+        with _lib.device_guard(feats[0]):
+            out, saved = dec._run_forward(list(feats), training_plan=needs_grad)
         ctx.dec, ctx.saved, ctx.nfeat = dec, saved, nfeat
         ctx.needs = ctx.needs_input_grad[2:]
         return out
@@ -33,7 +36,8 @@ class _FpnFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         dec = ctx.dec
-        dfeats, flat_grad = dec._run_backward(ctx.saved, dout, ctx.needs[:ctx.nfeat])
+        with _lib.device_guard(dout):
+            dfeats, flat_grad = dec._run_backward(ctx.saved, dout, ctx.needs[:ctx.nfeat])
         ctx.saved = None
         return (None, None) + tuple(dfeats) + tuple(dec.grad_views(flat_grad, ctx.needs[ctx.nfeat:]))
 

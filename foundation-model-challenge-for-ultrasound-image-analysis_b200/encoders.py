@@ -41,6 +41,8 @@ SWIN_ARCHS = {
 
 # hook used by parallel.GradAllReducer: called as fn(flat_grad, lo, hi) after each backward stage chunk
 _STAGE_GRAD_HOOK = None
+# hook used by parallel.GradAllReducer: called as fn() when the encoder's backward starts (heads / decoders are done)
+_PRE_BACKWARD_HOOK = None
 
 
 def default_precision() -> str:
@@ -62,7 +64,10 @@ class _SwinFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, core, x, *params):
         needs_grad = any(ctx.needs_input_grad[2:])
-        feats, saved = core._run_forward(x, training_plan=needs_grad)
+        if not x.is_cuda:
+            raise RuntimeError("mtus_b200: the Swin encoder runs only on CUDA (sm_100a); there is no CPU fallback")
+        with _lib.device_guard(x):
+            feats, saved = core._run_forward(x, training_plan=needs_grad)
         ctx.set_materialize_grads(False)         # unused features arrive as None, not as zero tensors to convert
         ctx.core = core
         ctx.saved = saved
@@ -72,7 +77,8 @@ class _SwinFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *dfeats):
         core = ctx.core
-        flat_grad = core._run_backward(ctx.saved, dfeats)
+        with _lib.device_guard(core._flat):          # autograd's backward thread may sit on another device
+            flat_grad = core._run_backward(ctx.saved, dfeats)
         ctx.saved = None
         return (None, None) + tuple(core.grad_views(flat_grad, ctx.param_needs))
 
@@ -221,6 +227,8 @@ class SwinCore(FlatParamModule):
         nhwc = bool(layouts) and all(layouts) and not out_f32
         gs = [None if g is None else (g if (nhwc or g.is_contiguous()) else g.contiguous()) for g in gs]
         hook = _STAGE_GRAD_HOOK
+        if _PRE_BACKWARD_HOOK is not None:
+            _PRE_BACKWARD_HOOK()
         nblk = sum(self.depths)
         chunks = self._backward_chunks() if hook is not None else [(nblk, 0, 0, self._n_flat)]
         for b_hi, b_lo, s_lo, s_hi in chunks:
@@ -277,15 +285,23 @@ class SwinTransformerEncoder(nn.Module):
     def __init__(self, model_name: str = "swin_b", pretrained: bool = True, img_size: int = 224,
                  moe_config: Optional[dict] = None, task_ids: Optional[List[str]] = None,
                  precision: Optional[str] = None, output_dtype: Optional[str] = None,
-                 zero_copy_features: bool = False, drop_path_rate: float = 0.1):
+                 zero_copy_features: bool = False, drop_path_rate: float = 0.1, pretrained_path: Optional[str] = None):
         super().__init__()
         full_model_name = SWIN_MODEL_MAPPING.get(model_name, model_name)
-        if pretrained:
-            raise RuntimeError(
-                "mtus_b200: ImageNet weights cannot be downloaded here; set model.encoder.pretrained: null and load a "
-                "checkpoint with load_state_dict (keys follow timm: encoder.model.layers_0.blocks.0...)")
         self.model = SwinCore(full_model_name, img_size=img_size, drop_path_rate=drop_path_rate, precision=precision,
                               output_dtype=output_dtype, zero_copy_features=zero_copy_features)
+        if pretrained:
+            # timm.create_model(..., pretrained=True) (encoders.py:53-59) downloads; here the weights come from a local
+            # timm / torchvision / reference checkpoint file (checkpoint.py), never from the network
+            from . import checkpoint as _ckpt
+            path = _ckpt.resolve_pretrained_path(full_model_name, pretrained_path)
+            if path is None:
+                raise RuntimeError(
+                    f"mtus_b200: pretrained weights for {full_model_name!r} requested but no local file was found (no "
+                    f"network here). Put {full_model_name}.pth (timm or torchvision state dict) into $MTUS_PRETRAINED_DIR, "
+                    "pass model.encoder.pretrained: /path/to/file, or set model.encoder.pretrained: null.")
+            _ckpt.load_pretrained(self.model, path)
+            self.pretrained_path = path
         self._out_channels = self.model.feature_info.channels()
         self.output_stride = 32
         moe_cfg = moe_config or {}
@@ -325,6 +341,7 @@ def build_encoder(config, task_ids=None, precision: Optional[str] = None, output
         precision = default_precision() if mp is None else ("bf16" if mp else "fp32")
     encoder = SwinTransformerEncoder(model_name=encoder_name, pretrained=pretrained, img_size=img_size,
                                      moe_config=config.get("model.moe", {}), task_ids=task_ids, precision=precision,
-                                     output_dtype=output_dtype, zero_copy_features=zero_copy_features)
+                                     output_dtype=output_dtype, zero_copy_features=zero_copy_features,
+                                     pretrained_path=encoder_weights if isinstance(encoder_weights, str) else None)
     print(f"Loaded Swin Transformer: {encoder_name} (img_size={img_size}, precision={precision}, sm_100a kernels)")
     return encoder

@@ -32,6 +32,10 @@ class DistributedTaskSampler(torch.utils.data.Sampler):
         self.batch_size, self.rank, self.world_size = int(batch_size), int(rank), int(world_size)
         if not (0 <= self.rank < self.world_size):
             raise ValueError("rank must be in [0, world_size)")
+        if self.world_size > 1 and seed is None:
+            # random.Random(None) seeds from OS entropy per process: ranks would draw different tasks, hold different
+            # sets of gradient-bearing parameters and issue mismatched collectives (hang or wrong sums)
+            raise ValueError("DistributedTaskSampler: world_size > 1 needs an explicit seed shared by all ranks")
         self.rng = random.Random(seed)          # identical stream on every rank
         self.indices_by_task: Dict[str, List[int]] = {}
         for idx, tid in enumerate(task_ids):
@@ -69,7 +73,20 @@ class DistributedTaskSampler(torch.utils.data.Sampler):
 
 
 class GradAllReducer:
-    """Mean all-reduce of the gradients of ``model`` over ``group`` (NCCL on GPUs, gloo in CPU tests)."""
+    """Mean all-reduce of the gradients of ``model`` over ``group`` (NCCL on GPUs, gloo in CPU tests).
+
+    Everything is reduced IN PLACE through contiguous gradient blocks, asynchronously on the collective's own stream,
+    while the encoder (the last and longest part of backward) still runs:
+
+    * heads: ``prepare(modules)`` points the ``.grad`` of the active head's parameters at views of one persistent flat
+      block before backward (autograd accumulates into them), so the head's gradient is one buffer -- no concatenate /
+      copy-back round trip;
+    * FPN decoders own a flat gradient block already (``FlatParamModule``);
+    * both are complete when the encoder's backward begins (``encoders._PRE_BACKWARD_HOOK``) and are reduced there;
+    * the encoder's flat block is reduced chunk by chunk as its backward proceeds (``encoders._STAGE_GRAD_HOOK``).
+
+    ``finish()`` reduces whatever the hooks did not see (frozen / absent encoder, foreign parameters) and makes the
+    current stream wait for all outstanding collectives."""
     _avg = None                                 # True: ReduceOp.AVG (NCCL); False: SUM then scale (gloo)
 
     def __init__(self, model: torch.nn.Module, group=None, overlap_encoder: bool = True):
@@ -77,6 +94,8 @@ class GradAllReducer:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.overlap = overlap_encoder
         self._handles = []
+        self._scale_later = []
+        self._done = set()
         self._enc_params = set()
         enc = getattr(model, "encoder", None)
         core = getattr(enc, "model", None)
@@ -87,6 +106,8 @@ class GradAllReducer:
         from ._native import FlatParamModule
         self._flat_modules = [m for m in model.modules() if isinstance(m, FlatParamModule)]
         self._all_params = list(model.parameters())
+        self._head_blocks = {}                  # id(module) -> (flat buffer, [(param, view)])
+        self._prepared = []
 
     def _avg_op(self):
         # NCCL averages in the collective; gloo (CPU tests) has no AVG: sum, then scale
@@ -95,41 +116,96 @@ class GradAllReducer:
             self._avg = backend == "nccl"
         return dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
 
+    def _reduce_async(self, buf: torch.Tensor):
+        self._handles.append(dist.all_reduce(buf, op=self._avg_op(), group=self.group, async_op=True))
+        if not self._avg:
+            self._scale_later.append(buf)
+
+    def _wait_all(self):
+        for h in self._handles:
+            h.wait()                            # stream-ordered wait, not a host sync (NCCL)
+        self._handles = []
+        for b in self._scale_later:
+            b.mul_(1.0 / self.world)
+        self._scale_later = []
+
+    # ---- head gradients as one flat block --------------------------------------------------------------------
+    def prepare(self, modules):
+        """Call after zero_grad and before backward with the non-flat modules that will receive gradients this step."""
+        self._prepared = []
+        if self.world == 1:
+            return
+        for mod in modules:
+            ent = self._head_blocks.get(id(mod))
+            ps = [p for p in mod.parameters() if p.requires_grad]
+            if not ps:
+                continue
+            if ent is None or ent[0].device != ps[0].device or len(ent[1]) != len(ps):
+                sizes = [((p.numel() + 3) // 4) * 4 for p in ps]
+                flat = torch.zeros(sum(sizes), dtype=ps[0].dtype, device=ps[0].device)
+                views, off = [], 0
+                for p, n in zip(ps, sizes):
+                    views.append((p, flat[off:off + p.numel()].view_as(p)))
+                    off += n
+                ent = self._head_blocks[id(mod)] = (flat, views)
+            flat, views = ent
+            if any(p.dtype != flat.dtype for p, _ in views):
+                continue                        # mixed dtypes: leave this module to the generic path in finish()
+            flat.zero_()
+            for p, v in views:
+                p.grad = v
+            self._prepared.append(ent)
+
+    # called from SwinCore._run_backward before its first chunk: heads and decoders have finished their backward
+    def _pre_backward_hook(self):
+        if self.world > 1:
+            self._reduce_early()
+
+    def _reduce_early(self):
+        for flat, views in self._prepared:
+            if all(p.grad is v or (p.grad is not None and p.grad.data_ptr() == v.data_ptr()) for p, v in views):
+                self._reduce_async(flat)
+                self._done |= {id(p) for p, _ in views}
+        self._prepared = []
+        for mod in self._flat_modules:
+            g = getattr(mod, "_last_flat_grad", None)
+            ps = mod.ordered_params()
+            if g is None or not ps or id(ps[0]) in self._done or id(ps[0]) in self._enc_params:
+                continue
+            self._reduce_async(g)
+            self._done |= {id(p) for p in ps}
+
     # called from SwinCore._run_backward after each chunk of blocks: flat_grad[lo:hi] is final
     def _stage_hook(self, flat_grad: torch.Tensor, lo: int, hi: int):
         if self.world > 1:
-            op = self._avg_op()
-            self._handles.append(dist.all_reduce(flat_grad[lo:hi], op=op, group=self.group, async_op=True))
+            self._reduce_async(flat_grad[lo:hi])
             if lo == self._first_lo:            # last chunk: the gradient views are handed to autograd next
-                for h in self._handles:
-                    h.wait()                    # stream-ordered wait, not a host sync (NCCL)
-                self._handles = []
-                if not self._avg:
-                    flat_grad.mul_(1.0 / self.world)
+                self._wait_all()
         self._enc_reduced = True
 
     def __enter__(self):
         self._enc_reduced = False
+        self._done = set()
         if self.overlap and self._enc_params and self.world > 1:
             core = self.model.encoder.model
             self._first_lo = core._stage_slices[0][0]
             _enc._STAGE_GRAD_HOOK = self._stage_hook
+            _enc._PRE_BACKWARD_HOOK = self._pre_backward_hook
         return self
 
     def __exit__(self, *exc):
         _enc._STAGE_GRAD_HOOK = None
+        _enc._PRE_BACKWARD_HOOK = None
         return False
 
     def finish(self):
-        """All-reduce what backward did not already reduce (FPN, heads; the encoder too when not overlapped).
-
-        Flat modules (FPN decoders, the encoder) are reduced in place through their one contiguous gradient block;
-        the remaining (head) gradients are coalesced into one call."""
+        """Reduce what backward did not already reduce and wait (stream-ordered) for every outstanding collective."""
         if self.world == 1:
             return
-        op = self._avg_op()
-        done = set(self._enc_params) if self._enc_reduced else set()
-        handles, scale_later = [], []
+        done = self._done | (set(self._enc_params) if self._enc_reduced else set())
+        self._done = done
+        self._reduce_early()                    # prepared heads / flat decoders the pre-backward hook did not see
+        done = self._done
         for mod in self._flat_modules:
             g = getattr(mod, "_last_flat_grad", None)
             ps = mod.ordered_params()
@@ -140,33 +216,64 @@ class GradAllReducer:
                 continue
             if not (g.data_ptr() <= first.data_ptr() < g.data_ptr() + g.numel() * g.element_size()):
                 continue                        # autograd copied the views: fall through to the generic path
-            handles.append(dist.all_reduce(g, op=op, group=self.group, async_op=True))
-            scale_later.append(g)
+            self._reduce_async(g)
             done |= {id(p) for p in ps}
         grads = [p.grad for p in self._all_params if p.grad is not None and id(p) not in done]
         flat = None
-        if grads:
+        if grads:                               # foreign parameters: one coalesced call and a copy back
             flat = torch.cat([g.reshape(-1) for g in grads])
-            handles.append(dist.all_reduce(flat, op=op, group=self.group, async_op=True))
-        for h in handles:
-            h.wait()
-        if not self._avg:
-            for g in scale_later:
-                g.mul_(1.0 / self.world)
-            if flat is not None:
-                flat.mul_(1.0 / self.world)
+            self._reduce_async(flat)
+        self._wait_all()
         if flat is not None:
             torch._foreach_copy_(grads, [v.view_as(g) for v, g in zip(flat.split_with_sizes([g.numel() for g in grads]), grads)])
 
+    # ---- replica consistency ---------------------------------------------------------------------------------
+    def broadcast_parameters(self, src: int = 0):
+        """Parameters and buffers of every rank := those of ``src`` (what DDP does at construction)."""
+        if self.world == 1:
+            return
+        with torch.no_grad():
+            seen = set()
+            for mod in self._flat_modules:
+                dist.broadcast(mod.flat_params(), src=src, group=self.group)
+                seen |= {id(p) for p in mod.ordered_params()}
+            for p in self._all_params:
+                if id(p) not in seen:
+                    dist.broadcast(p.data, src=src, group=self.group)
+            for b in self.model.buffers():
+                dist.broadcast(b.data, src=src, group=self.group)
+
+    def sync_buffers(self, modules=None):
+        """Average the floating-point buffers (BatchNorm running statistics of the detection heads) over the ranks and
+        take rank 0's integer buffers, so replicas -- and the rank-0 checkpoint -- stay identical."""
+        if self.world == 1:
+            return
+        mods = modules if modules is not None else [self.model]
+        with torch.no_grad():
+            for mod in mods:
+                for b in mod.buffers():
+                    if b.is_floating_point():
+                        dist.all_reduce(b.data, op=dist.ReduceOp.SUM, group=self.group)
+                        b.data.mul_(1.0 / self.world)
+                    else:
+                        dist.broadcast(b.data, src=0, group=self.group)
+
 
 class DataParallelTrainer:
-    """One training step with the reference's semantics (train.py:326,440-455) on 1..N ranks."""
+    """One training step with the reference's semantics (train.py:326,440-455) on 1..N ranks.
+
+    At construction every rank takes rank 0's parameters and buffers; each step the active head's buffers (BatchNorm
+    running statistics) are averaged over the ranks.  ``gradient_clip`` is THE clip threshold: an optimizer that clips
+    inside its step (``FlatAdamW``) is given this value (0 disables clipping, as in train.py:444-446)."""
 
     def __init__(self, model, optimizer, loss_functions, loss_weights=None, gradient_clip: float = 1.0, group=None):
         self.model, self.optimizer = model, optimizer
         self.loss_functions, self.loss_weights = loss_functions, loss_weights or {}
         self.clip = float(gradient_clip)
+        if getattr(optimizer, "handles_clipping", False):
+            optimizer.max_norm = self.clip
         self.reducer = GradAllReducer(model, group=group)
+        self.reducer.broadcast_parameters(0)
 
     def step(self, images, labels, task_id):
         from .losses import compute_task_loss
@@ -175,9 +282,14 @@ class DataParallelTrainer:
         loss = compute_task_loss(self.loss_functions, task_name, outputs, labels)
         total = loss * self.loss_weights.get(task_name, 1.0)
         self.optimizer.zero_grad()
+        head = self.model.heads[task_id] if hasattr(self.model, "heads") else None
+        if head is not None:
+            self.reducer.prepare([head])
         with self.reducer:
             total.backward()
         self.reducer.finish()
+        if head is not None and self.reducer.world > 1 and any(True for _ in head.buffers()):
+            self.reducer.sync_buffers([head])
         if self.clip > 0 and not getattr(self.optimizer, "handles_clipping", False):
             torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip)
         self.optimizer.step()

@@ -202,3 +202,43 @@ def test_persistent_buffers_keep_autograd_semantics():
     core._return_workspace(4, w1)
     assert core._take_workspace(4, 1024, dev).data_ptr() == w1.data_ptr()
     assert core._take_workspace(8, 1024, dev).data_ptr() != w1.data_ptr()
+
+
+def test_flat_adamw_is_a_torch_optimizer_and_follows_lr_schedulers():
+    """the reference's CosineAnnealingLR (code/train.py:222-253, stepped at :698-704) must be able to drive
+    FlatAdamW.  CPU part: a model without flat blocks (everything goes through the mirrored torch groups)."""
+    import torch
+    import torch.nn as nn
+    import mtus_b200 as m
+
+    class Toy(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.encoder = nn.Linear(6, 6)
+            self.heads = nn.Linear(6, 2)
+
+        def get_trainable_parameters(self):
+            return list(self.encoder.parameters()), list(self.heads.parameters())
+
+    torch.manual_seed(0)
+    a, b = Toy(), Toy()
+    b.load_state_dict(a.state_dict())
+    oa = m.FlatAdamW(a, lr=1e-2, weight_decay=0.1, max_grad_norm=0.0)
+    ob = torch.optim.AdamW([{"params": list(b.encoder.parameters()), "lr": 1e-3},
+                            {"params": list(b.heads.parameters()), "lr": 1e-2}], lr=1e-2, weight_decay=0.1)
+    assert isinstance(oa, torch.optim.Optimizer) and [g["lr"] for g in oa.param_groups] == [1e-3, 1e-2]
+    sa = torch.optim.lr_scheduler.CosineAnnealingLR(oa, T_max=5, eta_min=1e-6)
+    sb = torch.optim.lr_scheduler.CosineAnnealingLR(ob, T_max=5, eta_min=1e-6)
+    x = torch.randn(8, 6)
+    for _ in range(5):
+        for mod, opt, sch in ((a, oa, sa), (b, ob, sb)):
+            opt.zero_grad()
+            mod.heads(torch.tanh(mod.encoder(x))).square().mean().backward()
+            opt.step()
+            sch.step()
+        assert [g["lr"] for g in oa.param_groups] == [g["lr"] for g in ob.param_groups]
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(pa, pb, atol=1e-7)
+    sd = oa.state_dict()
+    oa.load_state_dict(sd)
+    assert [g["lr"] for g in oa.param_groups] == [g["lr"] for g in ob.param_groups]

@@ -172,3 +172,111 @@ def test_reference_multitask_model_on_shims_equals_oracle_model():
         ref(x, "no_such_task")
     with pytest.raises(ValueError):
         oracle(x, "no_such_task")
+
+
+# ---- second independent pin of the Swin restatement: Hugging Face transformers -------------------
+def _hf_state_dict_from_oracle(sd, depths):
+    """oracle / timm keys -> transformers.SwinModel keys (qkv split into query / key / value; HF stores the
+    PatchMerging of stage i+1 at the END of its layer i)."""
+    out = {}
+    for k, v in sd.items():
+        if k.startswith("patch_embed.proj."):
+            out["embeddings.patch_embeddings.projection." + k.rsplit(".", 1)[1]] = v
+        elif k.startswith("patch_embed.norm."):
+            out["embeddings.norm." + k.rsplit(".", 1)[1]] = v
+        elif k.startswith("layers_"):
+            i = int(k[len("layers_")])
+            rest = k.split(".", 1)[1]
+            if rest.startswith("downsample."):
+                out[f"encoder.layers.{i - 1}.{rest}"] = v
+                continue
+            _, j, tail = rest.split(".", 2)
+            pre = f"encoder.layers.{i}.blocks.{j}."
+            leaf = tail.rsplit(".", 1)[1] if "." in tail else tail
+            if tail.startswith("norm1."):
+                out[pre + "layernorm_before." + leaf] = v
+            elif tail.startswith("norm2."):
+                out[pre + "layernorm_after." + leaf] = v
+            elif tail == "attn.relative_position_bias_table":
+                out[pre + "attention.self.relative_position_bias_table"] = v
+            elif tail.startswith("attn.qkv."):
+                c = v.shape[0] // 3
+                for n, name in enumerate(("query", "key", "value")):
+                    out[pre + f"attention.self.{name}.{leaf}"] = v[n * c:(n + 1) * c]
+            elif tail.startswith("attn.proj."):
+                out[pre + "attention.output.dense." + leaf] = v
+            elif tail.startswith("mlp.fc1."):
+                out[pre + "intermediate.dense." + leaf] = v
+            elif tail.startswith("mlp.fc2."):
+                out[pre + "output.dense." + leaf] = v
+    return out
+
+
+@pytest.mark.parametrize("img", [224, 448])
+def test_swin_oracle_matches_huggingface_transformers(img):
+    """Unpadded configurations only: HF pads then rolls, timm rolls then pads.  224 -> maps 56/28/14/7 (last
+    stage unshifted, one window); 448 -> 112/56/28/14 (shifted windows and masks in all four stages)."""
+    transformers = pytest.importorskip("transformers")
+    from transformers import SwinConfig, SwinModel
+    from oracle import swin
+    name = "swin_micro_patch4_window7_test"
+    ed, depths, heads, win = swin.SWIN_VARIANTS[name]
+    torch.manual_seed(0)
+    o = swin.create_model(name, features_only=True, img_size=img, drop_path_rate=0.0).eval()
+    with torch.no_grad():
+        for p in o.parameters():
+            p.add_(torch.randn_like(p) * 0.02)          # biases / LayerNorm affine away from their (0, 1) init
+    cfg = SwinConfig(image_size=img, patch_size=4, num_channels=3, embed_dim=ed, depths=list(depths), num_heads=list(heads),
+                     window_size=win, mlp_ratio=4.0, qkv_bias=True, hidden_dropout_prob=0.0,
+                     attention_probs_dropout_prob=0.0, drop_path_rate=0.0, hidden_act="gelu",
+                     use_absolute_embeddings=False, layer_norm_eps=1e-5)
+    hf = SwinModel(cfg, add_pooling_layer=False).eval()
+    res = hf.load_state_dict(_hf_state_dict_from_oracle(o.state_dict(), depths), strict=False)
+    assert not res.unexpected_keys
+    assert not [k for k in res.missing_keys if "relative_position_index" not in k and not k.startswith("layernorm.")], res
+    x = torch.randn(1 if img > 224 else 2, 3, img, img, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        fo = o(x)
+        emb, dims = hf.embeddings(x)
+        enc = hf.encoder(emb, dims, output_hidden_states=True, output_hidden_states_before_downsampling=True, return_dict=True)
+    hs = enc.reshaped_hidden_states[1:]                  # [B, C, H, W] per stage, before the next PatchMerging
+    assert len(hs) == 4
+    for a, b in zip(fo, hs):
+        b = b.permute(0, 2, 3, 1)
+        assert a.shape == b.shape
+        assert torch.allclose(a, b, rtol=1e-4, atol=2e-5), float((a - b).abs().max())
+
+
+# ---- FPN lateral + top-down pathway vs torchvision.ops.FeaturePyramidNetwork ------------------------------------
+def test_fpn_lateral_topdown_matches_torchvision_feature_pyramid_network():
+    """smp's p5 = 1x1(c5), p_k = nearest_up(p_{k+1}) + 1x1(c_k) is torchvision's FPN inner pathway.  torchvision then
+    applies a 3x3 `layer_block` per level (smp has none): with identity kernels there its outputs ARE p2..p5, which the
+    oracle must reproduce from the same 1x1 weights."""
+    from collections import OrderedDict
+    from torchvision.ops import FeaturePyramidNetwork
+    from oracle.fpn import FPNDecoder
+    chans = [32, 64, 128, 256]
+    torch.manual_seed(0)
+    dec = FPNDecoder(encoder_channels=[3] + chans, encoder_depth=4, pyramid_channels=64, segmentation_channels=32,
+                     dropout=0.0, merge_policy="cat").eval()
+    tv = FeaturePyramidNetwork(chans, 64).eval()
+    with torch.no_grad():
+        lat = [dec.p2.skip_conv, dec.p3.skip_conv, dec.p4.skip_conv, dec.p5]
+        for blk, conv in zip(tv.inner_blocks, lat):
+            blk[0].weight.copy_(conv.weight)
+            blk[0].bias.copy_(conv.bias)
+        for blk in tv.layer_blocks:
+            blk[0].weight.zero_()
+            blk[0].bias.zero_()
+            for c in range(64):
+                blk[0].weight[c, c, 1, 1] = 1.0
+    g = torch.Generator().manual_seed(1)
+    feats = [torch.randn(2, c, s, s, generator=g) for c, s in zip(chans, (32, 16, 8, 4))]
+    with torch.no_grad():
+        out = tv(OrderedDict((str(i), f) for i, f in enumerate(feats)))
+        p5 = dec.p5(feats[3])
+        p4 = dec.p4(p5, feats[2])
+        p3 = dec.p3(p4, feats[1])
+        p2 = dec.p2(p3, feats[0])
+    for a, b in zip((p2, p3, p4, p5), out.values()):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-5), float((a - b).abs().max())

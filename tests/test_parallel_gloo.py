@@ -85,9 +85,7 @@ def _worker(rank, world, port, out):
     holder = nn.Module()
     holder.encoder = nn.Module()
     holder.encoder.model = core
-    red2 = m.GradAllReducer.__new__(m.GradAllReducer)
-    red2.model, red2.group, red2.world, red2.overlap = holder, None, world, True
-    red2._handles, red2._enc_params, red2._enc_reduced = [], {id(core._p[0])}, False
+    red2 = m.GradAllReducer(holder)
     g = torch.full((n,), float(rank + 1))
     with red2:
         hook = enc_mod._STAGE_GRAD_HOOK
@@ -99,8 +97,48 @@ def _worker(rank, world, port, out):
             hook(g, s_lo, s_hi)
     ok &= enc_mod._STAGE_GRAD_HOOK is None
     ok &= torch.allclose(g, torch.full((n,), sum(range(1, world + 1)) / world))
+    # ---- 4. active head reduced in place through one flat gradient block (prepare), buffers averaged ----------
+    torch.manual_seed(1 + rank)                          # replicas start DIFFERENT: the trainer must broadcast rank 0
+    model2 = _Toy()
+    model2.heads["a"] = nn.Sequential(nn.Linear(8, 2), nn.BatchNorm1d(2))
+    opt2 = torch.optim.SGD(model2.parameters(), lr=0.1)
+    tr2 = m.DataParallelTrainer(model2, opt2, {"Regression": nn.MSELoss()}, gradient_clip=0.0)
+    p0 = [None] * world
+    dist.all_gather_object(p0, torch.cat([p.detach().flatten() for p in model2.parameters()]))
+    ok &= torch.equal(p0[0], p0[1])                      # broadcast at construction
+    xs = torch.randn(4, 8, generator=torch.Generator().manual_seed(300 + rank))
+    ys = torch.randn(4, 2, generator=torch.Generator().manual_seed(400 + rank))
+    ref = _Toy()
+    ref.heads["a"] = nn.Sequential(nn.Linear(8, 2), nn.BatchNorm1d(2))
+    ref.load_state_dict(model2.state_dict())
+    (ref(xs, "a") - ys).square().mean().backward()
+    local2 = {k: p.grad.clone() for k, p in ref.named_parameters() if p.grad is not None}
+    g2 = [None] * world
+    dist.all_gather_object(g2, local2)
+    tr2.optimizer = type("NoStep", (), {"zero_grad": lambda self_: opt2.zero_grad(), "step": lambda self_: None})()
+    tr2.step(xs, ys, "a")
+    for k, p in model2.named_parameters():
+        if k.startswith("heads.b"):
+            ok &= p.grad is None
+            continue
+        ok &= torch.allclose(p.grad, sum(g[k] for g in g2) / world, atol=1e-7)
+    blk = tr2.reducer._head_blocks[id(model2.heads["a"])]
+    ok &= all(p.grad.data_ptr() == v.data_ptr() for p, v in blk[1])    # gradients ARE views of the flat block
+    rm = [None] * world
+    dist.all_gather_object(rm, model2.heads["a"][1].running_mean.clone())
+    ok &= torch.equal(rm[0], rm[1])                      # BatchNorm statistics stay identical across replicas
     out[rank] = bool(ok)
     dist.destroy_process_group()
+
+
+def test_sampler_needs_a_seed_when_distributed():
+    import pytest
+    import mtus_b200 as m
+    with pytest.raises(ValueError):
+        m.DistributedTaskSampler(["a", "b"] * 8, 2, rank=0, world_size=2, seed=None)
+    a = list(m.DistributedTaskSampler(["a", "b"] * 8, 2, rank=0, world_size=2, seed=5))
+    b = list(m.DistributedTaskSampler(["a", "b"] * 8, 2, rank=1, world_size=2, seed=5))
+    assert len(a) == len(b) and all(set(x).isdisjoint(y) for x, y in zip(a, b))
 
 
 def test_world_size_2_gloo():
