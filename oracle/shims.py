@@ -48,6 +48,11 @@ def install(force: bool = False) -> None:
     dfpn.decoder = dec
     for m in (smp, base, losses, decoders, dfpn, dec, encoders):
         sys.modules[m.__name__] = m
+    # importlib.util.find_spec() (used by libraries that probe for optional dependencies, e.g. transformers probing for
+    # timm) raises on a module whose __spec__ is None: give every stub a spec
+    import importlib.machinery
+    for m in (timm, smp, base, losses, decoders, dfpn, dec, encoders):
+        m.__spec__ = importlib.machinery.ModuleSpec(m.__name__, loader=None)
 
 
 def import_reference_models(reference_root: str = "/root/reference"):
