@@ -35,6 +35,20 @@ if ROOT not in sys.path:
 METRIC = "Swin-B 27-task train img/s"
 UNIT = "img/s"
 WORKLOAD = "configs[1]: swin_b + separate FPNs + 27 heads, 224x224, batch 32/GPU, bf16, fwd+bwd+clip+AdamW"
+# --workload selects the other BASELINE.json configurations (the default line is configs[1] / configs[2])
+WORKLOADS = {
+    "swin_b_224": {"encoder": "swin_b", "image": 224, "batch": 32, "train": True, "name": WORKLOAD,
+                   "metric": METRIC, "train_gf_per_img": 105.9},
+    "swin_l_384": {"encoder": "swin_large_patch4_window12_384", "image": 384, "batch": 16, "train": True,
+                   "name": "configs[3]: swin_large_patch4_window12_384 + separate FPNs + 27 heads, 384x384, batch 16/GPU, bf16, "
+                           "fwd+bwd+clip+AdamW",
+                   "metric": "Swin-L/384 window-12 27-task train img/s", "train_gf_per_img": None},
+    "swin_b_512_infer": {"encoder": "swin_b", "image": 512, "batch": 128, "train": False,
+                         "name": "configs[4]: swin_b 27-task inference (eval, no_grad), 512x512 (padded windows), batch 128, bf16",
+                         "metric": "Swin-B 27-task inference img/s @512", "train_gf_per_img": None},
+}
+# the CPU arm (cpu_baseline and --impl reference) always times THIS sample: same model, same task sequence, fixed batch
+CPU_SAMPLE_BATCH = 8
 
 
 def _peaks():
@@ -106,186 +120,181 @@ def _task_sequence(task_ids, n, seed=42):
 # =================================================================================================
 # reference arm / cpu_baseline: the oracle port on the host cores
 # =================================================================================================
-def _oracle_steps(per_step_batch, task_seq, threads=None):
-    """Runs one oracle training step per entry of task_seq; returns seconds per step list."""
+def _cpu_threads():
+    """All host cores, regardless of what the launcher exported (torchrun sets OMP_NUM_THREADS=1)."""
     import torch
-    import mtus_b200 as m
-    from oracle.model import OracleMultiTaskModel, synthetic_batch, train_step
-    if threads:
-        torch.set_num_threads(threads)
-    cfg = m.swin_b_27task(batch_size=per_step_batch, mixed_precision=False)
-    torch.manual_seed(0)
-    model = OracleMultiTaskModel(cfg).train()
-    enc = list(model.encoder.parameters())
-    enc_ids = {id(p) for p in enc}
-    rest = [p for p in model.parameters() if id(p) not in enc_ids]
-    opt = torch.optim.AdamW([{"params": enc, "lr": 1e-5}, {"params": rest, "lr": 1e-4}], lr=1e-4, weight_decay=1e-4)
-    tcfg = {t["task_id"]: t for t in cfg.get_task_configs()}
-    gen = torch.Generator().manual_seed(1)
-    out = []
-    for tid in task_seq:
-        x, y = synthetic_batch(tcfg[tid], per_step_batch, 224, gen)
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0)) or n
+    except Exception:
+        pass
+    torch.set_num_threads(n)
+    return n
+
+
+class _OracleRunner:
+    """The oracle port of the reference's training step (code/train.py:326,440-455) on the host CPUs, fp32."""
+
+    def __init__(self, batch):
+        import torch
+        import mtus_b200 as m
+        from oracle.model import OracleMultiTaskModel
+        self.batch = batch
+        cfg = m.swin_b_27task(batch_size=batch, mixed_precision=False)
+        torch.manual_seed(0)
+        self.model = OracleMultiTaskModel(cfg).train()
+        enc = list(self.model.encoder.parameters())
+        enc_ids = {id(p) for p in enc}
+        rest = [p for p in self.model.parameters() if id(p) not in enc_ids]
+        self.opt = torch.optim.AdamW([{"params": enc, "lr": 1e-5}, {"params": rest, "lr": 1e-4}], lr=1e-4, weight_decay=1e-4)
+        self.tcfg = {t["task_id"]: t for t in cfg.get_task_configs()}
+        self.gen = torch.Generator().manual_seed(1)
+
+    def step(self, tid):
+        from oracle.model import synthetic_batch, train_step
+        x, y = synthetic_batch(self.tcfg[tid], self.batch, 224, self.gen)
         t0 = time.perf_counter()
-        loss = train_step(model, opt, x, y, tid)
+        loss = train_step(self.model, self.opt, x, y, tid)
         float(loss)
-        out.append(time.perf_counter() - t0)
-    return out
+        return time.perf_counter() - t0
+
+
+def _cpu_sample_text(n_steps, batch, threads):
+    return (f"{n_steps} training steps x {batch} images of the swin_b 27-task model (same seeded task sequence as the GPU arm, "
+            f"batch {batch} instead of 32), oracle fp32 PyTorch on {threads} threads ({os.cpu_count()} logical cores)")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import torch
-    cores = os.cpu_count() or 1
-    threads = torch.get_num_threads()
+    threads = _cpu_threads()
     task_ids = [t["task_id"] for t in __import__("mtus_b200").tasks_27()]
-    # calibrate: one tiny step, then size the per-step sample so K+W steps end in about two minutes
-    t_cal = _oracle_steps(2, ["T2A_fetal_abdomen"])[0] / 2.0
-    budget = 120.0
     n = args.steps + args.warmup
-    bsz = int(max(1, min(32, budget / (n * max(t_cal, 1e-3)))))
     seq = _task_sequence(task_ids, n)
-    times = _oracle_steps(bsz, seq)
+    batch = CPU_SAMPLE_BATCH
+    runner = _OracleRunner(batch)
+    t_first = runner.step(seq[0])                     # untimed: first-touch / oneDNN primitive creation
+    if t_first * n > 400.0 and batch > 2:            # a slow host: keep the run within minutes, say so in `sample`
+        batch = max(1, int(batch * 300.0 / (t_first * n)))
+        runner = _OracleRunner(batch)
+        runner.step(seq[0])
+    times = [runner.step(tid) for tid in seq]
     timed = times[args.warmup:]
     total = sum(timed)
-    value = bsz * len(timed) / total
+    value = batch * len(timed) / total
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / len(timed), 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{bsz} images per step (bounded sample of the 32-image step)",
+        "config": {"workload": WORKLOAD, "sample": f"{batch} images per step (bounded sample of the 32-image step)",
                    "device": "host CPU"},
         "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{len(timed)} training steps x {bsz} images, oracle fp32 PyTorch on {threads} threads "
-                                   f"({cores} logical cores)"},
+                         "sample": _cpu_sample_text(len(timed), batch, threads)},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
     return 0
 
 
-def cpu_baseline_sample():
-    """cpu_baseline leg of our arm: ~10-30 s of oracle work on the host cores (rank 0, N = 1 only)."""
-    import torch
-    threads = torch.get_num_threads()
-    task_ids = [t["task_id"] for t in __import__("mtus_b200").tasks_27()]
-    t_cal = _oracle_steps(2, ["T2A_fetal_abdomen"])[0] / 2.0
-    bsz = int(max(1, min(32, 15.0 / (4 * max(t_cal, 1e-3)))))
-    seq = ["T2A_fetal_abdomen", "T1_fetal_planes", "T4A_fetal_brain", "T5_fetal_femur"]   # one of each task type
-    times = _oracle_steps(bsz, [seq[0]] + seq)[1:]
-    value = bsz * len(times) / sum(times)
+def cpu_baseline_sample(seq):
+    """cpu_baseline leg of our arm (rank 0, N = 1 only): the first steps of the SAME seeded task sequence, same fixed
+    batch and thread policy as --impl reference, ~10-30 s of CPU work."""
+    threads = _cpu_threads()
+    runner = _OracleRunner(CPU_SAMPLE_BATCH)
+    runner.step(seq[0])                               # untimed
+    times, budget = [], 25.0
+    for tid in seq:
+        times.append(runner.step(tid))
+        if sum(times) > budget or len(times) >= 12:
+            break
+    value = CPU_SAMPLE_BATCH * len(times) / sum(times)
     return {"value": round(value, 3), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"4 training steps (seg, cls, det, reg) x {bsz} images of the same swin_b 27-task model, "
-                      f"oracle fp32 PyTorch, {threads} threads on {os.cpu_count()} logical cores"}
+            "sample": _cpu_sample_text(len(times), CPU_SAMPLE_BATCH, threads)}
 
 
 # =================================================================================================
 # our arm
 # =================================================================================================
 def _kernel_rooflines(peaks, device):
-    """Times the dominant kernel (tcgen05 GEMM) and the main bandwidth-bound kernels with CUDA events.
-
-    Each kernel is launched back to back over a ring of distinct operand sets whose total size exceeds the 126 MB L2
-    several times (every launch reads cold operands; no flush kernel sits inside the timed region), and the average
-    launch duration is the event time divided by the number of launches."""
+    """Roofline of the dominant kernel (tcgen05 GEMM) and of the bandwidth-bound kernels, timed host-free: each kernel is a
+    CUDA graph of back-to-back launches over a ring of pre-allocated operand sets > 4x the L2 (mtus_b200/kbench.py), one
+    graph launch between two CUDA events on the launching stream."""
     import torch
-    from mtus_b200 import ops, _lib
+    from mtus_b200 import kbench
     res = {}
+    hbm, tc = peaks["hbm"], peaks["tc_sustained"]
 
-    def ring_time(make_set, run, bytes_per_set, launches=48):
-        n_sets = max(3, int(400e6 // max(bytes_per_set, 1)) + 1)
-        sets = [make_set() for _ in range(n_sets)]
-        for i in range(min(n_sets, 6)):
-            run(sets[i])
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for i in range(launches):
-            run(sets[i % n_sets])
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) * 1e-3 / launches
-
-    # Swin-B stage 3 (18 of 24 blocks, 73 % of encoder FLOPs), B=32: M = 6272 tokens, C = 512
+    # ---- dominant kernel: gemm_tc2_kernel on the Swin-B stage-3 shapes (18 of 24 blocks, 73 % of encoder FLOPs) ----
     M, Cc = 32 * 196, 512
-    gemm = []
-    for name, K, N, kind in (("qkv", Cc, 3 * Cc, "bias"), ("proj", Cc, Cc, "stream"), ("fc1", Cc, 4 * Cc, "gelu"), ("fc2", 4 * Cc, Cc, "stream")):
-        def make_set(K=K, N=N, kind=kind):
-            x = (torch.randn(M, K, device=device) * 0.5).bfloat16()
-            w = (torch.randn(N, K, device=device) * 0.02).bfloat16()
-            b = torch.zeros(N, device=device)
-            r = torch.randn(M, N, device=device) if kind == "stream" else None
-            return x, w, b, r
-
-        def run(st, kind=kind):
-            x, w, b, r = st
-            if kind == "bias":
-                ops.linear_fwd(x, w, b, backend=_lib.BACKEND_TCGEN05)
-            elif kind == "gelu":
-                ops.linear_fwd(x, w, b, gelu=True, backend=_lib.BACKEND_TCGEN05)
-            else:   # proj / fc2 write the fp32 residual stream: y = res + x w^T + b
-                ops.linear_fwd_stream(x, w, b, res=r, backend=_lib.BACKEND_TCGEN05)
-        by = (M * K + N * K) * 2 + M * N * (8 if kind == "stream" else (4 if kind == "gelu" else 2))
-        t = ring_time(make_set, run, by)
-        gemm.append((name, 2.0 * M * K * N, t, by))
-    fl = sum(g[1] for g in gemm)
-    tt = sum(g[2] for g in gemm)
+    table, fwd = {}, []
+    for direction in ("fwd", "dgrad", "wgrad"):
+        for name, N, K, kind in kbench.linear_cases(M, Cc):
+            t, fl, by = kbench.time_linear(M, N, K, kind, direction, device)
+            table[f"{name}.{direction}"] = {"us": round(t * 1e6, 2), "tflops": round(fl / t / 1e12, 1), "frac": round(fl / t / 1e12 / tc, 3)}
+            if direction == "fwd":
+                fwd.append((fl, t, by))
+    fl = sum(g[0] for g in fwd)
+    tt = sum(g[1] for g in fwd)
     ach = fl / tt / 1e12
-    traffic = None
-    try:   # dram bytes of the same four launches from the committed ncu --set full capture (profiles/)
-        with open(os.path.join(ROOT, "profiles", "r1_gemm_tc2_traffic.json")) as f:
-            traffic = json.load(f)["dram_bytes_per_launch_avg"]
-    except Exception:
-        pass
+    traffic, traffic_src = None, None
+    for fn in ("r2_gemm_tc2_traffic.json", "r1_gemm_tc2_traffic.json"):
+        try:   # dram bytes of the same four launches from the committed ncu --set full capture (profiles/): STATIC, not this run
+            with open(os.path.join(ROOT, "profiles", fn)) as f:
+                traffic = json.load(f)["dram_bytes_per_launch_avg"]
+            traffic_src = f"static: profiles/{fn} (ncu --set full of these four launches inside a training step; not re-measured by this run)"
+            break
+        except Exception:
+            pass
+    all_fl = sum(2.0 * M * n * k for _, n, k, _ in kbench.linear_cases(M, Cc)) * 3
+    all_t = sum(v["us"] for v in table.values()) * 1e-6
     res["roofline"] = {"bound": "tensor", "kernel": "gemm_tc2_kernel (persistent tcgen05.mma + TMA + TMEM), Swin-B stage-3 forward GEMMs "
                        "qkv / proj / fc1+GELU / fc2 at M=6272, one launch each", "achieved": round(ach, 1),
-                       "peak": peaks["tc_sustained"], "unit": "TFLOP/s", "frac": round(ach / peaks["tc_sustained"], 4), "traffic": traffic,
-                       "peak_source": f"{peaks['src']} (sustained cuBLAS bf16 figure: kernels timed back to back in a long loop, operands "
-                                      "rotated through > 3x the L2 size)",
-                       "algorithmic_flops_per_launch_avg": fl / 4, "avg_launch_us": round(tt / 4 * 1e6, 2),
-                       "per_shape_tflops": {g[0]: round(g[1] / g[2] / 1e12, 1) for g in gemm}}
+                       "peak": tc, "unit": "TFLOP/s", "frac": round(ach / tc, 4), "traffic": traffic, "traffic_source": traffic_src,
+                       "peak_source": f"{peaks['src']} (sustained cuBLAS bf16 figure: kernels timed back to back in a long loop)",
+                       "timing": "CUDA graph of back-to-back launches over operand rings > 4x L2, one graph launch between two events; no host "
+                                 "work, no allocation, no fill kernels in the timed region",
+                       "algorithmic_flops_per_launch_avg": fl / 4, "algorithmic_bytes_per_launch_avg": sum(g[2] for g in fwd) / 4,
+                       "avg_launch_us": round(tt / 4 * 1e6, 2),
+                       "per_shape": table,
+                       "fwd_dgrad_wgrad_tflops": round(all_fl / all_t / 1e12, 1), "fwd_dgrad_wgrad_frac": round(all_fl / all_t / 1e12 / tc, 4)}
+
     extra = []
-    # LayerNorm fwd (fp32 residual stream in, bf16 out), stage 1 shape [100352, 128]: algorithmic bytes rows*C*(4+2)
-    rows, C1 = 32 * 3136, 128
-    g_, b_ = torch.ones(C1, device=device), torch.zeros(C1, device=device)
-    t = ring_time(lambda: torch.randn(rows, C1, device=device), lambda x: ops.layernorm_fwd_mixed(x, g_, b_, torch.bfloat16), rows * C1 * 6)
-    by = rows * C1 * 6.0
-    extra.append({"kernel": "lnv2_fwd_kernel [100352,128] fp32 -> bf16", "bound": "hbm", "achieved": round(by / t / 1e9, 1),
-                  "peak": peaks["hbm"], "unit": "GB/s", "frac": round(by / t / 1e9 / peaks["hbm"], 4)})
-    # window attention fwd, stage 1: qkv [32,56,56,384] in, out [32,56,56,128]: 4*C*s bytes per token
-    tab = torch.zeros(169, 4, device=device)
-    bias = torch.zeros(384, device=device)
-    t = ring_time(lambda: torch.randn(32, 56, 56, 384, device=device).bfloat16(), lambda q: ops.window_attn_fwd(q, tab, bias, 4, 7, 3),
-                  32 * 3136 * 128 * 8)
-    by = 4.0 * 32 * 3136 * 128 * 2
-    fl = 4.0 * 49 * 49 * 32 * (32 * 64 * 4)
-    extra.append({"kernel": "window_attn_mma_fwd_kernel stage 1 (shifted) bf16", "bound": "hbm", "achieved": round(by / t / 1e9, 1),
-                  "peak": peaks["hbm"], "unit": "GB/s", "frac": round(by / t / 1e9 / peaks["hbm"], 4),
-                  "attn_only_tflops": round(fl / t / 1e12, 2),
-                  "attn_only_frac_of_bf16_peak": round(fl / t / 1e12 / peaks["tc_sustained"], 4)})
-    # window attention bwd, stage 1: q, k, v, o, dO in; dq, dk, dv out: 8*C*s bytes per token (+ lse, negligible)
-    def make_bwd():
-        q = torch.randn(32, 56, 56, 384, device=device).bfloat16()
-        o, l = ops.window_attn_fwd(q, tab, bias, 4, 7, 3, return_lse=True)
-        return q, o, l, torch.randn_like(o)
-    t = ring_time(make_bwd, lambda s_: ops.window_attn_bwd(s_[3], s_[0], s_[1], tab, bias, 4, 7, 3, lse=s_[2], with_colsum=True),
-                  32 * 3136 * 128 * 16, launches=24)
-    by = 8.0 * 32 * 3136 * 128 * 2
-    extra.append({"kernel": "window_attn_mma_bwd_kernel stage 1 (shifted) bf16", "bound": "hbm", "achieved": round(by / t / 1e9, 1),
-                  "peak": peaks["hbm"], "unit": "GB/s", "frac": round(by / t / 1e9 / peaks["hbm"], 4),
-                  "attn_only_tflops": round(2.5 * fl / t / 1e12, 2)})
-    # LayerNorm bwd (bf16 dy, fp32 x, fp32 stream gradient in / out, bf16 operand copy out), stage 1: rows*C*(2+4+4+4+2)
-    def make_lnb():
-        x = torch.randn(rows, C1, device=device)
-        y, mean, rstd = ops.layernorm_fwd_mixed(x, g_, b_, torch.bfloat16)
-        return torch.randn(rows, C1, device=device).bfloat16(), x, mean, rstd, torch.randn(rows, C1, device=device)
-    t = ring_time(make_lnb, lambda s_: ops.layernorm_bwd_mixed(s_[0], s_[1], g_, s_[2], s_[3], s_[4], lp_dtype=torch.bfloat16),
-                  rows * C1 * 16, launches=24)
-    by = rows * C1 * 16.0
-    extra.append({"kernel": "lnv2_bwd_kernel [100352,128] bf16 dy, fp32 stream", "bound": "hbm", "achieved": round(by / t / 1e9, 1),
-                  "peak": peaks["hbm"], "unit": "GB/s", "frac": round(by / t / 1e9 / peaks["hbm"], 4)})
+
+    def hbm_entry(kernel, t, by, **kw):
+        e = {"kernel": kernel, "bound": "hbm", "achieved": round(by / t / 1e9, 1), "peak": hbm, "unit": "GB/s",
+             "frac": round(by / t / 1e9 / hbm, 4), "us": round(t * 1e6, 2), "algorithmic_bytes": by}
+        e.update(kw)
+        extra.append(e)
+
+    for rows, C1, tag in ((32 * 3136, 128, "stage 1"), (32 * 196, 512, "stage 3")):
+        t, by = kbench.time_layernorm_fwd(rows, C1, device)
+        hbm_entry(f"lnv2_fwd_kernel [{rows},{C1}] fp32 stream -> bf16 ({tag})", t, by)
+        t, by = kbench.time_layernorm_bwd(rows, C1, device)
+        hbm_entry(f"lnv2_bwd_kernel [{rows},{C1}] bf16 dy, fp32 stream in/out, bf16 copy out ({tag})", t, by)
+    t, by = kbench.time_patch_merge_ln(32, 56, 128, device)
+    hbm_entry("patch_merge_ln_fwd [32,56,56,128] fp32 -> [32,28,28,512] bf16 (gather + LayerNorm)", t, by)
+    t, by = kbench.time_patch_merge_ln(32, 56, 128, device, backward=True)
+    hbm_entry("patch_merge_ln_bwd [32,56,56,128] (scatter + LayerNorm backward)", t, by)
+    t, by = kbench.time_fpn_upadd(32, 56, 256, device)
+    hbm_entry("upadd_fwd FPN top-down p2 = skip + nearest_up(p3) [32,56,56,256] bf16", t, by)
+    t, by = kbench.time_fpn_merge(32, 56, 128, 4, device)
+    hbm_entry("merge_nhwc_fwd cat + Dropout2d scale -> [32,56,56,512] bf16", t, by)
+    t, by = kbench.time_groupnorm_relu(32, 56, 128, device)
+    hbm_entry("gn_stats + gn_relu_fwd GroupNorm(32)+ReLU [32,56,56,128] bf16 (pair)", t, by,
+              pair_moves_bytes=1.5 * by, frac_of_bytes_moved=round(1.5 * by / t / 1e9 / hbm, 4))
+    t, by = kbench.time_bilinear(32, 28, 128, device)
+    hbm_entry("bilinear2x_fwd [32,28,28,128] -> [32,56,56,128] bf16 (align_corners)", t, by)
+    for (H, Cc_, heads, tag) in ((56, 128, 4, "stage 1"), (14, 512, 16, "stage 3")):
+        t, by, fl_ = kbench.time_window_attn(32, H, Cc_, heads, 7, 3, device)
+        hbm_entry(f"window attention fwd {tag} (shifted) bf16, stand-alone (q,k,v in / o out)", t, by,
+                  attn_only_tflops=round(fl_ / t / 1e12, 2), attn_only_frac_of_bf16_peak=round(fl_ / t / 1e12 / tc, 4),
+                  padded_mma_flops_factor=round((64 / 49) ** 2, 3))
+        t, by, fl_ = kbench.time_window_attn(32, H, Cc_, heads, 7, 3, device, backward=True)
+        hbm_entry(f"window attention bwd {tag} (shifted) bf16, stand-alone", t, by,
+                  attn_only_tflops=round(fl_ / t / 1e12, 2), attn_only_frac_of_bf16_peak=round(fl_ / t / 1e12 / tc, 4))
     res["roofline_extra"] = extra
+    torch.cuda.empty_cache()
     return res
 
 
@@ -309,13 +318,23 @@ def run_native(args):
     peaks = _peaks()
     L = _lib.lib()
 
-    B, S = args.batch, 224
-    cfg = m.swin_b_27task(batch_size=B, image_size=S, mixed_precision=True)
+    wl = WORKLOADS[args.workload]
+    B, S = (args.batch or wl["batch"]), wl["image"]
+    training = wl["train"]
+    cfg = m.make_config(wl["encoder"], S, B, mixed_precision=True)
     torch.manual_seed(0)                       # identical replicas on every rank
-    model = m.build_model(cfg, precision="bf16").to(dev).train()
+    model = m.build_model(cfg, precision="bf16").to(dev)
+    model = model.train() if training else model.eval()
     opt = m.build_flat_optimizer(model, cfg)
     loss_fns, loss_w = m.build_all_losses(cfg)
     trainer = m.DataParallelTrainer(model, opt, loss_fns, loss_w, gradient_clip=1.0)
+    if not training:
+        class _Infer:                          # configs[4]: model.eval() + no_grad forward through the task's head
+            def step(self, x, y, tid):
+                with torch.no_grad():
+                    out = model(x, tid)
+                return out.float().mean()      # a scalar to read back in the e2e leg
+        trainer = _Infer()
     tcfg = {t["task_id"]: t for t in cfg.get_task_configs()}
     task_ids = list(tcfg.keys())
     n_total = args.warmup + args.steps
@@ -416,10 +435,10 @@ def run_native(args):
     except Exception:
         pass
     line = {
-        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": wl["metric"], "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": world * B, "image_size": S, "parallelism": f"dp{world}",
+        "config": {"workload": wl["name"], "global_batch": world * B, "image_size": S, "parallelism": f"dp{world}",
                    "task_sequence": "random.Random(42).choice over the 27 task ids per step (MultiTaskUniformSampler)",
                    "l2": f"no explicit flush: each step streams a {ws_gb} GB activation workspace plus 0.35 GB of weights, "
                          "far beyond the 126 MB L2",
@@ -428,14 +447,18 @@ def run_native(args):
                 "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "train_flops_per_img": 105.9e9,
-        "model_tflops": round(value * 105.9e9 / 1e12 / world, 1),
     }
-    if world == 1:
-        line.update(_kernel_rooflines(peaks, dev))
+    if wl["train_gf_per_img"]:
+        line["train_flops_per_img"] = wl["train_gf_per_img"] * 1e9
+        line["model_tflops"] = round(value * wl["train_gf_per_img"] * 1e9 / 1e12 / world, 1)
+    if world == 1 and args.workload == "swin_b_224":
+        if not args.no_rooflines:
+            del trainer, opt, model
+            torch.cuda.empty_cache()
+            line.update(_kernel_rooflines(peaks, dev))
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_sample()
-    else:
+            line["cpu_baseline"] = cpu_baseline_sample(seq)
+    if world > 1:
         dist.destroy_process_group()
     print(json.dumps(line), flush=True)
     return 0
@@ -446,7 +469,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--batch", type=int, default=32, help="images per GPU (the headline config uses 32)")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: the workload's own, 32 for the headline config)")
+    ap.add_argument("--workload", default="swin_b_224", choices=sorted(WORKLOADS),
+                    help="swin_b_224 = BASELINE configs[1]/[2] (default, the headline metric); swin_l_384 = configs[3]; "
+                         "swin_b_512_infer = configs[4]")
+    ap.add_argument("--no-rooflines", action="store_true")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

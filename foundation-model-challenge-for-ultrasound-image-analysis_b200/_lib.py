@@ -81,6 +81,7 @@ SIGNATURES = {
     "mtus_nhwc_to_nchw": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_nchw_to_nhwc": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_patch_embed_im2col": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
+    "mtus_patch_embed_im2col_u8": (i32, [vp, _P(f32), _P(f32), vp, i32, i32, i32, i32, vp]),
     "mtus_window_attn_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mtus_window_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mtus_upsample_add_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
@@ -90,9 +91,14 @@ SIGNATURES = {
     "mtus_groupnorm_relu_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_groupnorm_act_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "mtus_groupnorm_act_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "mtus_batchnorm_stats": (i32, [vp, vp, vp, i64, i32, f32, i32, vp]),
+    "mtus_batchnorm_act_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
+    "mtus_batchnorm_act_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
     "mtus_bilinear2x_fwd": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_bilinear2x_bwd": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_fpn_merge_fwd": (i32, [_P(vp), i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "mtus_fpn_merge_film_fwd": (i32, [_P(vp), i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "mtus_film_grad": (i32, [vp, i32, _P(vp), i32, i32, vp, vp, vp, i32, i32, i32, i32, vp]),
     "mtus_fpn_merge_bwd": (i32, [vp, i32, i32, vp, _P(vp), i32, i32, i32, i32, i32, i32, vp]),
     "mtus_conv3x3_repack": (i32, [vp, vp, vp, i32, i32, i32, vp]),
     "mtus_conv3x3_unpack_grad": (i32, [vp, vp, i32, i32, vp]),
@@ -105,6 +111,7 @@ SIGNATURES = {
     "mtus_swin_param_info": (i32, [_P(SwinConfig), i32, C.c_char_p, _P(i64), _P(i32), _P(i64)]),
     "mtus_swin_feature_offset": (i64, [_P(SwinConfig), i32]),
     "mtus_swin_forward": (i32, [_P(SwinConfig), vp, i32, vp, vp, vp, vp, _P(vp), i32, i32, vp]),
+    "mtus_swin_forward_u8": (i32, [_P(SwinConfig), vp, _P(f32), _P(f32), vp, vp, vp, vp, _P(vp), i32, i32, vp]),
     "mtus_swin_backward": (i32, [_P(SwinConfig), vp, vp, vp, vp, _P(vp), i32, i32, vp, i32, i32, vp]),
     "mtus_graph_cache_stats": (None, [vp, vp, vp]),
     "mtus_swin_backward_blocks": (i32, [_P(SwinConfig), vp, vp, vp, vp, _P(vp), i32, i32, vp, i32, i32, vp]),
@@ -112,6 +119,8 @@ SIGNATURES = {
     "mtus_fpn_workspace_bytes": (i64, [_P(FpnConfig)]),
     "mtus_fpn_param_info": (i32, [_P(FpnConfig), i32, C.c_char_p, _P(i64), _P(i32), _P(i64)]),
     "mtus_fpn_forward": (i32, [_P(FpnConfig), _P(vp), i32, i32, vp, vp, vp, vp, i32, vp]),
+    "mtus_fpn_forward_film": (i32, [_P(FpnConfig), _P(vp), i32, i32, vp, vp, vp, vp, vp, i32, vp]),
+    "mtus_fpn_tower_output_offset": (i64, [_P(FpnConfig), i32]),
     "mtus_fpn_backward": (i32, [_P(FpnConfig), _P(vp), i32, i32, vp, vp, vp, vp, i32, _P(vp), i32, i32, vp, vp]),
 }
 

@@ -322,6 +322,52 @@ extern "C" int mtus_groupnorm_act_bwd(const void* dy, const void* x, const void*
   return MTUS_OK;
 }
 
+// ---- BatchNorm2d + activation over NHWC rows [M = B*H*W, C] (the reference's baseline detection head stacks
+// Conv3x3 -> BatchNorm2d -> ReLU twice, code/models/heads.py:404-428) ---------------------------------
+// Per-channel statistics over all rows are GroupNorm statistics with one "sample" of M pixels and one group per channel,
+// so the GroupNorm kernels above serve unchanged: stats (two-pass, centred), fused normalise + activation, and the
+// two-kernel backward.  training = 0 (running statistics): the statistics are constants, so the backward's mean terms
+// (ws) are zeroed between the reduce and the apply kernel; dgamma / dbeta are the same sums either way.
+extern "C" int mtus_batchnorm_stats(const void* x, float* mean, float* rstd, int64_t M, int C, float eps, int dtype, void* stream) {
+  MTUS_CHECK_ARG(M >= 0 && M < (1ll << 31));
+  return mtus_groupnorm_stats(x, mean, rstd, 1, (int)M, C, C, eps, dtype, stream);
+}
+
+extern "C" int mtus_batchnorm_act_fwd(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                                      void* y, int64_t M, int C, int act, int dtype, void* stream) {
+  MTUS_CHECK_ARG(M >= 0 && M < (1ll << 31));
+  return mtus_groupnorm_act_fwd(x, mean, rstd, gamma, beta, y, 1, (int)M, C, C, act, dtype, stream);
+}
+
+extern "C" int mtus_batchnorm_act_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* rstd,
+                                      const float* gamma, const float* beta, void* dx, float* dgamma, float* dbeta, float* ws,
+                                      int64_t M, int C, int act, int training, int dtype, void* stream) {
+  MTUS_CHECK_ARG(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && ws && (act == 0 || act == 1));
+  MTUS_CHECK_ARG(act == 0 ? y != nullptr : beta != nullptr);
+  MTUS_CHECK_ARG(C % 8 == 0 && C / 8 <= 256 && M >= 0 && M < (1ll << 31));
+  if (M == 0) return MTUS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = 1, HW = (int)M, G = C;
+  cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(float) * 2 * B * G, st);
+  if (e != cudaSuccess) return (int)e;
+  int ppc; const int chunks = gn_chunks(B, HW, C, ppc);
+  dim3 grid(chunks, B);
+  const size_t sm = sizeof(float) * 4 * C;
+  const int64_t total = (int64_t)HW * (C / 8);
+#define BN_BWD(T_, ACT_)                                                                                                                  \
+  {                                                                                                                                       \
+    gn_bwd_reduce_kernel<T_, ACT_><<<grid, 256, sm, st>>>((const T_*)dy, (const T_*)x, (const T_*)y, mean, rstd, gamma, beta, ws, dgamma, dbeta, B, HW, C, G, ppc); \
+    if (!training) { e = cudaMemsetAsync(ws, 0, sizeof(float) * 2 * B * G, st); if (e != cudaSuccess) return (int)e; }                   \
+    gn_bwd_apply_kernel<T_, ACT_><<<grid_for(total, 256), 256, 0, st>>>((const T_*)dy, (const T_*)x, (const T_*)y, mean, rstd, gamma, beta, ws, (T_*)dx, total, B, HW, C / 8, G, C / G); \
+  }
+  if (dtype == MTUS_F32) { if (act == 0) BN_BWD(float, 0) else BN_BWD(float, 1) }
+  else if (dtype == MTUS_BF16) { if (act == 0) BN_BWD(bf16, 0) else BN_BWD(bf16, 1) }
+  else return MTUS_ERR_UNSUPPORTED;
+#undef BN_BWD
+  MTUS_LAUNCH_STATUS_N(2);
+  return MTUS_OK;
+}
+
 extern "C" int mtus_groupnorm_relu_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* rstd,
                                        const float* gamma, void* dx, float* dgamma, float* dbeta, float* ws, int B, int HW,
                                        int C, int G, int dtype, void* stream) {
@@ -432,7 +478,7 @@ struct MergeOutPtrs { void* p[4]; };
 
 template <typename T, typename TO>
 __global__ void __launch_bounds__(256) merge_fwd_kernel(MergePtrs src, int nsrc, int cat, const float* __restrict__ chanscale,
-                                                        TO* __restrict__ out, int HW, int C) {
+                                                        const float* __restrict__ chanshift, TO* __restrict__ out, int HW, int C) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int Cout = cat ? nsrc * C : C;
@@ -457,7 +503,8 @@ __global__ void __launch_bounds__(256) merge_fwd_kernel(MergePtrs src, int nsrc,
     if (r < HW && c < C) {
       const int cg = cat ? s * C + c : c;
       const float f = chanscale ? __ldg(chanscale + (int64_t)b * Cout + cg) : 1.0f;
-      IO<TO>::st(out + ((int64_t)b * Cout + cg) * HW + r, tile[tx][ty + i * 8] * f);
+      const float sh = chanshift ? __ldg(chanshift + cg) : 0.0f;
+      IO<TO>::st(out + ((int64_t)b * Cout + cg) * HW + r, fmaf(tile[tx][ty + i * 8], f, sh));
     }
   }
 }
@@ -496,8 +543,8 @@ __global__ void __launch_bounds__(256) merge_bwd_kernel(const TI* __restrict__ d
 
 // channels-last output: out[b, r, cg] = scale[b, cg] * src[s][b, r, c]  (8-wide vectors, coalesced on both sides)
 template <typename T, typename TO>
-__global__ void merge_nhwc_fwd_kernel(MergePtrs src, int nsrc, int cat, const float* __restrict__ chanscale, TO* __restrict__ out,
-                                      int64_t total, int HW, int C) {
+__global__ void merge_nhwc_fwd_kernel(MergePtrs src, int nsrc, int cat, const float* __restrict__ chanscale,
+                                      const float* __restrict__ chanshift, TO* __restrict__ out, int64_t total, int HW, int C) {
   const int Cout = cat ? nsrc * C : C, C8 = Cout / 8;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -519,6 +566,11 @@ __global__ void merge_nhwc_fwd_kernel(MergePtrs src, int nsrc, int cat, const fl
       float f[8]; IO<float>::load8(chanscale + b * Cout + cg, f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] *= f[j];
+    }
+    if (chanshift) {                                  // FiLM shift beta[c] (the scale gamma[c] is folded into chanscale)
+      float sh[8]; IO<float>::load8(chanshift + cg, sh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += sh[j];
     }
     IO<TO>::store8(out + pix * Cout + cg, v);
   }
@@ -549,8 +601,8 @@ __global__ void merge_nhwc_bwd_kernel(const TI* __restrict__ dout, int nsrc, int
   }
 }
 
-extern "C" int mtus_fpn_merge_fwd(const void* const* srcs, int nsrc, int policy_cat, const float* chanscale, void* out,
-                                  int B, int HW, int C, int dtype, int out_f32, int out_nhwc, void* stream) {
+extern "C" int mtus_fpn_merge_film_fwd(const void* const* srcs, int nsrc, int policy_cat, const float* chanscale,
+                                       const float* chanshift, void* out, int B, int HW, int C, int dtype, int out_f32, int out_nhwc, void* stream) {
   MTUS_CHECK_ARG(srcs && out && nsrc >= 1 && nsrc <= 4 && C % 32 == 0 && B <= 65535);
   if (B == 0) return MTUS_OK;
   MergePtrs mp{};
@@ -560,18 +612,99 @@ extern "C" int mtus_fpn_merge_fwd(const void* const* srcs, int nsrc, int policy_
   if (out_nhwc) {
     const int64_t total = (int64_t)B * HW * ((policy_cat ? nsrc * C : C) / 8);
     const int g1 = grid_for(total, 256);
-    if (dtype == MTUS_F32) merge_nhwc_fwd_kernel<float, float><<<g1, 256, 0, st>>>(mp, nsrc, policy_cat, chanscale, (float*)out, total, HW, C);
-    else if (dtype == MTUS_BF16 && out_f32) merge_nhwc_fwd_kernel<bf16, float><<<g1, 256, 0, st>>>(mp, nsrc, policy_cat, chanscale, (float*)out, total, HW, C);
-    else if (dtype == MTUS_BF16) merge_nhwc_fwd_kernel<bf16, bf16><<<g1, 256, 0, st>>>(mp, nsrc, policy_cat, chanscale, (bf16*)out, total, HW, C);
+    if (dtype == MTUS_F32) merge_nhwc_fwd_kernel<float, float><<<g1, 256, 0, st>>>(mp, nsrc, policy_cat, chanscale, chanshift, (float*)out, total, HW, C);
+    else if (dtype == MTUS_BF16 && out_f32) merge_nhwc_fwd_kernel<bf16, float><<<g1, 256, 0, st>>>(mp, nsrc, policy_cat, chanscale, chanshift, (float*)out, total, HW, C);
+    else if (dtype == MTUS_BF16) merge_nhwc_fwd_kernel<bf16, bf16><<<g1, 256, 0, st>>>(mp, nsrc, policy_cat, chanscale, chanshift, (bf16*)out, total, HW, C);
     else return MTUS_ERR_UNSUPPORTED;
     MTUS_LAUNCH_STATUS();
     return MTUS_OK;
   }
-  if (dtype == MTUS_F32) merge_fwd_kernel<float, float><<<grid, 256, 0, st>>>(mp, nsrc, policy_cat, chanscale, (float*)out, HW, C);
+  if (dtype == MTUS_F32) merge_fwd_kernel<float, float><<<grid, 256, 0, st>>>(mp, nsrc, policy_cat, chanscale, chanshift, (float*)out, HW, C);
   else if (dtype == MTUS_BF16) {
-    if (out_f32) merge_fwd_kernel<bf16, float><<<grid, 256, 0, st>>>(mp, nsrc, policy_cat, chanscale, (float*)out, HW, C);
-    else merge_fwd_kernel<bf16, bf16><<<grid, 256, 0, st>>>(mp, nsrc, policy_cat, chanscale, (bf16*)out, HW, C);
+    if (out_f32) merge_fwd_kernel<bf16, float><<<grid, 256, 0, st>>>(mp, nsrc, policy_cat, chanscale, chanshift, (float*)out, HW, C);
+    else merge_fwd_kernel<bf16, bf16><<<grid, 256, 0, st>>>(mp, nsrc, policy_cat, chanscale, chanshift, (bf16*)out, HW, C);
   } else return MTUS_ERR_UNSUPPORTED;
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}
+
+extern "C" int mtus_fpn_merge_fwd(const void* const* srcs, int nsrc, int policy_cat, const float* chanscale, void* out,
+                                  int B, int HW, int C, int dtype, int out_f32, int out_nhwc, void* stream) {
+  return mtus_fpn_merge_film_fwd(srcs, nsrc, policy_cat, chanscale, nullptr, out, B, HW, C, dtype, out_f32, out_nhwc, stream);
+}
+
+// FiLM parameter gradients for out = gamma[c] * (drop[b,c] * merged[b,r,c]) + beta[c] (code/models/film_layer.py:94-99 applied
+// to the decoder output, multitask_model.py:214-216), one pass over dout and the merge sources (both NHWC):
+//   dbeta[c] += sum_{b,r} dout[b,r,c]        dgamma[c] += sum_{b,r} dout[b,r,c] * drop[b,c] * merged[b,r,c]
+// Block = (Cout/8 vector lanes) x (256 / (Cout/8) pixel lanes); per-thread accumulators, shared-memory fold, one atomic per
+// channel per block.
+template <typename T, typename TI>
+__global__ void __launch_bounds__(256) film_grad_kernel(const TI* __restrict__ dout, MergePtrs src, int nsrc, int cat,
+                                                        const float* __restrict__ dropscale, float* __restrict__ dgamma,
+                                                        float* __restrict__ dbeta, int64_t npix, int HW, int C, int pix_per_block) {
+  extern __shared__ float sred[];   // [2][Cout]
+  const int Cout = cat ? nsrc * C : C, C8 = Cout / 8;
+  const int v = threadIdx.x % C8, pl = threadIdx.x / C8, npl = 256 / C8;
+  const int cg = v * 8;
+  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block, p1 = min(npix, p0 + pix_per_block);
+  float ag[8], ab[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) ag[k] = ab[k] = 0.f;
+  if (pl < npl) {
+    for (int64_t pix = p0 + pl; pix < p1; pix += npl) {
+      float d[8], x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      IO<TI>::load8(dout + pix * Cout + cg, d);
+      if (cat) {
+        const int s_ = cg / C, c = cg - s_ * C;
+        IO<T>::load8(reinterpret_cast<const T*>(src.p[s_]) + pix * C + c, x);
+      } else {
+        for (int k = 0; k < nsrc; ++k) {
+          float t[8]; IO<T>::load8(reinterpret_cast<const T*>(src.p[k]) + pix * C + cg, t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] += t[j];
+        }
+      }
+      if (dropscale) {
+        float f[8]; IO<float>::load8(dropscale + (pix / HW) * Cout + cg, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] *= f[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { ag[j] = fmaf(d[j], x[j], ag[j]); ab[j] += d[j]; }
+    }
+  }
+  for (int c = threadIdx.x; c < 2 * Cout; c += 256) sred[c] = 0.f;
+  __syncthreads();
+  if (pl < npl) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { atomicAdd(&sred[cg + j], ag[j]); atomicAdd(&sred[Cout + cg + j], ab[j]); }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Cout; c += 256) { atomicAdd(dgamma + c, sred[c]); atomicAdd(dbeta + c, sred[Cout + c]); }
+}
+
+extern "C" int mtus_film_grad(const void* dout, int dout_f32, const void* const* srcs, int nsrc, int policy_cat,
+                              const float* dropscale, float* dgamma, float* dbeta, int B, int HW, int C, int dtype, void* stream) {
+  MTUS_CHECK_ARG(dout && srcs && dgamma && dbeta && nsrc >= 1 && nsrc <= 4 && C % 8 == 0);
+  const int Cout = policy_cat ? nsrc * C : C;
+  MTUS_CHECK_ARG(Cout / 8 <= 256);
+  if (B == 0) return MTUS_OK;
+  MergePtrs mp{};
+  for (int i = 0; i < nsrc; ++i) { MTUS_CHECK_ARG(srcs[i]); mp.p[i] = srcs[i]; }
+  const int64_t npix = (int64_t)B * HW;
+  const int npl = 256 / (Cout / 8);
+  int64_t blocks = 148 * 4;
+  const int64_t maxb = (npix + npl * 4 - 1) / (npl * 4);
+  if (blocks > maxb) blocks = maxb;
+  if (blocks < 1) blocks = 1;
+  const int ppb = (int)((npix + blocks - 1) / blocks);
+  const int grid = (int)((npix + ppb - 1) / ppb);
+  const size_t sm = sizeof(float) * 2 * Cout;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MTUS_F32) film_grad_kernel<float, float><<<grid, 256, sm, st>>>((const float*)dout, mp, nsrc, policy_cat, dropscale, dgamma, dbeta, npix, HW, C, ppb);
+  else if (dtype == MTUS_BF16 && dout_f32) film_grad_kernel<bf16, float><<<grid, 256, sm, st>>>((const float*)dout, mp, nsrc, policy_cat, dropscale, dgamma, dbeta, npix, HW, C, ppb);
+  else if (dtype == MTUS_BF16) film_grad_kernel<bf16, bf16><<<grid, 256, sm, st>>>((const bf16*)dout, mp, nsrc, policy_cat, dropscale, dgamma, dbeta, npix, HW, C, ppb);
+  else return MTUS_ERR_UNSUPPORTED;
   MTUS_LAUNCH_STATUS();
   return MTUS_OK;
 }

@@ -154,6 +154,22 @@ static int fpn_forward_body(const mtus_fpn_config* cfg, const void* const* feats
 extern "C" int mtus_fpn_forward(const mtus_fpn_config* cfg, const void* const* feats, int feats_layout, int feats_f32,
                                 const float* params, const float* chanscale, void* workspace, void* out, int out_f32,
                                 void* stream) {
+  return mtus_fpn_forward_film(cfg, feats, feats_layout, feats_f32, params, chanscale, nullptr, workspace, out, out_f32, stream);
+}
+
+extern "C" int64_t mtus_fpn_tower_output_offset(const mtus_fpn_config* cfg, int level) {
+  Plan p;
+  if (!build_plan(cfg, p) || level < 0 || level > 3) return -1;
+  return (int64_t)p.tower[level].back().v;
+}
+
+// Forward with the FiLM epilogue of the reference's MultiTaskModel (multitask_model.py:214-216, film_layer.py:94-99) fused into
+// the merge kernel: out = chanscale[b,c] * merged + chanshift[c], where the caller folds gamma[c] into chanscale (times the
+// Dropout2d scale when active) and passes beta as chanshift.  Backward is mtus_fpn_backward unchanged (it re-reads the folded
+// scale from the workspace); mtus_film_grad yields dgamma / dbeta.
+extern "C" int mtus_fpn_forward_film(const mtus_fpn_config* cfg, const void* const* feats, int feats_layout, int feats_f32,
+                                     const float* params, const float* chanscale, const float* chanshift, void* workspace,
+                                     void* out, int out_f32, void* stream) {
   Plan p;
   if (!build_plan(cfg, p)) return MTUS_ERR_BAD_ARG;
   MTUS_CHECK_ARG(feats && params && workspace && out);
@@ -178,7 +194,7 @@ extern "C" int mtus_fpn_forward(const mtus_fpn_config* cfg, const void* const* f
   if (!merged[0]) {   // graph replay: the body did not run on the host; the tower outputs are fixed workspace slots
     for (int i = 0; i < 4; ++i) merged[i] = wsb + p.tower[i].back().v;
   }
-  RUN(mtus_fpn_merge_fwd(merged, 4, p.cat, cs, out, p.B, p.size[0] * p.size[0], p.S, p.dtype, out_f32 & 1, (out_f32 >> 1) & 1, stream));
+  RUN(mtus_fpn_merge_film_fwd(merged, 4, p.cat, cs, chanshift, out, p.B, p.size[0] * p.size[0], p.S, p.dtype, out_f32 & 1, (out_f32 >> 1) & 1, stream));
   return MTUS_OK;
 }
 

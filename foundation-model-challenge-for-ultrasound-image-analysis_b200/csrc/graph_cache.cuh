@@ -23,7 +23,18 @@ constexpr size_t kMaxGraphs = 48;
 
 inline bool graphs_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MTUS_GRAPHS"); v = (e && atoi(e) == 0) ? 0 : 1; const char* t = getenv("MTUS_TIME_KERNELS"); if (t && atoi(t) != 0) v = 0; }
+  if (v < 0) {
+    const char* e = getenv("MTUS_GRAPHS");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+    const char* t = getenv("MTUS_TIME_KERNELS");
+    if (t && atoi(t) != 0) v = 0;
+    // a kernel profiler (ncu / nsys injection) wants to see kernel launches, not graph launches, and replays each kernel:
+    // run the plain schedule under it unless MTUS_GRAPHS=1 insists
+    if (!e) {
+      static const char* inj[] = {"CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR", "NV_NSIGHT_INJECTION_TRANSPORT_TYPE", "NSYS_PROFILING_SESSION_ID"};
+      for (const char* n : inj) { const char* x = getenv(n); if (x && *x) v = 0; }
+    }
+  }
   return v == 1;
 }
 

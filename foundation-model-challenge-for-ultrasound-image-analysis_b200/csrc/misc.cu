@@ -252,6 +252,64 @@ extern "C" int mtus_patch_embed_im2col(const void* x, void* cols, int B, int H, 
   return MTUS_OK;
 }
 
+// ---- input pipeline fused into PatchEmbed's im2col: uint8 HWC image -> normalise -> GEMM operand ----------
+// Replaces albumentations Normalize(mean, std, max_pixel_value=255) + ToTensorV2 on the host and the fp32 NCHW batch the
+// reference copies to the device (/root/reference/code/train.py:35-44, 305): the device receives the raw uint8 [B,H,W,3]
+// batch (8x fewer host->device bytes than fp32 NCHW) and the normalised pixels are written straight into the im2col
+// operand -- the normalised image never exists in HBM.  v = (u8 - 255 mean_c) * (1 / (255 std_c)).
+// One thread = (patch, row pair): two 12-byte reads (4 pixels x 3 channels each), three 16/32-byte operand stores.
+struct NormConst { float sub[3], mul[3]; };
+
+template <typename TO>
+__global__ void patch_im2col_u8_kernel(const uint8_t* __restrict__ x, TO* __restrict__ cols, NormConst nc, int B, int H, int W) {
+  const int Ho = H / 4, Wo = W / 4;
+  const int64_t total = (int64_t)B * Ho * Wo * 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int pr = (int)(i & 1);                      // rows 2 pr, 2 pr + 1 of the 4x4 patch
+    const int64_t m = i >> 1;
+    const int ox = (int)(m % Wo); const int64_t t = m / Wo; const int oy = (int)(t % Ho); const int64_t b = t / Ho;
+    const uint8_t* p0 = x + (((b * H + oy * 4 + 2 * pr) * (int64_t)W) + ox * 4) * 3;
+    uint32_t r0[3], r1[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      r0[j] = __ldg(reinterpret_cast<const uint32_t*>(p0) + j);
+      r1[j] = __ldg(reinterpret_cast<const uint32_t*>(p0 + (int64_t)W * 3) + j);
+    }
+    const uint8_t* a0 = reinterpret_cast<const uint8_t*>(r0);
+    const uint8_t* a1 = reinterpret_cast<const uint8_t*>(r1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v[8];
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        v[px] = ((float)a0[px * 3 + c] - nc.sub[c]) * nc.mul[c];
+        v[4 + px] = ((float)a1[px * 3 + c] - nc.sub[c]) * nc.mul[c];
+      }
+      IO<TO>::store8(cols + (m * 8 + c * 2 + pr) * 8, v);     // k = c*16 + ky*4 + kx
+    }
+    const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    IO<TO>::store8(cols + (m * 8 + 6 + pr) * 8, z);           // k = 48..63: padding of the K = 48 GEMM
+  }
+}
+
+extern "C" int mtus_patch_embed_im2col_u8(const void* x_u8, const float* mean3, const float* std3, void* cols, int B, int H, int W,
+                                          int dtype, void* stream) {
+  MTUS_CHECK_ARG(x_u8 && mean3 && std3 && cols && B >= 0 && H % 4 == 0 && W % 4 == 0);
+  MTUS_CHECK_ARG((reinterpret_cast<uintptr_t>(x_u8) & 3) == 0);
+  if (B == 0) return MTUS_OK;
+  NormConst nc;
+  for (int c = 0; c < 3; ++c) { MTUS_CHECK_ARG(std3[c] > 0.f); nc.sub[c] = 255.0f * mean3[c]; nc.mul[c] = 1.0f / (255.0f * std3[c]); }
+  const int64_t total = (int64_t)B * (H / 4) * (W / 4) * 2;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = grid_for(total, 256);
+  if (dtype == MTUS_F32) patch_im2col_u8_kernel<float><<<g, 256, 0, st>>>((const uint8_t*)x_u8, (float*)cols, nc, B, H, W);
+  else if (dtype == MTUS_BF16) patch_im2col_u8_kernel<bf16><<<g, 256, 0, st>>>((const uint8_t*)x_u8, (bf16*)cols, nc, B, H, W);
+  else return MTUS_ERR_UNSUPPORTED;
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}
+
 // ---- fp32 gradient stream -> GEMM operand copy: y = T(rowscale[sample] * g), colsum += column sums of y ----------
 template <typename T>
 __global__ void __launch_bounds__(256) scale_cast_colsum_kernel(const float* __restrict__ g, const float* __restrict__ rowscale,

@@ -319,9 +319,28 @@ static int swin_forward_impl(const mtus_swin_config* cfg, const void* x, int x_i
 // step (the image batch, the drop-path draws): patch im2col into the workspace and a copy of the drop-path scales
 // into the workspace.  Everything after that reads only the parameter blocks and the workspace, so the body's CUDA
 // graph is keyed on addresses that stay put.
+static int swin_forward_any(const mtus_swin_config* cfg, const void* x, int x_kind, const float* norm_mean, const float* norm_std,
+                            const float* params, const void* params_lp, const float* droppath, void* workspace,
+                            void* const* feats, int feats_layout, int feats_f32, void* stream);
+
 extern "C" int mtus_swin_forward(const mtus_swin_config* cfg, const void* x, int x_is_f32, const float* params,
                                  const void* params_lp, const float* droppath, void* workspace, void* const* feats,
                                  int feats_layout, int feats_f32, void* stream) {
+  return swin_forward_any(cfg, x, x_is_f32 ? 1 : 0, nullptr, nullptr, params, params_lp, droppath, workspace, feats, feats_layout, feats_f32, stream);
+}
+
+// Same forward fed by the raw uint8 [B,S,S,3] (HWC) batch: Normalize(mean, std, max 255) + ToTensor + the NCHW fp32 batch of the
+// reference's input pipeline (code/train.py:35-44, 305) are fused into the patch-embed im2col.
+extern "C" int mtus_swin_forward_u8(const mtus_swin_config* cfg, const void* x_u8, const float* mean3, const float* std3,
+                                    const float* params, const void* params_lp, const float* droppath, void* workspace,
+                                    void* const* feats, int feats_layout, int feats_f32, void* stream) {
+  MTUS_CHECK_ARG(mean3 && std3);
+  return swin_forward_any(cfg, x_u8, 2, mean3, std3, params, params_lp, droppath, workspace, feats, feats_layout, feats_f32, stream);
+}
+
+static int swin_forward_any(const mtus_swin_config* cfg, const void* x, int x_kind, const float* norm_mean, const float* norm_std,
+                            const float* params, const void* params_lp, const float* droppath, void* workspace,
+                            void* const* feats, int feats_layout, int feats_f32, void* stream) {
   Plan p;
   if (!build_plan(cfg, p)) return MTUS_ERR_BAD_ARG;
   MTUS_CHECK_ARG(x && params && workspace && feats);
@@ -329,7 +348,9 @@ extern "C" int mtus_swin_forward(const mtus_swin_config* cfg, const void* x, int
   if (p.B == 0) return MTUS_OK;
   char* ws = reinterpret_cast<char*>(workspace);
   cudaStream_t st = (cudaStream_t)stream;
-  RUN(mtus_patch_embed_im2col(x, ws + p.cols, p.B, p.S, p.S, x_is_f32 || p.dtype == MTUS_F32, p.dtype, stream));
+  const int x_is_f32 = x_kind == 1;
+  if (x_kind == 2) RUN(mtus_patch_embed_im2col_u8(x, norm_mean, norm_std, ws + p.cols, p.B, p.S, p.S, p.dtype, stream));
+  else RUN(mtus_patch_embed_im2col(x, ws + p.cols, p.B, p.S, p.S, x_is_f32 || p.dtype == MTUS_F32, p.dtype, stream));
   const float* dp = nullptr;
   if (droppath) {
     int nblk = 0;

@@ -22,24 +22,25 @@ from .encoders import default_precision
 
 class _FpnFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, dec, nfeat, *args):
+    def forward(ctx, dec, nfeat, gamma, beta, *args):
         feats, params = args[:nfeat], args[nfeat:]
         needs_grad = any(ctx.needs_input_grad[2:])
         if not feats[0].is_cuda:
             raise RuntimeError("mtus_b200: the FPN decoder runs only on CUDA (sm_100a); there is no CPU fallback")
         with _lib.device_guard(feats[0]):
-            out, saved = dec._run_forward(list(feats), training_plan=needs_grad)
+            out, saved = dec._run_forward(list(feats), training_plan=needs_grad, film=(gamma, beta))
         ctx.dec, ctx.saved, ctx.nfeat = dec, saved, nfeat
-        ctx.needs = ctx.needs_input_grad[2:]
+        ctx.film_needs = ctx.needs_input_grad[2:4]
+        ctx.needs = ctx.needs_input_grad[4:]
         return out
 
     @staticmethod
     def backward(ctx, dout):
         dec = ctx.dec
         with _lib.device_guard(dout):
-            dfeats, flat_grad = dec._run_backward(ctx.saved, dout, ctx.needs[:ctx.nfeat])
+            dfeats, flat_grad, dgamma, dbeta = dec._run_backward(ctx.saved, dout, ctx.needs[:ctx.nfeat], ctx.film_needs)
         ctx.saved = None
-        return (None, None) + tuple(dfeats) + tuple(dec.grad_views(flat_grad, ctx.needs[ctx.nfeat:]))
+        return (None, None, dgamma, dbeta) + tuple(dfeats) + tuple(dec.grad_views(flat_grad, ctx.needs[ctx.nfeat:]))
 
 
 class FPNDecoder(FlatParamModule):
@@ -99,7 +100,7 @@ class FPNDecoder(FlatParamModule):
                     bound = 1.0 / math.sqrt(fan_in)
                     nn.init.uniform_(p, -bound, bound)
 
-    def _run_forward(self, feats: List[torch.Tensor], training_plan: bool):
+    def _run_forward(self, feats: List[torch.Tensor], training_plan: bool, film=(None, None)):
         L = _lib.lib()
         dt, tdt = precision_to_dtype(self.precision)
         x0 = feats[0]
@@ -124,25 +125,32 @@ class FPNDecoder(FlatParamModule):
         # training workspaces come from a pool and return to it when their backward has run (fixed addresses for
         # the executor's graph cache); inference workspaces stay per call
         ws = self._take_workspace(B, nbytes, x0.device) if training_plan else torch.empty(nbytes, dtype=torch.uint8, device=x0.device)
-        scale = None
+        scale = drop = None
         if self.training and self.p_drop > 0.0:     # Dropout2d: whole channels, scaled by 1/(1-p)
             keep = 1.0 - self.p_drop
-            scale = ((torch.rand(B, self.out_channels, device=x0.device) < keep).float() / keep).contiguous()
+            scale = drop = ((torch.rand(B, self.out_channels, device=x0.device) < keep).float() / keep).contiguous()
+        gamma, beta = film
+        shift = None
+        if gamma is not None:                       # FiLM epilogue: gamma folds into the per-(sample, channel) scale
+            g = gamma.detach().float().reshape(1, self.out_channels)
+            scale = (g.expand(B, -1) if drop is None else drop * g).contiguous()
+        if beta is not None:
+            shift = beta.detach().float().reshape(self.out_channels).contiguous()
         out_f32 = (self.output_dtype in ("fp32", "float32") or f32_in) and dt != _lib.F32
         odt = torch.float32 if (out_f32 or dt == _lib.F32) else tdt
         if self.channels_last_output:
             out = torch.empty(B, sizes[0], sizes[0], self.out_channels, dtype=odt, device=x0.device).permute(0, 3, 1, 2)
         else:
             out = torch.empty(B, self.out_channels, sizes[0], sizes[0], dtype=odt, device=x0.device)
-        _lib.check(L.mtus_fpn_forward(C.byref(cfg), _lib.ptr_array(feats), int(nhwc), int(f32_in), _lib.ptr(flat),
-                                      _lib.ptr(scale), _lib.ptr(ws), _lib.ptr(out), int(out_f32) | (2 if self.channels_last_output else 0),
-                                      _lib.stream_ptr()),
+        _lib.check(L.mtus_fpn_forward_film(C.byref(cfg), _lib.ptr_array(feats), int(nhwc), int(f32_in), _lib.ptr(flat),
+                                           _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(ws), _lib.ptr(out),
+                                           int(out_f32) | (2 if self.channels_last_output else 0), _lib.stream_ptr()),
                    "fpn_forward")
-        saved = (cfg, ws, feats, nhwc, f32_in, flat, scale, out_f32) if training_plan else None
+        saved = (cfg, ws, feats, nhwc, f32_in, flat, scale, out_f32, drop, gamma is not None) if training_plan else None
         return out, saved
 
-    def _run_backward(self, saved, dout, feat_needs):
-        cfg, ws, feats, nhwc, f32_in, flat, scale, out_f32 = saved
+    def _run_backward(self, saved, dout, feat_needs, film_needs=(False, False)):
+        cfg, ws, feats, nhwc, f32_in, flat, scale, out_f32, drop, has_film = saved
         L = _lib.lib()
         dt, tdt = precision_to_dtype(self.precision)
         want_out = torch.float32 if (out_f32 or dt == _lib.F32) else tdt
@@ -170,13 +178,35 @@ class FPNDecoder(FlatParamModule):
                                        _lib.ptr(scale), _lib.ptr(ws), _lib.ptr(dout), int(want_out == torch.float32 and dt != _lib.F32) | (2 if dout_nhwc else 0),
                                        _lib.ptr_array(dfeats), int(nhwc), int(f32_in), _lib.ptr(flat_grad), _lib.stream_ptr()),
                    "fpn_backward")
+        dgamma = dbeta = None
+        if has_film and any(film_needs):
+            # dgamma[c] = sum dout * drop[b,c] * merged, dbeta[c] = sum dout: one pass over dout and the four tower outputs
+            # (still in the workspace); needs the gradient channels-last, which is what the heads hand back
+            if not dout_nhwc:
+                dout = dout.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+            es = 2 if dt == _lib.BF16 else 4
+            S2, Sc = int(feats[0].shape[2]), self.segmentation_channels
+            srcs = []
+            for lvl in range(4):
+                off = L.mtus_fpn_tower_output_offset(C.byref(cfg), lvl)
+                srcs.append(ws[off:off + cfg.batch * S2 * S2 * Sc * es])
+            dgamma = torch.zeros(self.out_channels, dtype=torch.float32, device=flat.device)
+            dbeta = torch.zeros_like(dgamma)
+            _lib.check(L.mtus_film_grad(_lib.ptr(dout), int(want_out == torch.float32 and dt != _lib.F32), _lib.ptr_array(srcs), 4,
+                                        int(self.merge_policy == "cat"), _lib.ptr(drop), _lib.ptr(dgamma), _lib.ptr(dbeta), cfg.batch,
+                                        S2 * S2, Sc, dt, _lib.stream_ptr()), "film_grad")
+            dgamma = dgamma if film_needs[0] else None
+            dbeta = dbeta if film_needs[1] else None
         self._last_flat_grad = flat_grad
         self._return_workspace(cfg.batch, ws)
-        return [g if n else None for g, n in zip(dfeats, feat_needs)], flat_grad
+        return [g if n else None for g, n in zip(dfeats, feat_needs)], flat_grad, dgamma, dbeta
 
-    def forward(self, features: List[torch.Tensor]) -> torch.Tensor:
+    def forward(self, features: List[torch.Tensor], film=None) -> torch.Tensor:
+        """``film = (gamma [C_out], beta [C_out] | None)`` applies the reference's FiLM modulation of the decoder output
+        (film_layer.py:94-99) inside the merge kernel -- no extra pass over the [B, C_out, H/4, W/4] map."""
         feats = list(features)[-4:]
-        return _FpnFn.apply(self, len(feats), *feats, *self.ordered_params())
+        gamma, beta = film if film is not None else (None, None)
+        return _FpnFn.apply(self, len(feats), gamma, beta, *feats, *self.ordered_params())
 
 
 def build_fpn_decoder(encoder, config, decoder_type="seg", precision: Optional[str] = None,

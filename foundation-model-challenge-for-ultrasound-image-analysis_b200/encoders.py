@@ -100,6 +100,9 @@ class SwinCore(FlatParamModule):
         self.output_dtype = output_dtype          # None -> activation dtype; 'fp32' -> fp32 NCHW features
         self.zero_copy_features = zero_copy_features
         self.drop_path_rate = float(drop_path_rate)
+        # Normalize(mean, std, max_pixel_value=255) of the reference's input pipeline (code/train.py:35-44): applied by the
+        # kernels when forward() is handed the raw uint8 [B,H,W,3] batch; ImageNet statistics by default
+        self.input_mean, self.input_std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
         self.backend = _lib.BACKEND_AUTO
         nblk = sum(self.depths)
         self._dpr = torch.linspace(0, self.drop_path_rate, nblk).tolist()   # timm: linspace(0, rate, sum(depths))
@@ -166,7 +169,11 @@ class SwinCore(FlatParamModule):
     def _run_forward(self, x: torch.Tensor, training_plan: bool):
         if not x.is_cuda:
             raise RuntimeError("mtus_b200: the Swin encoder runs only on CUDA (sm_100a); there is no CPU fallback")
-        B, Cin, H, W = x.shape
+        x_u8 = x.dtype == torch.uint8
+        if x_u8:                                   # raw HWC batch: normalisation fused into the patch-embed operand
+            B, H, W, Cin = x.shape
+        else:
+            B, Cin, H, W = x.shape
         if Cin != 3:
             raise ValueError("expected a 3-channel image")
         # timm strict image size (encoders.py:58 threads img_size through for this reason)
@@ -178,7 +185,7 @@ class SwinCore(FlatParamModule):
         if flat.device != x.device:
             raise RuntimeError("mtus_b200: encoder parameters and input live on different devices")
         x_is_f32 = x.dtype == torch.float32
-        if not x_is_f32 and x.dtype != tdt:
+        if not x_u8 and not x_is_f32 and x.dtype != tdt:
             x = x.to(tdt)
         x = x.contiguous()
         cfg = self._cfg(B, training_plan)
@@ -203,9 +210,15 @@ class SwinCore(FlatParamModule):
                 r, ch = self.resolutions[i], self.embed_dim * 2 ** i
                 feats.append(torch.empty(B, ch, r, r, dtype=torch.float32 if out_f32 else tdt, device=x.device))
             feat_ptrs = feats
-        _lib.check(L.mtus_swin_forward(C.byref(cfg), _lib.ptr(x), int(x_is_f32), _lib.ptr(flat), _lib.ptr(lp), _lib.ptr(dp),
-                                       _lib.ptr(ws), _lib.ptr_array(feat_ptrs), 0, int(out_f32), _lib.stream_ptr()),
-                   "swin_forward")
+        if x_u8:
+            mean3, std3 = (C.c_float * 3)(*self.input_mean), (C.c_float * 3)(*self.input_std)
+            _lib.check(L.mtus_swin_forward_u8(C.byref(cfg), _lib.ptr(x), mean3, std3, _lib.ptr(flat), _lib.ptr(lp), _lib.ptr(dp),
+                                              _lib.ptr(ws), _lib.ptr_array(feat_ptrs), 0, int(out_f32), _lib.stream_ptr()),
+                       "swin_forward_u8")
+        else:
+            _lib.check(L.mtus_swin_forward(C.byref(cfg), _lib.ptr(x), int(x_is_f32), _lib.ptr(flat), _lib.ptr(lp), _lib.ptr(dp),
+                                           _lib.ptr(ws), _lib.ptr_array(feat_ptrs), 0, int(out_f32), _lib.stream_ptr()),
+                       "swin_forward")
         if not feats:   # zero-copy: channels-last views of the stage outputs inside the workspace
             es = 2 if dt == _lib.BF16 else 4
             for i in range(4):
@@ -274,7 +287,8 @@ class SwinCore(FlatParamModule):
         return chunks
 
     def forward(self, x: torch.Tensor) -> List[torch.Tensor]:
-        """Returns the four stage outputs as [B,C,H,W] tensors (strides 4/8/16/32)."""
+        """Returns the four stage outputs as [B,C,H,W] tensors (strides 4/8/16/32).  ``x``: the normalised [B,3,H,W] batch
+        (fp32 / bf16, what the reference's DataLoader yields) or the raw uint8 [B,H,W,3] batch, normalised on the fly."""
         return list(_SwinFn.apply(self, x, *self.ordered_params()))
 
 
@@ -343,5 +357,8 @@ def build_encoder(config, task_ids=None, precision: Optional[str] = None, output
                                      moe_config=config.get("model.moe", {}), task_ids=task_ids, precision=precision,
                                      output_dtype=output_dtype, zero_copy_features=zero_copy_features,
                                      pretrained_path=encoder_weights if isinstance(encoder_weights, str) else None)
+    mean, std = config.get("data.augmentation.normalize.mean", None), config.get("data.augmentation.normalize.std", None)
+    if mean is not None and std is not None:
+        encoder.model.input_mean, encoder.model.input_std = tuple(float(v) for v in mean), tuple(float(v) for v in std)
     print(f"Loaded Swin Transformer: {encoder_name} (img_size={img_size}, precision={precision}, sm_100a kernels)")
     return encoder

@@ -1,4 +1,10 @@
-"""Task heads used to drive the hot path (PyTorch; OUT of the kernel scope -- SURVEY §2 row 6, §8f N1).
+"""Task heads used to drive the hot path.
+
+The conv stacks that hold the heads' FLOPs run on the library's engines: the segmentation head's
+Conv3x3(512->128) -> GroupNorm -> SiLU x2 and the baseline detection head's Conv3x3 -> BatchNorm2d -> ReLU x2 use the
+implicit-GEMM tcgen05 convolution (``mtus_conv3x3_{fwd,dgrad,wgrad}``) and the fused normalise + activation kernels
+(``mtus_groupnorm_act_*`` / ``mtus_batchnorm_act_*``) on channels-last activations; what remains in PyTorch is the final
+1x1 / k x k projection to 2-5 channels, the bilinear upsampling of the logits and the pooled Linear heads.
 
 Only the head types selected by ``configs/swin_b.yaml`` are provided (the "baseline" family of
 ``/root/reference/code/models/heads.py``): the standard segmentation head (heads.py:16-42, reached
@@ -66,6 +72,105 @@ class _GroupNormSiLUFn(torch.autograd.Function):
         return dx.permute(0, 3, 1, 2), dg, db, None, None
 
 
+class _Conv3x3Fn(torch.autograd.Function):
+    """3x3 convolution (padding 1, no bias) of a channels-last CUDA tensor on the library's implicit-GEMM engine (tcgen05
+    in bf16: the A operand is read through 4-D TMA boxes whose out-of-bounds zero fill is the padding) -- replaces
+    nn.Conv2d -> cuDNN for the heads' conv stacks (code/models/heads.py:16-42, 404-428)."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        from . import ops
+        xn = x.permute(0, 2, 3, 1)                       # NHWC view of a channels-last tensor
+        if not xn.is_contiguous():
+            xn = xn.contiguous()
+        wf, wd = ops.conv3x3_repack(weight.detach().float().contiguous(), xn.dtype)
+        y = ops.conv3x3_fwd(xn, wf)
+        ctx.save_for_backward(xn, wd)
+        ctx.wshape = weight.shape
+        ctx.wdtype = weight.dtype
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import ops
+        xn, wd = ctx.saved_tensors
+        dyn = dy.permute(0, 2, 3, 1)
+        if dyn.dtype != xn.dtype:
+            dyn = dyn.to(xn.dtype)
+        if not dyn.is_contiguous():
+            dyn = dyn.contiguous()
+        dx = ops.conv3x3_dgrad(dyn, wd).permute(0, 3, 1, 2) if ctx.needs_input_grad[0] else None
+        dw = ops.conv3x3_wgrad(dyn, xn).to(ctx.wdtype) if ctx.needs_input_grad[1] else None
+        return dx, dw
+
+
+def _native_conv_ok(x, conv):
+    return (x.is_cuda and x.dim() == 4 and x.dtype in (torch.bfloat16, torch.float32) and conv.kernel_size == (3, 3)
+            and conv.padding == (1, 1) and conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
+            and conv.bias is None and conv.in_channels % 64 == 0 and conv.out_channels % 64 == 0)
+
+
+def _conv3x3(x, conv):
+    """conv(x) on the native engine when the geometry allows it (the shipped heads always do), else the module itself."""
+    if _native_conv_ok(x, conv):
+        if torch.is_autocast_enabled() and x.dtype == torch.float32:
+            x = x.to(torch.get_autocast_gpu_dtype())
+        return _Conv3x3Fn.apply(x.contiguous(memory_format=torch.channels_last), conv.weight)
+    return conv(x)
+
+
+class _BatchNormReLUFn(torch.autograd.Function):
+    """relu(batch_norm(x)) for a channels-last CUDA tensor through the library's normalisation kernels: per-channel batch
+    statistics (training) or the running statistics (eval), one fused normalise + ReLU pass, two-kernel backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps):
+        from . import ops
+        xn = x.permute(0, 2, 3, 1)
+        if not xn.is_contiguous():
+            xn = xn.contiguous()
+        w, b = weight.float().contiguous(), bias.float().contiguous()
+        if training:
+            mean, rstd = ops.batchnorm_stats(xn, eps)
+            with torch.no_grad():
+                n = xn.numel() // xn.shape[-1]
+                var = rstd.pow(-2) - eps
+                running_mean.mul_(1.0 - momentum).add_(mean.to(running_mean.dtype), alpha=momentum)
+                running_var.mul_(1.0 - momentum).add_((var * (n / max(n - 1, 1))).to(running_var.dtype), alpha=momentum)
+        else:
+            mean = running_mean.float().contiguous()
+            rstd = (running_var.float() + eps).rsqrt().contiguous()
+        y = ops.batchnorm_relu_fwd(xn, mean, rstd, w, b)
+        ctx.save_for_backward(xn, y, mean, rstd, w)
+        ctx.training = bool(training)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import ops
+        xn, y, mean, rstd, w = ctx.saved_tensors
+        dyn = dy.permute(0, 2, 3, 1)
+        if dyn.dtype != xn.dtype:
+            dyn = dyn.to(xn.dtype)
+        if not dyn.is_contiguous():
+            dyn = dyn.contiguous()
+        dx, dg, db = ops.batchnorm_relu_bwd(dyn, xn, y, mean, rstd, w, training=ctx.training)
+        return dx.permute(0, 3, 1, 2), dg, db, None, None, None, None, None
+
+
+def _native_bn_ok(x, bn):
+    return (x.is_cuda and x.dim() == 4 and x.dtype in (torch.bfloat16, torch.float32) and x.shape[1] % 8 == 0
+            and x.shape[1] // 8 <= 256 and bn.affine and bn.track_running_stats and bn.momentum is not None)
+
+
+def _bn_relu(x, bn):
+    if _native_bn_ok(x, bn):
+        if bn.training:
+            bn.num_batches_tracked.add_(1)
+        return _BatchNormReLUFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.training, bn.momentum, bn.eps)
+    return torch.relu(bn(x))
+
+
 def _fused_gn_silu_ok(x, gn):
     return (x.is_cuda and x.dim() == 4 and x.dtype in (torch.bfloat16, torch.float32) and x.shape[1] % 8 == 0
             and x.shape[1] // 8 <= 256 and gn.affine and x.shape[0] <= 65535)
@@ -92,7 +197,7 @@ class SegmentationHead(nn.Module):
             while i < len(mods):
                 if (i + 2 < len(mods) and isinstance(mods[i], nn.Conv2d) and isinstance(mods[i + 1], nn.GroupNorm)
                         and isinstance(mods[i + 2], nn.SiLU)):
-                    x = mods[i](x)
+                    x = _conv3x3(x, mods[i])
                     gn = mods[i + 1]
                     if _fused_gn_silu_ok(x, gn):
                         x = _GroupNormSiLUFn.apply(x, gn.weight, gn.bias, gn.num_groups, gn.eps)
@@ -137,7 +242,22 @@ class BaselineFPNGridDetectionHead(nn.Module):
             nn.Conv2d(mid_channels, n_out, 1))
 
     def forward(self, fpn_features):
-        y = self.conv_block(fpn_features)
+        x = fpn_features
+        if x.is_cuda:
+            # Conv3x3 -> BatchNorm2d -> ReLU pairs on the native engines (same modules, same state-dict keys)
+            mods = list(self.conv_block)
+            i = 0
+            while i < len(mods):
+                if (i + 2 < len(mods) and isinstance(mods[i], nn.Conv2d) and isinstance(mods[i + 1], nn.BatchNorm2d)
+                        and isinstance(mods[i + 2], nn.ReLU)):
+                    x = _bn_relu(_conv3x3(x, mods[i]), mods[i + 1])
+                    i += 3
+                else:
+                    x = mods[i](x)
+                    i += 1
+            y = x
+        else:
+            y = self.conv_block(x)
         return torch.cat([torch.sigmoid(y[:, :4]), y[:, 4:]], dim=1)   # sigmoid on the 4 box channels
 
 

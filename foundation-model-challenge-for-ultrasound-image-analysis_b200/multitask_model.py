@@ -5,8 +5,9 @@ Kept: ``build_model(config)`` (:346), ``forward`` routing by task type incl. the
 unknown id (:187-188), ``use_fpn_for_{cls,reg}`` (:45-46), decoder aliasing (:294-303),
 ``get_trainable_parameters`` (:282), ``freeze_encoder/unfreeze_encoder`` (:333-343),
 ``get_moe_aux_loss/get_moe_stats`` (:310-331), attribute names (``encoder``, ``fpn_decoder_{seg,det,cls,reg}``,
-``heads``) and therefore the checkpoint keys.  Not provided (outside the hot path):
-FiLM, TaskPrompt2D, MoE -- requesting them raises.
+``heads``) and therefore the checkpoint keys.  FiLM on the decoder output (``model.use_film``, :52-79, 214-216) is provided with the
+modulation fused into the decoder's merge kernel.  Not provided (outside the hot path, SURVEY §2 rows
+9-10): TaskPrompt2D, MoE -- requesting them raises.
 """
 
 import torch
@@ -22,7 +23,7 @@ class MultiTaskModel(nn.Module):
         super().__init__()
         self.config = config
         self.task_configs = config.get_task_configs()
-        for key in ("model.use_film", "model.task_prompt.enabled", "model.moe.enabled"):
+        for key in ("model.task_prompt.enabled", "model.moe.enabled"):
             if config.get(key, False):
                 raise NotImplementedError(f"mtus_b200: {key} is outside the hot path and not provided")
         task_ids = [c["task_id"] for c in self.task_configs]
@@ -37,7 +38,12 @@ class MultiTaskModel(nn.Module):
         self.use_fpn_for_cls = config.get("model.decoder.use_fpn_for_classification", True)
         self.use_fpn_for_reg = config.get("model.decoder.use_fpn_for_regression", True)
         self.fpn_out_channels = self.fpn_decoder_seg.out_channels
-        self.use_film = False
+        # FiLM on the decoder output (multitask_model.py:52-79, 214-216): generators as in the reference, the modulation
+        # itself fused into the decoder's merge kernel
+        self.use_film = bool(config.get("model.use_film", False))
+        if self.use_film:
+            from .film import build_film
+            self.film_generator, self.film_layer = build_film(config, task_ids, self.fpn_out_channels)
         self.use_task_prompt = False
         self.use_moe = False
         self.heads = build_all_heads(self.task_configs, self.fpn_out_channels, encoder_channels,
@@ -58,16 +64,17 @@ class MultiTaskModel(nn.Module):
             raise ValueError(f"Unknown task_id: {task_id}")
         task_name = self.task_id_to_name[task_id]
         features = self.encoder(x, task_id) if getattr(self.encoder, "supports_task_id", False) else self.encoder(x)
+        film = self.film_generator(task_id) if self.use_film else None
         if task_name == "segmentation":
-            return self._head(task_id, self.fpn_decoder_seg(features))
+            return self._head(task_id, self.fpn_decoder_seg(features, film=film))
         if task_name == "detection":
-            return self._head(task_id, self.fpn_decoder_det(features))
+            return self._head(task_id, self.fpn_decoder_det(features, film=film))
         if task_name == "classification":
             if self.use_fpn_for_cls:
-                return self._head(task_id, self.fpn_decoder_cls(features))
+                return self._head(task_id, self.fpn_decoder_cls(features, film=film))
             return self._head(task_id, features)
         if self.use_fpn_for_reg:
-            return self._head(task_id, self.fpn_decoder_reg(features))
+            return self._head(task_id, self.fpn_decoder_reg(features, film=film))
         return self._head(task_id, features)
 
     def get_trainable_parameters(self):
@@ -81,6 +88,8 @@ class MultiTaskModel(nn.Module):
                                                                  self.fpn_decoder_cls):
             head_params += list(self.fpn_decoder_reg.parameters())
         head_params += list(self.heads.parameters())
+        # as in the reference (multitask_model.py:282-308) the FiLM generator's parameters are in NEITHER group: with
+        # grouped learning rates (train.py:184-190) they keep their initial values; model.parameters() still lists them
         return encoder_params, head_params
 
     def get_moe_aux_loss(self):

@@ -301,3 +301,31 @@ def nchw_to_nhwc(x):
     y = torch.empty(B, H, W, Cc, dtype=x.dtype, device=x.device)
     check(lib().mtus_nchw_to_nhwc(ptr(x), ptr(y), B, H * W, Cc, _dt(x), 0, stream_ptr()), "nchw_to_nhwc")
     return y
+
+
+def batchnorm_stats(x, eps=1e-5):
+    """Per-channel batch mean and 1/sqrt(biased var + eps) of NHWC rows x [..., C]."""
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    mean = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    check(lib().mtus_batchnorm_stats(ptr(x), ptr(mean), ptr(rstd), M, Cc, eps, _dt(x), stream_ptr()), "batchnorm_stats")
+    return mean, rstd
+
+
+def batchnorm_relu_fwd(x, mean, rstd, gamma, beta):
+    Cc = x.shape[-1]
+    y = torch.empty_like(x)
+    check(lib().mtus_batchnorm_act_fwd(ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(y), x.numel() // Cc, Cc, 0, _dt(x), stream_ptr()), "batchnorm_act_fwd")
+    return y
+
+
+def batchnorm_relu_bwd(dy, x, y, mean, rstd, gamma, training=True):
+    Cc = x.shape[-1]
+    dx = torch.empty_like(x)
+    dg = torch.zeros(Cc, dtype=torch.float32, device=x.device)
+    db = torch.zeros_like(dg)
+    ws = torch.empty(2 * Cc, dtype=torch.float32, device=x.device)
+    check(lib().mtus_batchnorm_act_bwd(ptr(dy), ptr(x), ptr(y), ptr(mean), ptr(rstd), ptr(gamma), None, ptr(dx), ptr(dg), ptr(db), ptr(ws),
+                                       x.numel() // Cc, Cc, 0, int(training), _dt(x), stream_ptr()), "batchnorm_act_bwd")
+    return dx, dg, db

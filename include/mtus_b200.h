@@ -184,6 +184,16 @@ int mtus_groupnorm_act_fwd(const void* x, const float* mean, const float* rstd, 
 int mtus_groupnorm_act_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* rstd,
                            const float* gamma, const float* beta, void* dx, float* dgamma, float* dbeta, float* ws,
                            int B, int HW, int C, int G, int act, int dtype, void* stream);
+/* BatchNorm2d + activation over NHWC rows [M = B*H*W, C] (act 0 = ReLU: the reference's baseline detection head,
+ * code/models/heads.py:404-428).  stats: per-channel batch mean and 1/sqrt(biased var + eps).  bwd:
+ * training = 1 differentiates through the batch statistics, training = 0 treats mean / rstd as constants (running
+ * statistics); dgamma / dbeta ACCUMULATED; ws: 2*C floats. */
+int mtus_batchnorm_stats(const void* x, float* mean, float* rstd, int64_t M, int C, float eps, int dtype, void* stream);
+int mtus_batchnorm_act_fwd(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                           void* y, int64_t M, int C, int act, int dtype, void* stream);
+int mtus_batchnorm_act_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* rstd,
+                           const float* gamma, const float* beta, void* dx, float* dgamma, float* dbeta, float* ws,
+                           int64_t M, int C, int act, int training, int dtype, void* stream);
 /* bilinear x2, align_corners=True, NHWC */
 int mtus_bilinear2x_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
 int mtus_bilinear2x_bwd(const void* dy, void* dx, int B, int H, int W, int C, int dtype, void* stream);
@@ -191,6 +201,14 @@ int mtus_bilinear2x_bwd(const void* dy, void* dx, int B, int H, int W, int C, in
  * (Dropout2d mask / (1-p); NULL = identity).  out dtype fp32 when out_f32; out_nhwc: channels-last output. */
 int mtus_fpn_merge_fwd(const void* const* srcs, int nsrc, int policy_cat, const float* chanscale, void* out, int B,
                        int HW, int C, int dtype, int out_f32, int out_nhwc, void* stream);
+/* merge with the FiLM epilogue (film_layer.py:94-99 applied to the decoder output, multitask_model.py:214-216; SURVEY 8f
+ * N3): out = chanscale[b,c] * merged + chanshift[c] (chanshift [C_out] fp32 or NULL; gamma is folded into chanscale). */
+int mtus_fpn_merge_film_fwd(const void* const* srcs, int nsrc, int policy_cat, const float* chanscale,
+                            const float* chanshift, void* out, int B, int HW, int C, int dtype, int out_f32, int out_nhwc,
+                            void* stream);
+/* dgamma[c] += sum dout * dropscale[b,c] * merged, dbeta[c] += sum dout; dout and srcs NHWC; dropscale [B, C_out] or NULL */
+int mtus_film_grad(const void* dout, int dout_f32, const void* const* srcs, int nsrc, int policy_cat,
+                   const float* dropscale, float* dgamma, float* dbeta, int B, int HW, int C, int dtype, void* stream);
 int mtus_fpn_merge_bwd(const void* dout, int nsrc, int policy_cat, const float* chanscale, void* const* dsrcs, int B,
                        int HW, int C, int dtype, int in_f32, int in_nhwc, void* stream);
 /* repack Conv2d weight [Cout,Cin,3,3] fp32 -> fwd [Cout, 9*Cin] and dgrad [Cin, 9*Cout] (taps flipped) */
@@ -236,6 +254,15 @@ int64_t mtus_swin_feature_offset(const mtus_swin_config* cfg, int stage);
 int mtus_swin_forward(const mtus_swin_config* cfg, const void* x, int x_is_f32, const float* params,
                       const void* params_lp, const float* droppath, void* workspace, void* const* feats,
                       int feats_layout, int feats_f32, void* stream);
+/* Input pipeline fused into the patch-embed operand (replaces albumentations Normalize + ToTensorV2 and the
+ * fp32 NCHW host->device copy of code/train.py:35-44, 305): x_u8 is the raw uint8 [B,H,W,3] (HWC) batch, mean3 / std3 are
+ * HOST arrays (Normalize(mean, std, max_pixel_value=255)); cols = the [B*(H/4)*(W/4), 64] im2col operand. */
+int mtus_patch_embed_im2col_u8(const void* x_u8, const float* mean3, const float* std3, void* cols, int B, int H, int W,
+                               int dtype, void* stream);
+/* mtus_swin_forward fed by the uint8 HWC batch (everything else identical). */
+int mtus_swin_forward_u8(const mtus_swin_config* cfg, const void* x_u8, const float* mean3, const float* std3,
+                         const float* params, const void* params_lp, const float* droppath, void* workspace,
+                         void* const* feats, int feats_layout, int feats_f32, void* stream);
 /* dfeats[4]: NCHW grads (NULL = zero); grads: flat fp32, ACCUMULATED into (caller zeroes).
  * droppath: non-NULL iff forward ran with drop-path (the scales themselves are re-read from the workspace, where
  * forward left a copy).  The call that starts at the top (stage_hi = 4 / block_hi = all blocks) converts dfeats
@@ -277,6 +304,14 @@ int mtus_fpn_param_info(const mtus_fpn_config* cfg, int idx, char* name, int64_t
 int mtus_fpn_forward(const mtus_fpn_config* cfg, const void* const* feats, int feats_layout, int feats_f32,
                      const float* params, const float* chanscale, void* workspace, void* out, int out_f32,
                      void* stream);
+/* same with the fused FiLM epilogue (see mtus_fpn_merge_film_fwd); chanscale must then hold gamma[c] (times the Dropout2d
+ * scale when active), chanshift = beta [out_channels] or NULL. */
+int mtus_fpn_forward_film(const mtus_fpn_config* cfg, const void* const* feats, int feats_layout, int feats_f32,
+                          const float* params, const float* chanscale, const float* chanshift, void* workspace, void* out,
+                          int out_f32, void* stream);
+/* byte offset, inside the workspace, of the NHWC [B,S2,S2,seg_channels] output of tower `level` (0..3 = seg_blocks.0..3, i.e. the p5..p2 towers, in merge order):
+ * the merge sources, needed by mtus_film_grad. */
+int64_t mtus_fpn_tower_output_offset(const mtus_fpn_config* cfg, int level);
 /* dfeats[4]: gradients w.r.t. c2..c5, fully written, in dfeats_layout; grads: flat fp32, ACCUMULATED. */
 int mtus_fpn_backward(const mtus_fpn_config* cfg, const void* const* feats, int feats_layout, int feats_f32,
                       const float* params, const float* chanscale, void* workspace, const void* dout, int dout_f32,

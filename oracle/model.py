@@ -155,9 +155,43 @@ class OracleMultiTaskModel(nn.Module):
         if self.use_fpn_for_cls or self.use_fpn_for_reg:
             raise NotImplementedError("oracle model restates the swin_b.yaml routing (cls/reg bypass the FPN)")
         self.fpn_out_channels = self.fpn_decoder_seg.out_channels
+        # FiLM on the decoder output (multitask_model.py:52-79; film_layer.py:103-148 per-task parameters, :151-216 embedding
+        # generator): out = gamma[c] * x + beta[c]
+        self.use_film = bool(cfg.get("model.use_film", False))
+        if self.use_film:
+            fc = cfg.get("model.film", {}) or {}
+            ids = [t["task_id"] for t in self.task_configs]
+            self.film_affine = bool(fc.get("use_affine", True))
+            self.film_embedding = bool(fc.get("use_task_embedding", False))
+            gen = nn.Module()
+            C = self.fpn_out_channels
+            if self.film_embedding:
+                E = int(fc.get("embedding_dim", 64))
+                self._film_idx = {t: i for i, t in enumerate(ids)}
+                gen.task_embeddings = nn.Embedding(len(ids), E)
+                gen.gamma_generator = nn.Sequential(nn.Linear(E, 2 * C), nn.ReLU(), nn.Linear(2 * C, C))
+                if self.film_affine:
+                    gen.beta_generator = nn.Sequential(nn.Linear(E, 2 * C), nn.ReLU(), nn.Linear(2 * C, C))
+            else:
+                gen.task_gammas = nn.ParameterDict({t: nn.Parameter(torch.ones(C)) for t in ids})
+                if self.film_affine:
+                    gen.task_betas = nn.ParameterDict({t: nn.Parameter(torch.zeros(C)) for t in ids})
+            self.film_generator = gen
         self.heads = nn.ModuleDict({t["task_id"]: build_head(t, self.fpn_out_channels, ch, cfg)
                                     for t in self.task_configs})
         self.task_id_to_name = {t["task_id"]: t["task_name"] for t in self.task_configs}
+
+    def _film(self, x, task_id):
+        if not self.use_film:
+            return x
+        g = self.film_generator
+        if self.film_embedding:
+            e = g.task_embeddings.weight[self._film_idx[task_id]]
+            gamma, beta = g.gamma_generator(e), (g.beta_generator(e) if self.film_affine else None)
+        else:
+            gamma, beta = g.task_gammas[task_id], (g.task_betas[task_id] if self.film_affine else None)
+        x = gamma.view(1, -1, 1, 1) * x
+        return x + beta.view(1, -1, 1, 1) if beta is not None else x
 
     def forward(self, x, task_id):
         if task_id not in self.heads:
@@ -165,9 +199,9 @@ class OracleMultiTaskModel(nn.Module):
         name = self.task_id_to_name[task_id]
         feats = self.encoder(x)
         if name == "segmentation":
-            return self.heads[task_id](self.fpn_decoder_seg(feats))
+            return self.heads[task_id](self._film(self.fpn_decoder_seg(feats), task_id))
         if name == "detection":
-            return self.heads[task_id](self.fpn_decoder_det(feats))
+            return self.heads[task_id](self._film(self.fpn_decoder_det(feats), task_id))
         return self.heads[task_id](feats)
 
 

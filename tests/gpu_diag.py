@@ -322,7 +322,12 @@ def g_fpn_ops():
     return ok
 
 
-def _model_group(precision, gemm_env, tol, cos_min, variants):
+FPN_TASK_TYPES = ("segmentation", "detection")
+
+
+def _model_group(precision, gemm_env, tol, cos_min, variants, cos_fpn=None):
+    """cos_min: per-tensor gradient cosine floor (north star: 0.999); cos_fpn: the floor for bf16 gradients of tasks that run
+    through the FPN (measured 0.9976 at random init), None = same as cos_min."""
     import torch
     torch.backends.cudnn.allow_tf32 = False          # the oracle (and the PyTorch heads) must be true fp32
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -364,7 +369,8 @@ def _model_group(precision, gemm_env, tol, cos_min, variants):
             ok &= report(f"{enc}@{img} {precision} output[{tid}]", ym, yo, tol)
             yo.float().square().mean().backward()
             ym.float().square().mean().backward()
-            ok &= _compare_grads(f"{enc}@{img} {precision} grads[{tid}]", model, oracle, cos_min)
+            via_fpn = model.task_id_to_name[tid] in FPN_TASK_TYPES
+            ok &= _compare_grads(f"{enc}@{img} {precision} grads[{tid}]", model, oracle, cos_fpn if (via_fpn and cos_fpn) else cos_min)
     return ok
 
 
@@ -411,11 +417,11 @@ def g_model_fp32():
 
 
 def g_model_bf16_simt():
-    return _model_group("bf16", "simt", 2e-2, 0.99, _VARIANTS_SMALL[:4])
+    return _model_group("bf16", "simt", 2e-2, 0.999, _VARIANTS_SMALL[:4], cos_fpn=0.995)
 
 
 def g_model_bf16_tc():
-    return _model_group("bf16", "tc", 2e-2, 0.99, _VARIANTS_SMALL)
+    return _model_group("bf16", "tc", 2e-2, 0.999, _VARIANTS_SMALL, cos_fpn=0.995)
 
 
 def main():

@@ -2,8 +2,9 @@
 the C-ABI of libmtus_b200.so, against the oracle / plain PyTorch fp32 on the same seeded inputs.
 
 Tolerances (BASELINE.json north_star): fp32 mode rtol 1e-4 on outputs, bf16 mode rtol 2e-2 (max-abs error over the
-reference's max-abs), per-parameter gradient cosine > 0.999 (fp32) -- bf16 mode is held to > 0.99 per tensor for now
-(see DESIGN.md "precision"), with the worst tensor printed.
+reference's max-abs, plus relative L2 and an element-wise rtol/atol check at model level), per-parameter gradient
+cosine > 0.999 -- except bf16 gradients of tasks that run through the FPN, held to FPN_BF16_COS_FLOOR (measured minimum
+0.9976), with the worst tensor printed.
 """
 import os
 import sys
@@ -51,7 +52,7 @@ def test_model_group(group):
 
 
 @pytest.mark.parametrize("name", ["micro_64_4types", "config1_swin_t_224"])
-@pytest.mark.parametrize("precision,tol,cos_min", [("fp32", 1e-4, 0.999), ("bf16", 2e-2, 0.99)])
+@pytest.mark.parametrize("precision,tol,cos_min", [("fp32", 1e-4, 0.999), ("bf16", 2e-2, 0.995)])
 def test_cuda_path_reproduces_reference_goldens(name, precision, tol, cos_min):
     """Our CUDA path against the committed fixtures produced by the reference's own MultiTaskModel (CPU, fp32)."""
     sys.path.insert(0, GOLDEN)
@@ -86,7 +87,9 @@ def test_cuda_path_reproduces_reference_goldens(name, precision, tol, cos_min):
             if g.norm() == 0:
                 continue
             c = torch.nn.functional.cosine_similarity(grads[k].float().cpu().flatten(), g.flatten(), dim=0).item()
-            assert c >= cos_min, f"{tid} {k}: cosine {c}"
+            via_fpn = model.task_id_to_name[tid] in gpu_diag.FPN_TASK_TYPES
+            floor = cos_min if (precision == "fp32" or via_fpn) else 0.999
+            assert c >= floor, f"{tid} {k}: cosine {c}"
 
 
 def _full_size_model(batch, precision="bf16"):
@@ -110,14 +113,13 @@ def test_full_size_swin_b_against_oracle_on_gpu():
         oracle.zero_grad(set_to_none=True)
         model.zero_grad(set_to_none=True)
         yo, ym = oracle(x, tid), model(x, tid)
-        rel = ((ym.float() - yo).abs().max() / yo.abs().max()).item()
-        assert rel <= 2e-2, f"{tid}: rel {rel}"
+        _elementwise(f"swin_b@224 bf16 output[{tid}]", ym.detach(), yo.detach(), 2e-2)
         yo.square().mean().backward()
         ym.float().square().mean().backward()
         # encoder-only task types (classification, regression): every tensor meets the 0.999 target of the north star;
         # through the FPN, bf16 forward arithmetic alone limits a few tensors to 0.9976-0.999
         enc_only = model.task_id_to_name[tid] in ("classification", "Regression")
-        assert gpu_diag._compare_grads(f"swin_b@224 bf16 {tid}", model, oracle, 0.999 if enc_only else 0.99)
+        assert gpu_diag._compare_grads(f"swin_b@224 bf16 {tid}", model, oracle, 0.999 if enc_only else FPN_BF16_COS_FLOOR)
 
 
 def test_full_size_properties_batch_32():
@@ -296,3 +298,301 @@ def test_device_prefetcher_delivers_the_issued_batch():
     assert torch.equal(xd.cpu(), x) and torch.equal(yd.cpu(), y)
     with pytest.raises(RuntimeError):
         pf.take()
+
+
+# ======================================================================================================================
+# round 2: BASELINE configs[3] / configs[4] at model level, element-wise metrics, optimizer surface, NCCL data parallel
+# ======================================================================================================================
+def _elementwise(name, got, ref, tol):
+    """Relative L2 and element-wise closeness next to the max-norm metric: |got - ref| <= tol * (|ref| + rms(ref)) must
+    hold for (almost) every element, so small-magnitude outputs are constrained too."""
+    got, ref = got.float(), ref.float()
+    rl2 = ((got - ref).norm() / (ref.norm() + 1e-30)).item()
+    rms = ref.square().mean().sqrt().item()
+    viol = ((got - ref).abs() > tol * (ref.abs() + rms)).float().mean().item()
+    mx = ((got - ref).abs().max() / (ref.abs().max() + 1e-30)).item()
+    print(f"  {name}: max-norm rel {mx:.3e}  rel-L2 {rl2:.3e}  elements outside rtol/atol {viol:.2e}", flush=True)
+    assert mx <= tol, f"{name}: max-norm rel {mx}"
+    assert rl2 <= tol, f"{name}: rel-L2 {rl2}"
+    # fp32: (almost) every element inside rtol/atol; bf16: the per-element error is ~1e-2 rms (measured 2.3e-2 of the
+    # elements of the segmentation logits outside 2e-2 (|ref| + rms) at swin_b@224), so the fraction is bounded, not zero
+    assert viol <= (1e-3 if tol <= 1e-3 else 5e-2), f"{name}: {viol:.3e} of the elements violate |d| <= {tol} (|ref| + rms)"
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_config3_swin_large_window12_384_against_oracle(precision, tol):
+    """BASELINE configs[3]: swin_large_patch4_window12_384 (144-token windows, 529-entry tables), one segmentation and one
+    classification task, batch 2, forward + backward against the fp32 oracle on the GPU."""
+    import mtus_b200 as m
+    from oracle.model import OracleMultiTaskModel
+    ids = ("T2A_fetal_abdomen", "T1_fetal_planes")
+    tasks = [t for t in m.tasks_27() if t["task_id"] in ids]
+    cfg = m.make_config("swin_large_patch4_window12_384", 384, 2, tasks=tasks, dropout=0.0, mixed_precision=(precision == "bf16"))
+    torch.manual_seed(0)
+    oracle = OracleMultiTaskModel(cfg, drop_path_rate=0.0).cuda().eval()
+    model = m.build_model(cfg, precision=precision).cuda().eval()
+    model.load_state_dict(oracle.state_dict())
+    x = torch.randn(2, 3, 384, 384, generator=torch.Generator().manual_seed(2)).cuda()
+    with torch.no_grad():
+        for i, (a, b) in enumerate(zip(model.encoder(x), oracle.encoder(x))):
+            _elementwise(f"swin_l@384 {precision} feature[{i}]", a, b, tol)
+    for tid in ids:
+        oracle.zero_grad(set_to_none=True)
+        model.zero_grad(set_to_none=True)
+        yo, ym = oracle(x, tid), model(x, tid)
+        _elementwise(f"swin_l@384 {precision} output[{tid}]", ym.detach(), yo.detach(), tol)
+        yo.square().mean().backward()
+        ym.float().square().mean().backward()
+        enc_only = model.task_id_to_name[tid] in ("classification", "Regression")
+        floor = 0.999 if (precision == "fp32" or enc_only) else FPN_BF16_COS_FLOOR
+        assert gpu_diag._compare_grads(f"swin_l@384 {precision} grads[{tid}]", model, oracle, floor)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_config4_swin_b_512_inference_against_oracle(precision, tol):
+    """BASELINE configs[4]: swin_b at 512x512 (maps 128/64/32/16 padded to 133/70/35/21, shifted windows in all four stages,
+    timm's roll-then-pad order), eval + no_grad, all four task types."""
+    import mtus_b200 as m
+    from oracle.model import OracleMultiTaskModel
+    ids = ("T2B_adult_liver_segment_5", "T3C_thyroid_nodule", "T4A_fetal_femur", "T5_fetal_brain")
+    tasks = [t for t in m.tasks_27() if t["task_id"] in ids]
+    cfg = m.make_config("swin_b", 512, 2, tasks=tasks, dropout=0.0, mixed_precision=(precision == "bf16"))
+    torch.manual_seed(0)
+    oracle = OracleMultiTaskModel(cfg, drop_path_rate=0.0).cuda().eval()
+    model = m.build_model(cfg, precision=precision).cuda().eval()
+    model.load_state_dict(oracle.state_dict())
+    x = torch.randn(2, 3, 512, 512, generator=torch.Generator().manual_seed(4)).cuda()
+    with torch.no_grad():
+        for i, (a, b) in enumerate(zip(model.encoder(x), oracle.encoder(x))):
+            _elementwise(f"swin_b@512 {precision} feature[{i}]", a, b, tol)
+        for tid in ids:
+            _elementwise(f"swin_b@512 {precision} output[{tid}]", model(x, tid), oracle(x, tid), tol)
+
+
+# bf16 mode, gradients of tasks that run through the FPN: measured per-tensor minimum 0.9970 (swin_t) .. 0.9982 against the
+# fp32 oracle at random initialisation.  profiles/r2_fpn_limit_diag.txt shows the same minimum when the EXACT fp32 oracle
+# decoder + head are fed the bf16 encoder's features, i.e. it is the bf16 FORWARD perturbation of the features flipping
+# GroupNorm -> ReLU masks, not decoder or backward arithmetic (DESIGN.md section 4).  Asserted below the measurement so a
+# regression shows; encoder-only tasks and every fp32-mode tensor are held to the north star's 0.999.
+FPN_BF16_COS_FLOOR = 0.995
+
+
+def test_flat_adamw_follows_cosine_schedule_and_resumes_from_a_cpu_mapped_checkpoint(tmp_path):
+    """FlatAdamW + CosineAnnealingLR == torch AdamW + CosineAnnealingLR on the native model, and a state dict
+    saved, reloaded with map_location='cpu' and loaded back continues exactly like the uninterrupted run."""
+    import mtus_b200 as m
+    tasks = [t for t in m.tasks_27() if t["task_id"] in ("T2A_fetal_abdomen", "T1_fetal_planes")]
+    cfg = m.make_config("swin_micro_patch4_window7_test", 64, 4, tasks=tasks, dropout=0.0)
+
+    def make(flat):
+        torch.manual_seed(0)
+        model = m.build_model(cfg, precision="fp32").cuda().eval()
+        opt = m.build_flat_optimizer(model, cfg) if flat else m.build_optimizer(model, cfg, fused=False)
+        sch = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=6, eta_min=1e-7)
+        fns, w = m.build_all_losses(cfg)
+        return model, opt, sch, m.DataParallelTrainer(model, opt, fns, w, gradient_clip=1.0)
+
+    def run(tr, sch, steps, start=0):
+        gen = torch.Generator().manual_seed(3)
+        batches = [m.synthetic_batch(tasks[s % 2], 4, 64, generator=gen, device="cuda") for s in range(6)]
+        for s in range(start, steps):
+            x, y = batches[s]
+            tr.step(x, y, tasks[s % 2]["task_id"])
+            sch.step()
+
+    ma, oa, sa, ta = make(True)
+    mb, ob, sb, tb = make(False)
+    run(ta, sa, 6)
+    run(tb, sb, 6)
+    assert abs(oa.param_groups[0]["lr"] - ob.param_groups[0]["lr"]) < 1e-12
+    for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert torch.allclose(pa, pb, rtol=2e-4, atol=2e-6), k
+    # resume: 3 steps, save, reload on CPU, load, 3 more steps == 6 uninterrupted steps
+    mc, oc, sc, tc = make(True)
+    run(tc, sc, 3)
+    path = os.path.join(tmp_path, "ckpt.pth")
+    torch.save({"model": mc.state_dict(), "opt": oc.state_dict(), "sch": sc.state_dict()}, path)
+    md, od, sd_, td = make(True)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    md.load_state_dict(ck["model"])
+    od.load_state_dict(ck["opt"])
+    sd_.load_state_dict(ck["sch"])
+    assert all(f["m"].is_cuda for f in od.flat if f["m"] is not None)
+    run(td, sd_, 6, start=3)
+    for (k, pa), (_, pd) in zip(ma.named_parameters(), md.named_parameters()):
+        assert torch.allclose(pa, pd, rtol=1e-5, atol=1e-7), k
+
+
+def test_model_on_a_non_current_device_is_guarded():
+    """the wrappers make the tensors' device current for the C-ABI calls (needs 2 GPUs)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import mtus_b200 as m
+    torch.manual_seed(0)
+    enc0 = m.SwinTransformerEncoder("swin_micro_patch4_window7_test", pretrained=False, img_size=64, precision="bf16").to("cuda:0").eval()
+    enc1 = m.SwinTransformerEncoder("swin_micro_patch4_window7_test", pretrained=False, img_size=64, precision="bf16").to("cuda:1").eval()
+    enc1.load_state_dict(enc0.state_dict())
+    x = torch.randn(2, 3, 64, 64)
+    torch.cuda.set_device(0)
+    with torch.no_grad():
+        f0 = enc0(x.to("cuda:0"))
+        f1 = enc1(x.to("cuda:1"))           # current device is still 0
+    for a, b in zip(f0, f1):
+        assert b.device.index == 1 and torch.equal(a.cpu(), b.cpu())
+
+
+def test_nccl_data_parallel_parity():
+    """all-reduced gradient == mean over ranks of the oracle's per-rank gradients, over NCCL on 2 GPUs
+    (tests/dp_nccl_check.py under torch.distributed.run).  Skipped on a single-GPU box; the committed log of a 2-GPU run is
+    profiles/r2_dp_nccl_check_2gpu.txt."""
+    import subprocess
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(here, "dp_nccl_check.py")], capture_output=True, text=True, timeout=900)
+    print(r.stdout[-6000:])
+    print(r.stderr[-3000:])
+    assert r.returncode == 0 and r.stdout.count("DP_NCCL_CHECK PASS") == 2
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_head_conv_stacks_on_the_native_engines_match_pytorch(dtype, tol):
+    """SegmentationHead's Conv3x3(512->128)-GN-SiLU x2 (code/models/heads.py:16-42) and the baseline
+    detection head's Conv3x3-BatchNorm2d-ReLU x2 (:404-428) through mtus_conv3x3_* / mtus_groupnorm_act_* /
+    mtus_batchnorm_act_* against the same nn.Modules evaluated by PyTorch in fp32: outputs, input gradient, every
+    parameter gradient, BatchNorm running statistics (training mode) and the eval-mode path."""
+    import copy
+    from mtus_b200 import heads as H
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(1)
+    x0 = (torch.randn(2, 512, 56, 56, generator=g) * 0.7).cuda().to(memory_format=torch.channels_last)
+    for kind in ("seg", "det_train", "det_eval"):
+        head = (H.SegmentationHead(512, 2, upsampling=4, mid_channels=128, num_layers=2) if kind == "seg"
+                else H.BaselineFPNGridDetectionHead(512, num_classes=1, mid_channels=128)).cuda().to(memory_format=torch.channels_last)
+        with torch.no_grad():
+            for m_ in head.modules():
+                if isinstance(m_, (torch.nn.GroupNorm, torch.nn.BatchNorm2d)):
+                    m_.weight.uniform_(0.5, 1.5)
+                    m_.bias.normal_(0, 0.2)
+                if isinstance(m_, torch.nn.BatchNorm2d):
+                    m_.running_mean.normal_(0, 0.1)
+                    m_.running_var.uniform_(0.5, 1.5)
+        head.train(kind != "det_eval")
+        ref = copy.deepcopy(head)
+        # reference: the plain nn.Module path in fp32
+        xr = x0.clone().requires_grad_(True)
+        if kind == "seg":
+            yr = ref.head(ref.pre_head(xr))
+        else:
+            t = ref.conv_block(xr)
+            yr = torch.cat([torch.sigmoid(t[:, :4]), t[:, 4:]], dim=1)
+        dy = torch.randn(yr.shape, generator=g).cuda()
+        yr.backward(dy)
+        # native path (what MultiTaskModel._head runs: autocast in bf16 mode)
+        xk = x0.to(dtype).requires_grad_(True)
+        if dtype == torch.bfloat16:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                yk = head(xk)
+        else:
+            yk = head(xk)
+        yk.float().backward(dy)
+        _elementwise(f"{kind} {dtype} output", yk.detach(), yr.detach(), tol)
+        _elementwise(f"{kind} {dtype} dx", xk.grad, xr.grad, tol)
+        for (k, pk), (_, pr) in zip(head.named_parameters(), ref.named_parameters()):
+            c = torch.nn.functional.cosine_similarity(pk.grad.float().flatten(), pr.grad.flatten(), dim=0).item()
+            rn = (pk.grad.float().norm() / pr.grad.norm()).item()
+            assert c >= 0.999 and 0.97 < rn < 1.03, f"{kind} {dtype} {k}: cosine {c} norm ratio {rn}"
+        for (k, bk), (_, br) in zip(head.named_buffers(), ref.named_buffers()):
+            assert torch.allclose(bk.float(), br.float(), rtol=2e-2 if dtype == torch.bfloat16 else 1e-4, atol=1e-3), f"{kind} buffer {k}"
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_film_epilogue_fused_into_the_merge_kernel_matches_the_oracle(precision, tol):
+    """model.use_film (best_config.yaml:58; film_layer.py:94-99 at multitask_model.py:214-216) with the
+    gamma * x + beta modulation inside mtus_fpn_merge_film_fwd: outputs and EVERY gradient (film_generator.* included) vs
+    the oracle, per-task parameters and the embedding generator, with Dropout2d off (parity) -- plus a dropout-on run that
+    checks dgamma / dbeta against autograd through the same sampled mask."""
+    import mtus_b200 as m
+    from oracle.model import OracleMultiTaskModel
+    ids = ("T2C_fetal_head", "T4A_fetal_femur", "T3A_breast_tumor")
+    tasks = [t for t in m.tasks_27() if t["task_id"] in ids]
+    for embedding in (False, True):
+        cfg = m.make_config("swin_micro_patch4_window7_test", 128, 2, tasks=tasks, dropout=0.0, mixed_precision=(precision == "bf16"))
+        cfg.config["model"]["use_film"] = True
+        cfg.config["model"]["film"] = {"use_task_embedding": embedding, "embedding_dim": 16, "use_affine": True}
+        torch.manual_seed(0)
+        oracle = OracleMultiTaskModel(cfg, drop_path_rate=0.0).cuda().eval()
+        with torch.no_grad():
+            for k, p in oracle.named_parameters():
+                if k.startswith("film_generator."):
+                    p.add_(torch.randn_like(p) * 0.3)
+        model = m.build_model(cfg, precision=precision).cuda().eval()
+        model.load_state_dict(oracle.state_dict())
+        x = torch.randn(2, 3, 128, 128, generator=torch.Generator().manual_seed(2)).cuda()
+        for tid in ids:
+            oracle.zero_grad(set_to_none=True)
+            model.zero_grad(set_to_none=True)
+            yo, ym = oracle(x, tid), model(x, tid)
+            _elementwise(f"film(embedding={embedding}) {precision} output[{tid}]", ym.detach(), yo.detach(), tol)
+            yo.square().mean().backward()
+            ym.float().square().mean().backward()
+            via_fpn = model.task_id_to_name[tid] in gpu_diag.FPN_TASK_TYPES
+            floor = 0.999 if (precision == "fp32" or not via_fpn) else FPN_BF16_COS_FLOOR
+            assert gpu_diag._compare_grads(f"film(embedding={embedding}) {precision} grads[{tid}]", model, oracle, floor)
+            if via_fpn:
+                assert any(k.startswith("film_generator.") and p.grad is not None and p.grad.abs().sum() > 0
+                           for k, p in model.named_parameters())
+    # Dropout2d on: d(loss)/d(gamma, beta) must be consistent with the decoder's own output under the SAME mask
+    cfg = m.make_config("swin_micro_patch4_window7_test", 128, 2, tasks=tasks, dropout=0.5, mixed_precision=(precision == "bf16"))
+    cfg.config["model"]["use_film"] = True
+    torch.manual_seed(0)
+    model = m.build_model(cfg, precision=precision).cuda().train()
+    dec = model.fpn_decoder_seg
+    feats = [f.detach() for f in model.encoder(x)]
+    gamma = (torch.rand(dec.out_channels, device="cuda") + 0.5).requires_grad_(True)
+    beta = (torch.randn(dec.out_channels, device="cuda") * 0.1).requires_grad_(True)
+    torch.manual_seed(5)
+    plain = dec(feats).float()                       # dropout mask drawn from seed 5
+    torch.manual_seed(5)
+    out = dec(feats, film=(gamma, beta)).float()     # same mask
+    ref = gamma.view(1, -1, 1, 1) * plain.detach() + beta.view(1, -1, 1, 1)
+    _elementwise(f"film + dropout {precision} output", out.detach(), ref.detach(), tol)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    gk, bk = gamma.grad.clone(), beta.grad.clone()
+    gamma.grad = beta.grad = None
+    (ref * w).sum().backward()
+    for name, a, b in (("dgamma", gk, gamma.grad), ("dbeta", bk, beta.grad)):
+        c = torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0).item()
+        assert c >= 0.999, f"{name}: cosine {c}"
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_uint8_input_pipeline_fused_into_patch_embed(precision, tol):
+    """forward(uint8 [B,H,W,3]) == forward(Normalize(mean, std)(img) as fp32 NCHW) (code/train.py:35-44) --
+    features vs the oracle fed the host-normalised batch, and the patch-embed gradients of both input forms agree."""
+    import mtus_b200 as m
+    from oracle.model import OracleSwinEncoder
+    name, img = "swin_micro_patch4_window7_test", 112
+    torch.manual_seed(0)
+    oracle = OracleSwinEncoder(name, img, drop_path_rate=0.0).cuda().eval()
+    enc = m.SwinTransformerEncoder(name, pretrained=False, img_size=img, precision=precision).cuda().eval()
+    enc.load_state_dict(oracle.state_dict())
+    mean, std = (0.4, 0.5, 0.3), (0.25, 0.2, 0.3)
+    enc.model.input_mean, enc.model.input_std = mean, std
+    u8 = torch.randint(0, 256, (3, img, img, 3), generator=torch.Generator().manual_seed(1), dtype=torch.uint8).cuda()
+    xf = ((u8.float() / 255.0 - torch.tensor(mean, device="cuda")) / torch.tensor(std, device="cuda")).permute(0, 3, 1, 2).contiguous()
+    fo = oracle(xf)
+    fk = enc(u8)
+    for i, (a, b) in enumerate(zip(fk, fo)):
+        _elementwise(f"uint8 input {precision} feature[{i}]", a.detach(), b.detach(), tol)
+    sum(f.float().square().mean() for f in fk).backward()
+    g_u8 = {k: p.grad.clone() for k, p in enc.named_parameters()}
+    enc.zero_grad(set_to_none=True)
+    sum(f.float().square().mean() for f in enc(xf)).backward()
+    for k, p in enc.named_parameters():
+        c = torch.nn.functional.cosine_similarity(p.grad.flatten(), g_u8[k].flatten(), dim=0).item()
+        assert c >= 0.9999, f"{k}: uint8 vs float input gradient cosine {c}"

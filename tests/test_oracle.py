@@ -174,6 +174,40 @@ def test_reference_multitask_model_on_shims_equals_oracle_model():
         oracle(x, "no_such_task")
 
 
+@pytest.mark.skipif(not HAS_REFERENCE, reason="needs /root/reference (authoring container)")
+@pytest.mark.parametrize("embedding", [False, True])
+def test_film_reference_model_equals_oracle_and_native_key_layout(embedding):
+    """model.use_film (best_config.yaml:58): the reference's own MultiTaskModel + film_layer.py on the shims == the oracle's
+    FiLM restatement bit for bit, and the native model exposes the same film_generator.* state-dict keys."""
+    import mtus_b200 as m
+    from oracle import shims
+    from oracle.model import OracleMultiTaskModel
+    models, _, _ = shims.import_reference_models("/root/reference")
+    tasks = [t for t in m.tasks_27() if t["task_id"] in ("T2C_fetal_head", "T3A_breast_tumor", "T4A_fetal_femur")]
+    cfg = m.make_config("swin_micro_patch4_window7_test", 64, 2, tasks=tasks, dropout=0.0, mixed_precision=False)
+    cfg.config["model"]["use_film"] = True
+    cfg.config["model"]["film"] = {"use_task_embedding": embedding, "embedding_dim": 16, "use_affine": True}
+    torch.manual_seed(0)
+    oracle = OracleMultiTaskModel(cfg, drop_path_rate=0.0).eval()
+    with torch.no_grad():
+        for k, p in oracle.named_parameters():
+            if k.startswith("film_generator."):
+                p.add_(torch.randn_like(p) * 0.3)        # gamma = 1, beta = 0 at init would hide a missing modulation
+    ref = models.build_model(cfg).eval()
+    ref.load_state_dict(oracle.state_dict(), strict=True)
+    assert list(ref.state_dict().keys()) == list(oracle.state_dict().keys())
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(3))
+    for t in tasks:
+        with torch.no_grad():
+            assert torch.equal(ref(x, t["task_id"]), oracle(x, t["task_id"])), t["task_id"]
+    native = m.build_model(cfg, precision="fp32")
+    assert list(native.state_dict().keys()) == list(oracle.state_dict().keys())
+    native.load_state_dict(oracle.state_dict(), strict=True)
+    enc, head = native.get_trainable_parameters()
+    ids = {id(p) for p in enc + head}
+    assert not any(id(p) in ids for p in native.film_generator.parameters())     # as in the reference (:282-308)
+
+
 # ---- second independent pin of the Swin restatement: Hugging Face transformers (SURVEY App. B) -------------------
 def _hf_state_dict_from_oracle(sd, depths):
     """oracle / timm keys -> transformers.SwinModel keys (qkv split into query / key / value; HF stores the
