@@ -314,6 +314,24 @@ def g_fpn_ops():
             du = torch.randn(B, 2 * H, 2 * W, Cc, device=dev).to(dt)
             ur.backward(du.float().permute(0, 3, 1, 2))
             ok &= report(f"bilinear2x_bwd", ops.bilinear2x_bwd(du), xr2.grad.permute(0, 2, 3, 1), tol)
+            # BatchNorm2d + ReLU over NHWC rows (the GroupNorm kernels with one group per channel), training and eval
+            for training in (True, False):
+                xb = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+                gb, bb = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+                rm, rv = torch.randn(Cc, device=dev) * 0.1, torch.rand(Cc, device=dev) + 0.5
+                preb = F.batch_norm(xb, rm.clone(), rv.clone(), gb, bb, training, 0.1, 1e-5)
+                if training:
+                    mean_k, rstd_k = ops.batchnorm_stats(x)
+                else:
+                    mean_k, rstd_k = rm.clone(), (rv + 1e-5).rsqrt()
+                yk = ops.batchnorm_relu_fwd(x, mean_k, rstd_k, g, b)
+                ok &= report(f"bn_relu_fwd training={training}", yk, F.relu(preb).permute(0, 2, 3, 1), tol)
+                gate_b = (yk.float() > 0).permute(0, 3, 1, 2)
+                (preb * gate_b).backward(dy.float().permute(0, 3, 1, 2))
+                dxk, dgk, dbk = ops.batchnorm_relu_bwd(dy, x, yk, mean_k, rstd_k, g, training=training)
+                ok &= report(f"bn_relu_bwd dx training={training}", dxk, xb.grad.permute(0, 2, 3, 1), max(tol, 1e-4))
+                ok &= report(f"bn_relu_bwd dgamma", dgk, gb.grad, max(tol, 3e-4))
+                ok &= report(f"bn_relu_bwd dbeta", dbk, bb.grad, max(tol, 3e-4))
             top = torch.randn(B, H, W, Cc, device=dev).to(dt)
             skip = torch.randn(B, 2 * H, 2 * W, Cc, device=dev).to(dt)
             refu = skip.float() + F.interpolate(top.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
@@ -417,11 +435,11 @@ def g_model_fp32():
 
 
 def g_model_bf16_simt():
-    return _model_group("bf16", "simt", 2e-2, 0.999, _VARIANTS_SMALL[:4], cos_fpn=0.995)
+    return _model_group("bf16", "simt", 2e-2, 0.999, _VARIANTS_SMALL[:4], cos_fpn=0.993)
 
 
 def g_model_bf16_tc():
-    return _model_group("bf16", "tc", 2e-2, 0.999, _VARIANTS_SMALL, cos_fpn=0.995)
+    return _model_group("bf16", "tc", 2e-2, 0.999, _VARIANTS_SMALL, cos_fpn=0.993)
 
 
 def main():
