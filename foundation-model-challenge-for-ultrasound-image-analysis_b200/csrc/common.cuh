@@ -131,27 +131,30 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 #define MTUS_GELU_C1 7.40112920e-02f
 #define MTUS_GELU_C2 -7.03033580e-04f
 #define MTUS_NLOG2E -1.4426950408889634f
-__device__ __forceinline__ float gelu_sigmoid_core(float x, float& x2_out, float& xc_out) {   // sigmoid(q(x))
+// sigmoid(q(x)) = 0.5 + 0.5 tanh(q(x) / 2): ONE special-function op (tanh.approx, |rel err| <= 2^-11, i.e. <= 2.5e-4
+// absolute on the sigmoid -- an eighth of a bf16 ulp of the result) instead of ex2 + rcp; on B200 the epilogues of the
+// K = 128 / 256 GEMMs were bound by the XU pipe (MUFU + F2F) and the issue rate (profiles/r2_ncu_gemm_tc2_gelu_epilogue.txt).
+__device__ __forceinline__ float gelu_sigmoid_core(float x, float& x2_out, float& xc_out, float& t_out) {
   const float xc = fminf(fmaxf(x, -5.0f), 5.0f);
   const float x2 = xc * xc;
-  float t = fmaf(x2, MTUS_GELU_C2 * MTUS_NLOG2E, MTUS_GELU_C1 * MTUS_NLOG2E);
-  t = fmaf(t, x2, MTUS_GELU_C0 * MTUS_NLOG2E);
-  float e, s;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t * xc));        // exp(-q)
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(1.0f + e));
-  x2_out = x2; xc_out = xc;
-  return s;
+  float p = fmaf(x2, 0.5f * MTUS_GELU_C2, 0.5f * MTUS_GELU_C1);
+  p = fmaf(p, x2, 0.5f * MTUS_GELU_C0);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(p * xc));           // tanh(q / 2)
+  x2_out = x2; xc_out = xc; t_out = t;
+  return fmaf(0.5f, t, 0.5f);
 }
 __device__ __forceinline__ float gelu_fast_f(float x) {
-  float x2, xc;
-  return x * gelu_sigmoid_core(x, x2, xc);
+  float x2, xc, t;
+  return x * gelu_sigmoid_core(x, x2, xc, t);
 }
 __device__ __forceinline__ float gelu_grad_fast_f(float x) {
-  float x2, xc;
-  const float s = gelu_sigmoid_core(x, x2, xc);
+  float x2, xc, t;
+  const float s = gelu_sigmoid_core(x, x2, xc, t);
   float dq = fmaf(x2, 5.0f * MTUS_GELU_C2, 3.0f * MTUS_GELU_C1);     // q'(x) = c0 + 3 c1 x^2 + 5 c2 x^4
   dq = fmaf(dq, x2, MTUS_GELU_C0);
-  return fmaf(xc * s * (1.0f - s), dq, s);
+  const float w = fmaf(-0.25f * t, t, 0.25f);                        // s (1 - s) = (1 - t^2) / 4
+  return fmaf(xc * w, dq, s);
 }
 
 // ---- fused GEMM epilogue (shared by the SIMT fp32 GEMM and the tcgen05 bf16 GEMM) -----------

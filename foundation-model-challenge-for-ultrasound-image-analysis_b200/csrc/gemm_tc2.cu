@@ -23,8 +23,16 @@
 
 #define T2_BM 128
 #define T2_BK 64
-#define T2_THREADS 384
-#define T2_EPI_THREADS 256
+// Epilogue warps: T2_NQ column groups x 4 TMEM lane quarters.  With 8 warps (T2_NQ = 2) the epilogues that do real math
+// (GELU / GELU' at K = 128 / 256, where the main loop is short) ran at ~47 % issue-slot utilisation: two warps per
+// scheduler cannot cover the MUFU / LDS / TMEM-load latencies.  16 warps (T2_NQ = 4) give every scheduler four epilogue
+// warps and halve the accumulator registers per thread (16 columns instead of 32).
+#ifndef T2_NQ
+#define T2_NQ 4
+#endif
+#define T2_EPI_WARPS (4 * T2_NQ)
+#define T2_EPI_THREADS (32 * T2_EPI_WARPS)
+#define T2_THREADS (128 + T2_EPI_THREADS)
 #define T2_EPI_BAR 1
 
 struct T2Conv {   // geometry of conv operands (NHWC [B,H,W,C]); pixel tiles of th x tw
@@ -40,17 +48,17 @@ struct T2Epi {
   int act;                // 0 none | 1 GELU (pre-activation -> X out) | 2 multiply by GELU'(X in)
   int x_mode;             // 0 none | 1 residual in (out += X) | 2 aux in (act 2) | 3 aux out (act 1)
   int reduce;             // fp32 output: 1 = TMA reduce-add into the destination (split-K weight gradients), 0 = store
-  float* colsum;          // bf16 output only: colsum[n] += sum over rows of the stored (rounded) output (bias gradients)
+  float* colsum;          // bf16 output only: colsum[n] += sum over rows of the fp32 (un-rounded) output values (bias gradients)
 };
 
-template <int BN, bool OUT_F32>
+template <int BN, bool OUT_F32, int CS = 1>
 struct T2Smem {
   static constexpr int A_BYTES = T2_BM * T2_BK * 2;
-  static constexpr int B_BYTES = BN * T2_BK * 2;
+  static constexpr int B_BYTES = (BN / CS) * T2_BK * 2;             // CTA pair (CS = 2): each CTA stages half of the B tile
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int SUB_BYTES = 128 * 128;                       // epilogue sub-tile: 128 rows x 128 bytes
   static constexpr int EPI_BUFS = 2;   // (measured: a deeper ring with a single-buffered epilogue is not faster)
-  static constexpr int STAGES = (BN == 256) ? 3 : ((BN >= 128) ? 4 : 6);
+  static constexpr int STAGES = (CS == 2) ? 4 : ((BN == 256) ? 3 : ((BN >= 128) ? 4 : 6));
   static constexpr int TMEM_COLS = (2 * BN > 256) ? 512 : ((2 * BN > 128) ? 256 : 128);   // two accumulators, power of two
   static constexpr int EPI_OFF = STAGES * STAGE;
   static constexpr int BAR_OFF = EPI_OFF + 2 * EPI_BUFS * SUB_BYTES;   // X[EPI_BUFS], D[EPI_BUFS]
@@ -62,15 +70,18 @@ struct T2Smem {
 
 // A_MODE: 0 K-major 2-D | 1 MN-major 2-D | 2 conv im2col (K-major, 128-pixel row tiles) | 3 conv pixel-major (wgrad)
 // B_MODE: 0 K-major 2-D | 1 MN-major 2-D | 2 conv pixel-major with tap shift (wgrad)
-// CS: thread-block cluster size along M.  The CS CTAs of a cluster work on CS consecutive m-blocks of the same n-tile in
-// lock step: each loads its own A tile and 1/CS of the shared B tile, multicast into every CTA's shared memory, so
-// the L2 -> SM operand traffic (the main-loop limiter of these GEMMs) drops from A+B to A+B/CS per CTA.
+// CS = 2: CTA PAIR (tcgen05 cta_group::2).  The two CTAs of a cluster work on two consecutive m-blocks of the same n-tile:
+// each loads its own 128-row A tile and HALF of the B tile into its own shared memory (transaction bytes signalled on the
+// leader's barrier), the leader (cluster rank 0) issues 256 x BN MMAs that read both CTAs' shared memory and leave 128
+// accumulator rows in each CTA's TMEM, and each CTA runs its own epilogue.  Per SM and k-block the operand traffic drops
+// from A + B to A + B/2 -- these GEMMs are bound by the L2 -> SM operand rate.  (Round 1 tried multicasting B halves to
+// both CTAs with cta_group::1 MMAs: the same bytes still enter every SM, so it did not help and was removed.)
 template <int BN, int A_MODE, int B_MODE, bool OUT_F32, int CS>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, int M, int N, int K,
                 int kb_per_split, int total_kb, int m_tiles, int n_tiles, int n_work, T2Conv cv, T2Epi ep) {
-  using S = T2Smem<BN, OUT_F32>;
+  using S = T2Smem<BN, OUT_F32, CS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = smem_u32(smem);
@@ -95,14 +106,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int cl_id = blockIdx.x / CS, n_cl = gridDim.x / CS;
   constexpr uint16_t cl_mask = (uint16_t)((1u << CS) - 1);
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < S::STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CS); }
+    // pair mode: full / tempty are used in the leader only (fed by both CTAs); empty / tfull get one multicast commit each
+    for (int s = 0; s < S::STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 8);
-      mbar_init(bar_xfull + 8 * b, 1); mbar_init(bar_xempty + 8 * b, 8);
+      mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, CS * T2_EPI_WARPS);
+      mbar_init(bar_xfull + 8 * b, 1); mbar_init(bar_xempty + 8 * b, T2_EPI_WARPS);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), S::TMEM_COLS);
+  if (warp == 2) { if (CS == 2) tmem_alloc_2cta(smem_u32(tmem_slot), S::TMEM_COLS); else tmem_alloc(smem_u32(tmem_slot), S::TMEM_COLS); }
   tc_fence_before();
   __syncthreads();
   if (CS > 1) cluster_sync_all();          // barrier inits visible cluster-wide before any remote arrive / multicast
@@ -135,8 +147,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         const uint32_t full = bar_full + 8 * s;
         const uint32_t sa = smem_base + s * S::STAGE, sb = sa + S::A_BYTES;
-        mbar_expect_tx(full, S::STAGE);
         const int kb = kb0 + i, k0 = kb * T2_BK;
+        if (CS == 2) {
+          // CTA pair: only the leader's barrier counts, and it expects the bytes of BOTH CTAs
+          static_assert(CS == 1 || (A_MODE == 0 && B_MODE != 2), "pair mode: K-major A, 2-D B");
+          if (cl_rank == 0) mbar_expect_tx(full, 2 * S::STAGE);
+          tma_load_2d_2cta(sa, &tmA, k0, m_blk * T2_BM, full);
+          if (B_MODE == 0) {          // tmB box = (64 k, BN/2 rows)
+            tma_load_2d_2cta(sb, &tmB, k0, n_blk * BN + cl_rank * (BN / 2), full);
+          } else {                    // MN-major: BN/128 chunks of 64 n per CTA
+#pragma unroll
+            for (int j = 0; j < BN / 128; ++j)
+              tma_load_2d_2cta(sb + j * 8192, &tmB, n_blk * BN + cl_rank * (BN / 2) + j * 64, k0, full);
+          }
+          continue;
+        }
+        mbar_expect_tx(full, S::STAGE);
         int pb = 0, py0 = 0, px0 = 0;                    // pixel patch of this k-block (conv wgrad)
         if (A_MODE == 3 || B_MODE == 2) {
           int q = kb; const int tx = q % cv.ktiles_x; q /= cv.ktiles_x; const int ty = q % cv.ktiles_y; pb = q / cv.ktiles_y;
@@ -154,39 +180,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tma_load_4d(sa, &tmA, m_blk * T2_BM, px0, py0, pb, full);
           tma_load_4d(sa + 8192, &tmA, m_blk * T2_BM + 64, px0, py0, pb, full);
         }
-        if (CS == 1) {
-          if (B_MODE == 0) {
-            tma_load_2d(sb, &tmB, k0, n_blk * BN, full);
-          } else if (B_MODE == 1) {
+        if (B_MODE == 0) {
+          tma_load_2d(sb, &tmB, k0, n_blk * BN, full);
+        } else if (B_MODE == 1) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, n_blk * BN + j * 64, k0, full);
-          } else {                    // x [pixels, Cin] shifted by the tap of this n-tile: N index = tap*C + c
-            const int n0 = n_blk * BN;
-            const int tap = n0 / cv.C, c0 = n0 - tap * cv.C;
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, n_blk * BN + j * 64, k0, full);
+        } else {                    // x [pixels, Cin] shifted by the tap of this n-tile: N index = tap*C + c
+          const int n0 = n_blk * BN;
+          const int tap = n0 / cv.C, c0 = n0 - tap * cv.C;
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_4d(sb + j * 8192, &tmB, c0 + j * 64, px0 + tap % 3 - 1, py0 + tap / 3 - 1, pb, full);
-          }
-        } else {                      // this CTA's 1/CS of the B tile, multicast to every CTA of the cluster
-          if (B_MODE == 0) {          // tmB box = (64 k, BN/CS rows)
-            tma_load_2d_mc(sb + cl_rank * (BN / CS) * 128, &tmB, k0, n_blk * BN + cl_rank * (BN / CS), full, cl_mask);
-          } else if (B_MODE == 1) {
-#pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              if (j % CS == cl_rank) tma_load_2d_mc(sb + j * 8192, &tmB, n_blk * BN + j * 64, k0, full, cl_mask);
-          } else {
-            const int n0 = n_blk * BN;
-            const int tap = n0 / cv.C, c0 = n0 - tap * cv.C;
-#pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              if (j % CS == cl_rank) tma_load_4d_mc(sb + j * 8192, &tmB, c0 + j * 64, px0 + tap % 3 - 1, py0 + tap / 3 - 1, pb, full, cl_mask);
-          }
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_4d(sb + j * 8192, &tmB, c0 + j * 64, px0 + tap % 3 - 1, py0 + tap / 3 - 1, pb, full);
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ================================ MMA issuer ================================
-    constexpr uint32_t idesc = umma_idesc(T2_BM, BN, (A_MODE == 1 || A_MODE == 3) ? 1 : 0, B_MODE != 0 ? 1 : 0);
+  } else if (warp == 1 && lane == 0 && (CS == 1 || cl_rank == 0)) {
+    // ================================ MMA issuer (pair mode: the leader CTA only) ================================
+    constexpr uint32_t idesc = umma_idesc(T2_BM * CS, BN, (A_MODE == 1 || A_MODE == 3) ? 1 : 0, B_MODE != 0 ? 1 : 0);
     uint32_t it = 0, tc = 0;
     for (int t = cl_id; t < n_work; t += n_cl, ++tc) {
       T2_DECODE(t)
@@ -204,12 +214,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int k = 0; k < T2_BK / 16; ++k) {
           const uint64_t ad = (A_MODE == 1 || A_MODE == 3) ? umma_smem_desc(sa + k * 2048, 8192, 1024) : umma_smem_desc(sa + k * 32, 0, 1024);
           const uint64_t bd = (B_MODE != 0) ? umma_smem_desc(sb + k * 2048, 8192, 1024) : umma_smem_desc(sb + k * 32, 0, 1024);
-          umma_bf16(tacc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          if (CS == 1) umma_bf16(tacc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          else umma_bf16_2cta(tacc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
         }
         if (CS == 1) umma_commit(bar_empty + 8 * s);
-        else umma_commit_mc(bar_empty + 8 * s, cl_mask);   // the stage is free once EVERY CTA of the cluster has read it
+        else umma_commit_2cta(bar_empty + 8 * s, cl_mask);   // frees this stage in BOTH CTAs once the pair's MMAs have read it
       }
-      umma_commit(bar_tfull + 8 * ab);
+      if (CS == 1) umma_commit(bar_tfull + 8 * ab);
+      else umma_commit_2cta(bar_tfull + 8 * ab, cl_mask);     // accumulators complete: both CTAs' epilogues may start
     }
   } else if (warp == 3 && lane == 0) {
     // ================================ TMA loader of the epilogue operand ================================
@@ -226,9 +238,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp >= 4) {
-    // ================================ epilogue (8 warps: lane quarter q, column half hf) ================================
+    // ================================ epilogue (4 T2_NQ warps: lane quarter q, column group hf) ================================
     const int ew = warp - 4, q = ew & 3, hf = ew >> 2, row = q * 32 + lane, etid = threadIdx.x - 128;
-    constexpr int CH = OUT_F32 ? 16 : 32;     // accumulator columns per thread per sub-tile (64 bytes of output)
+    constexpr int CH = S::SUB_COLS / T2_NQ;   // accumulator columns per thread per sub-tile
+    constexpr int CPT = 8 / T2_NQ;            // 16-byte chunks of the 128-byte output row per thread
     uint32_t tc = 0, e = 0;
     // One named barrier per sub-tile: thread 0 waits until every TMA store issued so far has finished READING shared
     // memory right before the barrier, so after it the other buffer (last stored one sub-tile ago) may be overwritten
@@ -265,13 +278,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (x_in) mbar_wait(bar_xfull + 8 * b, (e / S::EPI_BUFS) & 1);
         uint32_t v[CH];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * BN + sub * S::SUB_COLS + hf * CH;
-        if (OUT_F32) tmem_ld16_nowait(taddr, *reinterpret_cast<uint32_t(*)[16]>(v));
-        else tmem_ld32_nowait(taddr, *reinterpret_cast<uint32_t(*)[32]>(v));
-        uint32_t xr[16];
+        tmem_ld_n_nowait<CH>(taddr, v);
+        uint32_t xr[4 * CPT];
         if (x_in) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t src = sx + (((hf * 4 + c) ^ (row & 7)) << 4);
+          for (int c = 0; c < CPT; ++c) {
+            const uint32_t src = sx + (((hf * CPT + c) ^ (row & 7)) << 4);
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xr[4 * c]), "=r"(xr[4 * c + 1]), "=r"(xr[4 * c + 2]), "=r"(xr[4 * c + 3]) : "r"(src));
           }
         }
@@ -279,7 +291,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (sub == S::NSUB - 1) {       // accumulator fully read: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * ab);
+          if (lane == 0) { if (CS == 1) mbar_arrive(bar_tempty + 8 * ab); else mbar_arrive_cluster(bar_tempty + 8 * ab, 0); }
         }
         float f[CH];
 #pragma unroll
@@ -302,22 +314,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int j = 0; j < CH; ++j) f[j] += __uint_as_float(xr[j]);
           }
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t off = (((hf * 4 + c) ^ (row & 7)) << 4);
+          for (int c = 0; c < CPT; ++c) {
+            const uint32_t off = (((hf * CPT + c) ^ (row & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sd + off), "r"(__float_as_uint(f[4 * c])), "r"(__float_as_uint(f[4 * c + 1])),
                          "r"(__float_as_uint(f[4 * c + 2])), "r"(__float_as_uint(f[4 * c + 3])) : "memory");
           }
         } else {
-          uint32_t pre[16];
+          uint32_t pre[CH / 2];
           if (ep.act == 1) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < CH / 2; ++j) {
               pre[j] = pack2_bf16(f[2 * j], f[2 * j + 1]);
               f[2 * j] = gelu_fast_f(f[2 * j]); f[2 * j + 1] = gelu_fast_f(f[2 * j + 1]);
             }
           } else if (ep.act == 2) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < CH / 2; ++j) {
               const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xr[j]));
               f[2 * j] *= gelu_grad_fast_f(h.x); f[2 * j + 1] *= gelu_grad_fast_f(h.y);
             }
@@ -328,37 +340,49 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           if (ep.x_mode == 1) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < CH / 2; ++j) {
               const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xr[j]));
               f[2 * j] += h.x; f[2 * j + 1] += h.y;
             }
           }
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t off = (((hf * 4 + c) ^ (row & 7)) << 4);
+          for (int c = 0; c < CPT; ++c) {
+            const uint32_t off = (((hf * CPT + c) ^ (row & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sd + off), "r"(pack2_bf16(f[8 * c], f[8 * c + 1])), "r"(pack2_bf16(f[8 * c + 2], f[8 * c + 3])),
                          "r"(pack2_bf16(f[8 * c + 4], f[8 * c + 5])), "r"(pack2_bf16(f[8 * c + 6], f[8 * c + 7])) : "memory");
             if (ep.act == 1)
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sx + off), "r"(pre[4 * c]), "r"(pre[4 * c + 1]), "r"(pre[4 * c + 2]), "r"(pre[4 * c + 3]) : "memory");
           }
           if (ep.colsum) {
-            // column sums of the 32 rows of this warp: recursive halving over the lanes (31 shuffles); lane l ends
-            // up with column l of this 32-column chunk; rows beyond M contribute nothing
+            // column sums of the 32 rows of this warp: recursive halving over the lanes while more than one column is
+            // held, plain butterfly adds afterwards; lane l ends up with column l >> (5 - log2 CH) of this CH-column chunk
+            // (the lowest lane of each group of 32 / CH writes); rows beyond M contribute nothing
             const bool row_ok = (int64_t)m_blk * T2_BM + row < M;
-            float cs[32];
+            float cs[CH];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) cs[j] = row_ok ? __bfloat162float(__float2bfloat16_rn(f[j])) : 0.f;
+            for (int j = 0; j < CH; ++j) cs[j] = row_ok ? f[j] : 0.f;   // fp32 values: the exact bias gradient, no F2F round trips
+            int held = CH;
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) {
-              const bool hi = (lane & off) != 0;
+              if (held > 1) {
+                const int hlf = held >> 1;
+                const bool hi = (lane & off) != 0;
 #pragma unroll
-              for (int j = 0; j < off; ++j) {
-                const float send = hi ? cs[j] : cs[j + off];
-                const float recv = __shfl_xor_sync(0xffffffffu, send, off);
-                cs[j] = (hi ? cs[j + off] : cs[j]) + recv;
+                for (int j = 0; j < CH / 2; ++j) {
+                  if (j < hlf) {
+                    const float send = hi ? cs[j] : cs[j + hlf];
+                    const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+                    cs[j] = (hi ? cs[j + hlf] : cs[j]) + recv;
+                  }
+                }
+                held = hlf;
+              } else {
+                cs[0] += __shfl_xor_sync(0xffffffffu, cs[0], off);
               }
             }
-            if (n0 + lane < N) atomicAdd(ep.colsum + n0 + lane, cs[0]);
+            constexpr int LPC = 32 / CH;          // lanes per column
+            const int col = lane / LPC;
+            if ((lane % LPC) == 0 && n0 + col < N) atomicAdd(ep.colsum + n0 + col, cs[0]);
           }
         }
         if (x_in) { __syncwarp(); if (lane == 0) mbar_arrive(bar_xempty + 8 * b); }
@@ -385,7 +409,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (CS > 1) cluster_sync_all();          // no CTA leaves while a peer may still multicast into it or arrive on its barriers
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, S::TMEM_COLS); }
+  if (warp == 2) { tc_fence_after(); if (CS == 2) tmem_dealloc_2cta(tmem_base, S::TMEM_COLS); else tmem_dealloc(tmem_base, S::TMEM_COLS); }
 #undef T2_DECODE
 }
 
@@ -407,6 +431,12 @@ static int make_map_2d_f32(CUtensorMap* m, const void* p, int64_t inner, int64_t
   return r == CUDA_SUCCESS ? MTUS_OK : MTUS_ERR_DRIVER;
 }
 
+// Measured on B200 at the Swin-B stage-3 shapes (M = 6272; profiles/r2_gemm_cta_pair_ab.txt): the CTA-pair engine is parity-
+// clean but SLOWER than single-CTA tiles (qkv fwd 13.2 -> 18.9 us, fc1 21.5 -> 25.6 us): 25 m-pairs x n-tiles quantise worse on
+// 74 pairs than 49 x n-tiles on 148 CTAs (qkv: 3 waves instead of 2), and at 1-3 tiles per CTA these kernels are bound by the
+// epilogue and by fill / drain latency, not by the operand stream the pairing halves.  Kept for large-M GEMMs, off by default.
+static bool t2_pair_default() { return false; }
+
 static int g_sm_count = 0;
 static int sm_count() {
   if (!g_sm_count) {
@@ -426,7 +456,7 @@ static int t2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   auto kern = gemm_tc2_kernel<BN, A_MODE, B_MODE, OUT_F32, CS>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Smem<BN, OUT_F32>::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Smem<BN, OUT_F32, CS>::TOTAL);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
@@ -437,7 +467,7 @@ static int t2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   const int n_cl = n_units < max_cl ? n_units : max_cl;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n_cl * CS); cfg.blockDim = dim3(T2_THREADS);
-  cfg.dynamicSmemBytes = T2Smem<BN, OUT_F32>::TOTAL; cfg.stream = st;
+  cfg.dynamicSmemBytes = T2Smem<BN, OUT_F32, CS>::TOTAL; cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -516,9 +546,17 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
   CUtensorMap ta, tb, tx, td;
   T2Conv cv{};
   int rc;
-  // wide tiles: plain Linear shapes only (K-major A); fp32 output (residual stream) with K-major B
-  const bool wide_ok = !d->a_conv && !d->b_conv && !d->a_mn_major && (!d->out_f32 || !d->b_mn_major);
-  const int BN = t2_pick_bn(M, N, K, wide_ok);
+  // wide tiles: plain Linear shapes (K-major A; fp32 output = residual stream only with K-major B) and the Linear weight
+  // gradients (both operands MN-major, fp32 reduce-add output): a 128x256 tile pulls 48 KB per k-block for twice the MACs of
+  // a 128x128 tile's 32 KB -- the weight gradients are L2->SM operand-bound (K = all tokens), so this is +33 % flop per byte
+  const bool lin_wgrad = !d->a_conv && !d->b_conv && d->a_mn_major && d->b_mn_major && d->out_f32 && d->atomic;
+  const bool wide_ok = (!d->a_conv && !d->b_conv && !d->a_mn_major && (!d->out_f32 || !d->b_mn_major)) || lin_wgrad;
+  int BN = t2_pick_bn(M, N, K, wide_ok && !lin_wgrad);
+  if (lin_wgrad) {
+    static int wg_bn = -1;
+    if (wg_bn < 0) { const char* e = getenv("MTUS_WGRAD_BN"); wg_bn = e ? atoi(e) : 128; }   // measured: 128x256 weight-gradient tiles are 5-20 % SLOWER (fewer, longer work items)
+    BN = (N <= 64) ? 64 : ((wg_bn == 256 && N % 256 == 0) ? 256 : 128);
+  }
   int m_tiles = ceil_div(M, T2_BM), n_tiles = ceil_div(N, BN), total_kb = ceil_div(K, T2_BK);
   if (d->a_conv || d->b_conv) {
     cv.H = d->conv_h; cv.W = d->conv_w; cv.C = d->conv_c;
@@ -531,9 +569,9 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
   {
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("MTUS_CLUSTER"); forced = e ? atoi(e) : 0; }
-    CS = forced ? forced : 1;   // measured: multicasting B across a 2-CTA cluster does not speed these shapes up (not L2-bound)
-    if (CS != 1 && CS != 2) CS = 2;
-    if (m_tiles < 2 || BN < 128) CS = 1;
+    // CTA pairs (cta_group::2) for the plain Linear shapes with 256-wide tiles: MTUS_CLUSTER=1 disables, =2 forces where legal
+    const bool pair_ok = !d->a_conv && !d->b_conv && !d->a_mn_major && BN == 256 && m_tiles >= 2;
+    CS = (forced == 1) ? 1 : ((pair_ok && (forced == 2 || t2_pair_default())) ? 2 : 1);
   }
   int am, bm;
   if (d->a_conv) {
@@ -575,19 +613,31 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
 
   int splits = d->split_k > 0 ? d->split_k : 1;
   if (!d->atomic) splits = 1;
+  if (lin_wgrad && d->split_k > 0 && BN != 128) {
+    // the caller sized split_k for 128x128 tiles; keep the same number of work items (~4 waves) with this tile width
+    const int64_t tiles = (int64_t)m_tiles * n_tiles;
+    int64_t want = (4ll * sm_count() + tiles - 1) / tiles;
+    const int64_t maxs = total_kb / 4 > 0 ? total_kb / 4 : 1;
+    if (want > maxs) want = maxs;
+    if (want < 1) want = 1;
+    splits = (int)want;
+  }
   if (splits > total_kb) splits = total_kb;
   const int kbps = ceil_div(total_kb, splits);
   splits = ceil_div(total_kb, kbps);
 
 #define T2_GO2(BN_, AM_, BM_, F32_)                                                                                                  \
   {                                                                                                                                  \
-    if (CS == 2) return t2_launch<BN_, AM_, BM_, F32_, 2>(ta, tb, tx, td, M, N, K, kbps, total_kb, m_tiles, n_tiles, splits, cv, ep, st); \
+    if constexpr (BN_ == 256 && AM_ == 0 && BM_ != 2) {                                                                              \
+      if (CS == 2) return t2_launch<BN_, AM_, BM_, F32_, 2>(ta, tb, tx, td, M, N, K, kbps, total_kb, m_tiles, n_tiles, splits, cv, ep, st); \
+    }                                                                                                                                \
     return t2_launch<BN_, AM_, BM_, F32_, 1>(ta, tb, tx, td, M, N, K, kbps, total_kb, m_tiles, n_tiles, splits, cv, ep, st);              \
   }
 #define T2_GO(BN_, AM_, BM_, F32_) T2_GO2(BN_, AM_, BM_, F32_)
   if (d->out_f32) {
     if (BN == 256) {
       if (am == 0 && bm == 0) T2_GO(256, 0, 0, true);
+      if (am == 1 && bm == 1) T2_GO(256, 1, 1, true);
     } else if (BN == 192) {
       if (am == 0 && bm == 0) T2_GO(192, 0, 0, true);
     } else if (BN == 128) {

@@ -18,20 +18,26 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
-  uint32_t spins = 0;
+  uint32_t polls = 0;
+  uint64_t t0 = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)      // suspend-time hint (ns): park the warp instead of re-polling (polls cost issue slots)
         : "memory");
     if (done) break;
-    if (++spins > (1u << 26)) {  // a lost arrive must fault, never hang the GPU
-      printf("mtus gemm_tc: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
-             threadIdx.x);
-      __trap();
+    // a lost arrive must fault, never hang the GPU: wall-clock bound (2 s), checked every 64 unsuccessful polls
+    if ((++polls & 63u) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) {
+        printf("mtus gemm_tc: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+        __trap();
+      }
     }
   }
 }
@@ -121,6 +127,44 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
 
+// ---- CTA pairs (cta_group::2): one tcgen05.mma spans both SMs of a 2-CTA cluster -------------------------------------------
+// Each CTA holds 128 rows of A and HALF of the B tile; the leader CTA (cluster rank 0) issues the MMAs, which read A and B
+// from both CTAs' shared memory at the same offsets and write 128 accumulator rows into each CTA's TMEM.  Per SM and
+// k-block the operand traffic is A + B/2 instead of A + B: these GEMMs are L2 -> SM operand-bound (gemm_tc2.cu header).
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// completion of all prior MMAs of the pair -> one arrive on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+// TMA loads of a CTA pair: data lands in the issuing CTA's shared memory, the transaction bytes are signalled on the LEADER's
+// barrier (shared::cluster address of the same offset in rank 0: the CTA-rank bit 24 of the window address cleared)
+#define MTUS_PEER_BIT_MASK 0xFEFFFFFFu
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar & MTUS_PEER_BIT_MASK)
+      : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
 // ---- additions used by the persistent kernel -------------------------------------------------------
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -169,6 +213,19 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+}
+template <int N> __device__ __forceinline__ void tmem_ld_n_nowait(uint32_t taddr, uint32_t (&r)[N]) {
+  static_assert(N == 8 || N == 16 || N == 32, "tcgen05.ld 32x32b.xN: N in {8, 16, 32}");
+  if constexpr (N == 8) tmem_ld8_nowait(taddr, r);
+  else if constexpr (N == 16) tmem_ld16_nowait(taddr, r);
+  else tmem_ld32_nowait(taddr, r);
 }
 __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);

@@ -15,6 +15,8 @@ Module / parameter names match the reference so its checkpoints load.  Under the
 smp) are not available on the benchmark box.
 """
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -105,6 +107,8 @@ class _Conv3x3Fn(torch.autograd.Function):
 
 
 def _native_conv_ok(x, conv):
+    if os.environ.get("MTUS_HEAD_CONV", "native") != "native":      # A/B switch for measurements only (cuDNN path)
+        return False
     return (x.is_cuda and x.dim() == 4 and x.dtype in (torch.bfloat16, torch.float32) and conv.kernel_size == (3, 3)
             and conv.padding == (1, 1) and conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
             and conv.bias is None and conv.in_channels % 64 == 0 and conv.out_channels % 64 == 0)

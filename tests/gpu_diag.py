@@ -179,7 +179,9 @@ def _gemm_group(backend, dts):
             ys = ops.linear_fwd_stream(x, w, bias, res=resf, rowscale=rs, rows_per_sample=rps, backend=backend)
             ok &= report(f"linear_fwd_stream (fp32 out + fp32 residual)", ys, resf + sc * yr, max(tol * 0.05, 2e-5) if dt == torch.bfloat16 else tol)
             dx3, cs3 = ops.linear_dgrad(dy, w, gelu_pre=hp, backend=backend, with_colsum=True)
-            ok &= report(f"linear_dgrad*gelu' + colsum", cs3, dx3.float().sum(0), 2e-4)
+            # the fused column sum adds the fp32 (un-rounded) values: compare with the fp32 reference of dx, not with the
+            # sum of the stored bf16 values (those differ by the accumulated rounding, ~2^-9 of the term scale)
+            ok &= report(f"linear_dgrad*gelu' + colsum", cs3, hpf.grad.sum(0), 3e-3 if dt == torch.bfloat16 else 2e-4)
             dw, db = ops.linear_wgrad(dy, x, backend=backend)
             ok &= report(f"linear_wgrad dw", dw, dy.float().t() @ x.float(), max(tol, 1e-4))
             ok &= report(f"linear_wgrad db", db, dy.float().sum(0), max(tol, 1e-4))
