@@ -447,12 +447,12 @@ int mtus_window_attn_mma_fwd(const void* qkv, const float* rel_table, const floa
   if (B == 0) return MTUS_OK;
   const int blocks = am_plan(g, AM_FWD_OCC);
   const size_t smem = am_cta_bytes(false);
-  static bool configured = false;
-  if (!configured) {
+  static mtus_per_device_flag configured;
+  if (!configured.get()) {
     cudaError_t e = cudaFuncSetAttribute(window_attn_mma_fwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(window_attn_mma_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    configured = true;
+    configured.set();
   }
   cudaError_t le;
   if (g.N <= 56) le = mtus_launch_pdl(window_attn_mma_fwd_kernel<7>, dim3(blocks), dim3(AM_WARPS * 32), smem, st, (const bf16*)qkv, rel_table, qkv_bias, (bf16*)out, lse, g);
@@ -473,12 +473,12 @@ int mtus_window_attn_mma_bwd(const void* dout, const void* qkv, const void* out,
   if (B == 0) return MTUS_OK;
   const int blocks = am_plan(g, AM_BWD_OCC);
   const size_t smem = am_cta_bytes(true);
-  static bool configured = false;
-  if (!configured) {
+  static mtus_per_device_flag configured;
+  if (!configured.get()) {
     cudaError_t e = cudaFuncSetAttribute(window_attn_mma_bwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(window_attn_mma_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    configured = true;
+    configured.set();
   }
   cudaError_t le;
   if (g.N <= 56)

@@ -461,11 +461,11 @@ int mtus_window_attn_mma144_fwd(const void* qkv, const float* rel_table, const f
   if ((g.Hp != H || g.Wp != W) && !qkv_bias) return MTUS_ERR_BAD_ARG;
   if (B == 0) return MTUS_OK;
   const size_t smem = a4_fwd_bytes();
-  static bool configured = false;
-  if (!configured) {
+  static mtus_per_device_flag configured;
+  if (!configured.get()) {
     cudaError_t e = cudaFuncSetAttribute(window_attn_mma144_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    configured = true;
+    configured.set();
   }
   cudaError_t le = mtus_launch_pdl(window_attn_mma144_fwd_kernel, dim3(g.groups * heads), dim3(A4_THREADS), smem, st, (const bf16*)qkv, rel_table,
                                    qkv_bias, (bf16*)out, lse, g);
@@ -484,11 +484,11 @@ int mtus_window_attn_mma144_bwd(const void* dout, const void* qkv, const void* o
   if ((g.Hp != H || g.Wp != W) && !(qkv_bias && dqkv_bias)) return MTUS_ERR_BAD_ARG;
   if (B == 0) return MTUS_OK;
   const size_t smem = a4_bwd_bytes(g.ntab);
-  static bool configured = false;
-  if (!configured) {
+  static mtus_per_device_flag configured;
+  if (!configured.get()) {
     cudaError_t e = cudaFuncSetAttribute(window_attn_mma144_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
     if (e != cudaSuccess) return (int)e;
-    configured = true;
+    configured.set();
   }
   cudaError_t le = mtus_launch_pdl(window_attn_mma144_bwd_kernel, dim3(g.groups * heads), dim3(A4_THREADS), smem, st, (const bf16*)dout, (const bf16*)qkv,
                                    (const bf16*)out, lse, rel_table, qkv_bias, (bf16*)dqkv, drel_table, dqkv_bias, dqkv_colsum, g);

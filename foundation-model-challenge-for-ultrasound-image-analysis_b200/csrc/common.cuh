@@ -17,6 +17,14 @@ extern "C" void mtus_internal_count_launches(int n);
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Function attributes (cudaFuncSetAttribute: opt-in shared memory above 48 KB) are PER DEVICE: a process that drives several
+// GPUs must set them once on each, not once per process.
+struct mtus_per_device_flag {
+  bool done[64] = {};
+  bool get() const { int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false; return done[dev]; }
+  void set() { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true; }
+};
+
 // ---- programmatic dependent launch (PDL) ----------------------------------------------------
 // The kernels of the encoder chain (LayerNorm, GEMM, attention) are launched with programmatic stream serialization:
 // kernel N+1 may be scheduled while kernel N is still running, executes its prologue (barrier / TMEM set-up, table

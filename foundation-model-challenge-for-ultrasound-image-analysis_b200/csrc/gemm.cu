@@ -4,7 +4,6 @@
 #include <stdlib.h>
 #include <string.h>
 
-static int g_no_tc2 = 0;
 static int g_force_backend = -1;  // MTUS_GEMM env override: "simt" | "tc"
 
 static int forced_backend() {
@@ -13,7 +12,6 @@ static int forced_backend() {
     g_force_backend = 0;
     if (e && !strcmp(e, "simt")) g_force_backend = MTUS_BACKEND_SIMT;
     if (e && !strcmp(e, "tc")) g_force_backend = MTUS_BACKEND_TCGEN05;
-    if (e && !strcmp(e, "tc1")) { g_force_backend = MTUS_BACKEND_TCGEN05; g_no_tc2 = 1; }  // A/B: one-tile-per-CTA engine
   }
   return g_force_backend;
 }
@@ -39,12 +37,12 @@ extern "C" int mtus_gemm(const mtus_gemm_desc* d, void* stream) {
   if (f) backend = f;
   if (backend == MTUS_BACKEND_AUTO) backend = (d->dtype == MTUS_BF16) ? MTUS_BACKEND_TCGEN05 : MTUS_BACKEND_SIMT;
   if (backend == MTUS_BACKEND_TCGEN05) {
-    if (!g_no_tc2 && mtus_gemm_tc2_supported(d)) return mtus_gemm_tc2(d, st);   // persistent TMA-in / TMA-out engine
+    if (mtus_gemm_tc2_supported(d)) return mtus_gemm_tc2(d, st);   // persistent TMA-in / TMA-out tcgen05 engine
+    if (d->backend == MTUS_BACKEND_TCGEN05 && !f) return MTUS_ERR_UNSUPPORTED;  // explicit request: fail loudly
   }
-  int rc;
-  if (backend == MTUS_BACKEND_TCGEN05 && !d->res_f32 && mtus_gemm_tc_supported(d)) rc = mtus_gemm_tc(d, ep, st);
-  else if (backend == MTUS_BACKEND_TCGEN05 && d->backend == MTUS_BACKEND_TCGEN05 && !f) return MTUS_ERR_UNSUPPORTED;  // explicit request: fail loudly
-  else rc = mtus_gemm_simt(d, ep, st);
+  // shapes the tensor-core engine does not take (unaligned leading dimensions, conv weight gradients with Cin % 128 != 0,
+  // fp32 mode): the SIMT engine
+  int rc = mtus_gemm_simt(d, ep, st);
   if (rc) return rc;
   // engines without the fused column sum: one stand-alone pass over the stored output
   if (d->out_colsum) {

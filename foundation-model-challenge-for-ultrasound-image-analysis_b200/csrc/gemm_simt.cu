@@ -2,7 +2,7 @@
 //
 // This is the *fp32 parity mode* engine (north_star: "fp32 mode within rtol 1e-4" -- tcgen05
 // kind::tf32 keeps only 10 mantissa bits, so exact-fp32 contractions stay on the FMA pipes) and
-// the bring-up engine for bf16 storage.  The bf16 production path is gemm_tc.cu (tcgen05/TMEM/TMA).
+// the bring-up engine for bf16 storage.  The bf16 production path is gemm_tc2.cu (tcgen05/TMEM/TMA).
 //
 // Replaces: the nn.Linear calls of timm WindowAttention.qkv/proj, Mlp.fc1/fc2,
 // PatchMerging.reduction, PatchEmbed.proj (as im2col GEMM) and smp FPN 1x1 / 3x3 convs

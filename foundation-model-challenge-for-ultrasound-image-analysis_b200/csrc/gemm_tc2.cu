@@ -10,7 +10,7 @@
 //     memory -> TMA store (bf16) or TMA reduce-add (fp32, split-K weight gradients).  No per-thread global
 //     loads or stores: every byte of HBM traffic of this kernel moves through TMA, fully coalesced.
 //
-// Operand forms are those of gemm_tc.cu (K-major / MN-major / implicit-im2col 4-D boxes) plus the conv3x3 weight
+// Operand forms: K-major / MN-major 2-D tiles, implicit-im2col 4-D boxes (3x3 convolutions), and the conv3x3 weight
 // gradient (both operands pixel-major 4-D boxes).  Replaces the cuBLAS / cuDNN calls behind timm's nn.Linear
 // layers and smp's FPN convolutions.
 //
@@ -454,11 +454,11 @@ static int t2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
                      int N, int K, int kbps, int total_kb, int m_tiles, int n_tiles, int splits, const T2Conv& cv,
                      const T2Epi& ep, cudaStream_t st) {
   auto kern = gemm_tc2_kernel<BN, A_MODE, B_MODE, OUT_F32, CS>;
-  static bool configured = false;
-  if (!configured) {
+  static mtus_per_device_flag configured;
+  if (!configured.get()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Smem<BN, OUT_F32, CS>::TOTAL);
     if (e != cudaSuccess) return (int)e;
-    configured = true;
+    configured.set();
   }
   const int64_t units64 = (int64_t)splits * ceil_div(m_tiles, CS) * n_tiles;
   if (units64 > (1ll << 30)) return MTUS_ERR_UNSUPPORTED;

@@ -407,6 +407,14 @@ extern "C" int mtus_convert(const void* x, void* y, int B, int R, int Cc, int tr
 
 // ---- flat AdamW (decoupled weight decay) over a contiguous fp32 parameter block, with the global-norm clip
 //      coefficient read from device memory (no host sync): torch.optim.AdamW update rule (code/train.py:208,446,455) ----
+// Deterministic: every block leaves its partial sum in a per-device scratch slot and the LAST block to finish adds the slots up
+// in index order, so the same gradient gives the same norm bit for bit -- on every rank of a data-parallel job (replicas that
+// clip with norms differing in the last bit drift apart; an atomicAdd per block would order the additions by arrival).
+// The scratch is per device and calls are stream-ordered (the optimizer issues them back to back on one stream).
+#define MTUS_SUMSQ_MAX_BLOCKS (148 * 8)
+__device__ float g_sumsq_partial[MTUS_SUMSQ_MAX_BLOCKS];
+__device__ unsigned int g_sumsq_ticket = 0;
+
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n4, float* __restrict__ out) {
   float acc = 0.f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -416,12 +424,23 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   }
   acc = warp_sum(acc);
   __shared__ float red[8];
+  __shared__ bool last;
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int i = 0; i < 8; ++i) s += red[i];
-    atomicAdd(out, s);
+    g_sumsq_partial[blockIdx.x] = s;
+    __threadfence();
+    last = (atomicAdd(&g_sumsq_ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x < 32) {
+    __threadfence();
+    float s = 0.f;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += 32) s += __ldcg(&g_sumsq_partial[i]);   // fixed assignment of slots to lanes
+    s = warp_sum(s);                                                                                 // fixed butterfly order
+    if (threadIdx.x == 0) { *out += s; g_sumsq_ticket = 0; }
   }
 }
 

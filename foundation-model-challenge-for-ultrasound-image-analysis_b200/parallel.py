@@ -145,7 +145,11 @@ class GradAllReducer:
                 flat = torch.zeros(sum(sizes), dtype=ps[0].dtype, device=ps[0].device)
                 views, off = [], 0
                 for p, n in zip(ps, sizes):
-                    views.append((p, flat[off:off + p.numel()].view_as(p)))
+                    # same sizes AND strides as the parameter (channels-last conv weights): fused optimizers require
+                    # gradient and parameter layouts to agree
+                    dense = p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last)
+                    v = flat[off:off + p.numel()]
+                    views.append((p, v.as_strided(p.shape, p.stride()) if dense else v.view_as(p)))
                     off += n
                 ent = self._head_blocks[id(mod)] = (flat, views)
             flat, views = ent

