@@ -83,6 +83,7 @@ SIGNATURES = {
     "mtus_patch_embed_im2col": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_patch_embed_im2col_u8": (i32, [vp, _P(f32), _P(f32), vp, i32, i32, i32, i32, vp]),
     "mtus_window_attn_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "mtus_window_attn_tc_launch_count": (i64, []),
     "mtus_window_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mtus_upsample_add_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_upsample_add_bwd": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),

@@ -13,6 +13,7 @@
 // Stand-alone this op is HBM-bound (24.5 FLOP/B at N=49): algorithmic bytes per token =
 // 4*C*s forward (q,k,v in, o out), 8*C*s backward (q,k,v,o,do in; dq,dk,dv out).
 #include "common.cuh"
+#include "internal.h"
 #include <stdlib.h>
 #include <string.h>
 
@@ -241,6 +242,8 @@ extern "C" int mtus_window_attn_fwd(const void* qkv, const float* rel_table, con
                                     int B, int H, int W, int C, int heads, int win_h, int win_w, int shift_h, int shift_w,
                                     int dtype, void* stream) {
   MTUS_CHECK_ARG(qkv && rel_table && out);
+  if (mtus_window_attn_tc_eligible(B, H, W, C, heads, win_h, win_w, shift_h, shift_w, dtype))      // tcgen05 / TMEM / TMA engine
+    return mtus_window_attn_tc_fwd(qkv, rel_table, out, lse, B, H, W, C, heads, win_h, win_w, shift_h, shift_w, (cudaStream_t)stream);
   if (att_use_mma(win_h, win_w, dtype))
     return mtus_window_attn_mma_fwd(qkv, rel_table, qkv_bias, out, lse, B, H, W, C, heads, win_h, win_w, shift_h, shift_w, (cudaStream_t)stream);
   if (att_use_mma144(win_h, win_w, dtype) && lse)

@@ -16,6 +16,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+#ifndef MTUS_MBAR_HINT_NS
+#define MTUS_MBAR_HINT_NS 200u
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   uint32_t polls = 0;
@@ -26,7 +29,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(20000u)      // suspend-time hint (ns): park the warp instead of re-polling (polls cost issue slots)
+        : "r"(bar), "r"(parity), "r"(MTUS_MBAR_HINT_NS)      // suspend-time hint (ns): park the warp instead of re-polling (polls cost issue slots)
         : "memory");
     if (done) break;
     // a lost arrive must fault, never hang the GPU: wall-clock bound (2 s), checked every 64 unsuccessful polls

@@ -149,6 +149,9 @@ int mtus_patch_embed_im2col(const void* x_nchw, void* cols, int B, int H, int W,
 int mtus_window_attn_fwd(const void* qkv, const float* rel_table, const float* qkv_bias, void* out, float* lse, int B,
                          int H, int W, int C, int heads, int win_h, int win_w, int shift_h, int shift_w, int dtype,
                          void* stream);
+/* launches of the tcgen05 / TMEM / TMA forward engine (attention_tc.cu; opt-in with MTUS_ATTN_TC=1: bf16, windows <= 64 tokens,
+ * unpadded maps, even head count) since process start -- lets tests assert which engine ran. */
+int64_t mtus_window_attn_tc_launch_count(void);
 /* out = the forward output (delta_i = dout_i . out_i); lse = what forward wrote (required by the tensor-core engine:
  * bf16, windows of <= 64 tokens; [B*H*W, heads] fp32, log2 domain; may be NULL for the general engine);
  * dqkv fully written; drel_table [(2wh-1)(2ww-1), heads] and dqkv_bias [3C] (gradient reaching the bias through

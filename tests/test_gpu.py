@@ -621,3 +621,20 @@ def test_uint8_input_pipeline_fused_into_patch_embed(precision, tol):
     for k, p in enc.named_parameters():
         c = torch.nn.functional.cosine_similarity(p.grad.flatten(), g_u8[k].flatten(), dim=0).item()
         assert c >= 0.9999, f"{k}: uint8 vs float input gradient cosine {c}"
+
+
+@pytest.mark.parametrize("loads", ["tma", "cpasync"])
+def test_tcgen05_window_attention_engine_parity(loads):
+    """attention_tc.cu (tcgen05.mma + TMEM accumulators + TMA window-row boxes; opt-in with MTUS_ATTN_TC=1): the whole
+    attention kernel group (shifted / unshifted, 7x7 windows, several heads, fp32 reference incl. the backward that consumes
+    its log-sum-exp) in a subprocess with the engine switched on, and a check that the engine really launched."""
+    import subprocess
+    env = dict(os.environ, MTUS_ATTN_TC="1", MTUS_ATTN_TC_LOADS=loads)
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import gpu_diag, mtus_b200 as m; ok = gpu_diag.g_attention(); "
+            "n = m._lib.lib().mtus_window_attn_tc_launch_count(); print('TC_LAUNCHES', n); sys.exit(0 if (ok and n >= 4) else 1)"
+            % (here, os.path.dirname(here)))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:])
+    print(r.stderr[-2000:])
+    assert r.returncode == 0
