@@ -10,6 +10,7 @@
 // fp32 via a two-pass (mean, then centred variance) over registers, warp-shuffle reductions.
 // Algorithmic bytes: fwd 2*rows*C*s (+8 B/row stats), bwd 3*rows*C*s (+ dres: 4*rows*C*s).
 #include "common.cuh"
+#include <stdlib.h>
 
 struct MergeGeom { int B, H, W, C, Ho, Wo; };  // input [B,H,W,C] -> rows (b,i,j) of 4C columns
 
@@ -735,6 +736,12 @@ static int lnv2_fwd_launch(const void* x, const float* gamma, const float* beta,
   return MTUS_OK;
 }
 
+static int ln_bwd_bps_override() {     // MTUS_LN_BWD_BPS: CTAs per SM of the LayerNorm backward (tuning sweeps)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTUS_LN_BWD_BPS"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 template <typename T, typename TDY, typename TX, int MODE>
 static int lnv2_bwd_launch(const LnxBwdArgs& a, MergeGeom g, cudaStream_t st) {
   const int C = a.C, nvec = C / 8;
@@ -743,7 +750,8 @@ static int lnv2_bwd_launch(const LnxBwdArgs& a, MergeGeom g, cudaStream_t st) {
   {                                                                                                          \
     const int rpi = (32 / LPR_) * U_ * 4;                                                                    \
     int64_t blocks = (a.rows + rpi - 1) / rpi;                                                               \
-    if (blocks > 148 * BPS_) blocks = 148 * BPS_;                                                            \
+    const int bps = ln_bwd_bps_override() > 0 ? ln_bwd_bps_override() : BPS_;                                \
+    if (blocks > 148 * bps) blocks = 148 * bps;                                                              \
     auto kern = lnv2_bwd_kernel<T, TDY, TX, LPR_, NV_, U_, MODE>;                                            \
     if (sm > 48 * 1024) {                                                                                    \
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);      \

@@ -259,7 +259,10 @@ class SwinCore(FlatParamModule):
         cross a stage, each with the slice of the flat gradient it completes (the chunk holding a stage's block 0 also
         completes that stage's PatchMerging -- or, for stage 0, the patch-embed -- gradients, which precede the
         blocks in the parameter layout).  Used by the data-parallel wrapper to start all-reducing early."""
-        k = blocks_per_chunk or int(os.environ.get("MTUS_DP_BLOCKS_PER_CHUNK", "6"))
+        # default: one chunk per stage.  Measured at 2 GPUs (profiles/r2_dp_chunk_sweep.txt): 6 blocks per chunk 11.75 ms/step,
+        # 12 -> 11.48, per stage -> 11.27 (one GPU: 10.88): every extra chunk costs a graph launch, a join of the weight-gradient
+        # stream and an NCCL enqueue, which outweighs starting the reduction of the long stage earlier
+        k = blocks_per_chunk or int(os.environ.get("MTUS_DP_BLOCKS_PER_CHUNK", "24"))
         cached = getattr(self, "_chunk_cache", None)
         if cached is not None and cached[0] == k:
             return cached[1]
