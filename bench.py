@@ -281,8 +281,11 @@ def _kernel_rooflines(peaks, device):
     t, by = kbench.time_fpn_merge(32, 56, 128, 4, device)
     hbm_entry("merge_nhwc_fwd cat + Dropout2d scale -> [32,56,56,512] bf16", t, by)
     t, by = kbench.time_groupnorm_relu(32, 56, 128, device)
-    hbm_entry("gn_stats + gn_relu_fwd GroupNorm(32)+ReLU [32,56,56,128] bf16 (pair)", t, by,
-              pair_moves_bytes=1.5 * by, frac_of_bytes_moved=round(1.5 * by / t / 1e9 / hbm, 4))
+    hbm_entry("gn_fused_fwd_kernel GroupNorm(32)+ReLU [32,56,56,128] bf16 (one cluster kernel: statistics through distributed shared "
+              "memory, one read + one write)", t, by)
+    t, by = kbench.time_groupnorm_relu(32, 56, 128, device, fused=False)
+    hbm_entry("gn_stats x2 + gn_relu_fwd, the two-pass fallback of the same op (3 reads + 1 write)", t, by,
+              pair_moves_bytes=2.0 * by, frac_of_bytes_moved=round(2.0 * by / t / 1e9 / hbm, 4))
     t, by = kbench.time_bilinear(32, 28, 128, device)
     hbm_entry("bilinear2x_fwd [32,28,28,128] -> [32,56,56,128] bf16 (align_corners)", t, by)
     for (H, Cc_, heads, tag) in ((56, 128, 4, "stage 1"), (14, 512, 16, "stage 3")):

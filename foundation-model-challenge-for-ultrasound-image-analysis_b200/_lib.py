@@ -92,6 +92,7 @@ SIGNATURES = {
     "mtus_groupnorm_relu_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_groupnorm_act_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "mtus_groupnorm_act_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "mtus_groupnorm_act_fused_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, i32, vp]),
     "mtus_batchnorm_stats": (i32, [vp, vp, vp, i64, i32, f32, i32, vp]),
     "mtus_batchnorm_act_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
     "mtus_batchnorm_act_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),

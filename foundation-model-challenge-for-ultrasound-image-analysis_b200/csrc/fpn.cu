@@ -8,6 +8,7 @@
 // cat, feature_dropout_ that eager PyTorch runs for smp (reached from
 // /root/reference/code/models/decoders.py:42-49).  HBM roofline; 16-byte vectorised, coalesced.
 #include "common.cuh"
+#include <stdlib.h>
 
 static inline int grid_for(int64_t work_items, int threads, int max_blocks = 148 * 16) {
   int64_t b = (work_items + threads - 1) / threads;
@@ -161,6 +162,12 @@ extern "C" int mtus_groupnorm_stats(const void* x, float* mean, float* rstd, int
 
 // ACT 0: ReLU (smp Conv3x3GNReLU) | ACT 1: SiLU (the reference's segmentation head, code/models/heads.py:16-42)
 __device__ __forceinline__ float gn_sigmoid(float z) { return 1.0f / (1.0f + __expf(-z)); }
+// z = (x - mean) * rstd * gamma + beta evaluated as ONE fma x * a + s with a = rstd * gamma, s = beta - mean * a.  Every kernel
+// that needs z (forward, fused forward, the backward's ReLU-gate recomputation) uses this form, so the gate is bit-identical.
+__device__ __forceinline__ void gn_affine(float mean, float rstd, float gamma, float beta, float& a, float& s) {
+  a = rstd * gamma;
+  s = fmaf(-mean, a, beta);
+}
 
 template <typename T, int ACT>
 __global__ void gn_relu_fwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -178,11 +185,175 @@ __global__ void gn_relu_fwd_kernel(const T* __restrict__ x, const float* __restr
     for (int k = 0; k < 8; ++k) {
       const int g = (v * 8 + k) / cpg;
       const float m = __ldg(mean + b * G + g), r = __ldg(rstd + b * G + g);
-      const float z = (a[k] - m) * r * gm[k] + bt[k];
+      float ga, gs;
+      gn_affine(m, r, gm[k], bt[k], ga, gs);
+      const float z = fmaf(a[k], ga, gs);
       a[k] = ACT == 0 ? fmaxf(z, 0.f) : z * gn_sigmoid(z);
     }
     IO<T>::store8(y + i * 8, a);
   }
+}
+
+// ---- fused GroupNorm + activation forward: ONE kernel, one HBM read + one HBM write (the algorithmic minimum) ------------------
+// A thread-block CLUSTER of CL CTAs owns one sample: each CTA pulls its slice of the sample's pixels into shared memory once
+// (cp.async, every load of the CTA in flight together), the per-group sums are exchanged through DISTRIBUTED SHARED MEMORY
+// (cluster.map_shared_rank), and mean -> centred variance -> normalise + activation all run out of shared memory.  Replaces
+// memset x2 + gn_stats x2 + gn_finalize + gn_relu_fwd (6 launches, 3 reads + 1 write of the tensor).  mean / rstd are still
+// written for the backward.  Used when a sample's slice fits (bf16 [56,56,128] = 98 KB per CTA at CL = 8); everything else
+// (fp32 at the largest map, BatchNorm's single "sample" of all rows) stays on the two-pass kernels above.
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+template <typename T, int ACT>
+__global__ void __launch_bounds__(256) gn_fused_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int HW, int C,
+                                                           int G, int ppc, float eps) {
+  extern __shared__ __align__(16) uint8_t gf_smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int b = blockIdx.y, C8 = C / 8, cpg = C / G, tid = threadIdx.x;
+  const int p0 = min(HW, rank * ppc), p1 = min(HW, p0 + ppc), npix = p1 - p0, nvec = npix * C8;
+  T* sdata = reinterpret_cast<T*>(gf_smem);                                   // [ppc][C]
+  float* sred = reinterpret_cast<float*>(gf_smem + (size_t)ppc * C * sizeof(T));   // [C] per-channel partial sums
+  float* sgA = sred + C;        // [G] this CTA's group sums (read by the peers)
+  float* sgB = sgA + G;         // [G] this CTA's centred group sums of squares
+  float* smu = sgB + G;         // [G]
+  float* srs = smu + G;         // [G]
+  const T* src = x + ((int64_t)b * HW + p0) * C;
+  constexpr int PIECES = sizeof(T) * 8 / 16;                                  // 16-byte pieces per 8-element vector
+  for (int i = tid; i < nvec * PIECES; i += 256) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<uint8_t*>(sdata) + (size_t)i * 16);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(reinterpret_cast<const uint8_t*>(src) + (size_t)i * 16) : "memory");
+  }
+  for (int c = tid; c < C; c += 256) sred[c] = 0.f;
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // this thread's vectors: i = tid + 256 j -> channel vector v = tid % C8 for every j (256 % C8 == 0)
+  const int v = tid % C8;
+  auto ld8 = [&](int i, float (&a)[8]) {
+    if (sizeof(T) == 2) {
+      const uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(sdata) + (size_t)i * 16);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h[k]); a[2 * k] = f.x; a[2 * k + 1] = f.y; }
+    } else {
+      const float4 lo = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(sdata) + (size_t)i * 32);
+      const float4 hi = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(sdata) + (size_t)i * 32 + 16);
+      a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w; a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
+    }
+  };
+  // block reduction of 8 per-thread channel sums: lanes that hold the same channel vector first (C8 < 32), then shared atomics
+  auto block_reduce = [&](float (&acc)[8]) {
+    for (int off = C8; off < 32; off <<= 1) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+    }
+    if ((tid & 31) < C8 || C8 >= 32) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(&sred[v * 8 + k], acc[k]);
+    }
+  };
+  // cluster-wide group totals of the per-channel sums in sred, through this CTA's slot sg (read remotely by the peers)
+  auto cluster_total = [&](float* sg, float* dst, bool is_var) {
+    __syncthreads();
+    for (int g = tid; g < G; g += 256) {
+      float t = 0.f;
+      for (int k = 0; k < cpg; ++k) t += sred[g * cpg + k];
+      sg[g] = t;
+    }
+    cluster.sync();
+    const float inv_n = 1.0f / ((float)HW * (float)cpg);
+    for (int g = tid; g < G; g += 256) {
+      float t = 0.f;
+      for (int r = 0; r < CL; ++r) t += cluster.map_shared_rank(sg, r)[g];
+      dst[g] = is_var ? rsqrtf(t * inv_n + eps) : t * inv_n;
+    }
+    __syncthreads();
+  };
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int i = tid; i < nvec; i += 256) {
+    float a[8];
+    ld8(i, a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += a[k];
+  }
+  block_reduce(acc);
+  cluster_total(sgA, smu, false);
+  float mu[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) mu[k] = smu[(v * 8 + k) / cpg];
+  for (int c = tid; c < C; c += 256) sred[c] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int i = tid; i < nvec; i += 256) {
+    float a[8];
+    ld8(i, a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float d = a[k] - mu[k]; acc[k] = fmaf(d, d, acc[k]); }
+  }
+  block_reduce(acc);
+  cluster_total(sgB, srs, true);
+  cluster.barrier_arrive();                             // this CTA has read its peers' slots; it may not exit before they have read its own
+  if (rank == 0) {
+    for (int g = tid; g < G; g += 256) { mean_out[b * G + g] = smu[g]; rstd_out[b * G + g] = srs[g]; }
+  }
+  float ga[8], gs[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = v * 8 + k;
+    gn_affine(mu[k], srs[c / cpg], __ldg(gamma + c), __ldg(beta + c), ga[k], gs[k]);
+  }
+  T* dstp = y + ((int64_t)b * HW + p0) * C;
+  for (int i = tid; i < nvec; i += 256) {
+    float a[8];
+    ld8(i, a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float z = fmaf(a[k], ga[k], gs[k]);
+      a[k] = ACT == 0 ? fmaxf(z, 0.f) : z * gn_sigmoid(z);
+    }
+    IO<T>::store8(dstp + (size_t)i * 8, a);
+  }
+  cluster.barrier_wait();
+}
+
+// cluster size and pixels per CTA of the fused kernel; 0 = not eligible
+static int gn_fused_plan(int B, int HW, int C, int G, int esize, int& ppc, size_t& smem) {
+  const int C8 = C / 8;
+  if (C % 8 || C8 > 256 || 256 % C8 || G <= 0 || C % G || B > 65535 || HW <= 0) return 0;
+  int CL = 8;
+  while (CL > 1 && (int64_t)B * CL > 2 * 148) CL >>= 1;                     // about one wave of CTAs at two per SM
+  while (CL < 8 && (int64_t)((HW + CL - 1) / CL) * C * esize > 100 * 1024) CL <<= 1;
+  ppc = (HW + CL - 1) / CL;
+  smem = (size_t)ppc * C * esize + sizeof(float) * (C + 4 * G) + 16;
+  if (smem > 200 * 1024) return 0;
+  return CL;
+}
+
+template <typename T, int ACT>
+static int gn_fused_launch(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int B, int HW, int C, int G,
+                           float eps, int CL, int ppc, size_t smem, cudaStream_t st) {
+  auto kern = gn_fused_fwd_kernel<T, ACT>;
+  static mtus_per_device_flag configured;
+  if (!configured.get()) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    configured.set();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CL, B); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, (const T*)x, gamma, beta, (T*)y, mean, rstd, HW, C, G, ppc, eps);
+  if (e != cudaSuccess) return (int)e;
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
 }
 
 extern "C" int mtus_groupnorm_act_fwd(const void* x, const float* mean, const float* rstd, const float* gamma,
@@ -205,17 +376,43 @@ extern "C" int mtus_groupnorm_relu_fwd(const void* x, const float* mean, const f
   return mtus_groupnorm_act_fwd(x, mean, rstd, gamma, beta, y, B, HW, C, G, 0, dtype, stream);
 }
 
-// d act(z) / dz times dy.  ReLU: mask from the saved output y; SiLU: z recomputed from x (sigma(z) (1 + z (1 - sigma(z)))).
-template <int ACT>
-__device__ __forceinline__ float gn_act_grad(float dy, float yv, float xh, float gm, float bt) {
-  if (ACT == 0) return yv > 0.f ? dy : 0.f;
-  const float z = xh * gm + bt, sg = gn_sigmoid(z);
+// statistics + normalise + activation in one call: the fused cluster kernel when a sample's slice fits in shared memory,
+// else mtus_groupnorm_stats followed by mtus_groupnorm_act_fwd.  mean / rstd [B, G] are outputs (saved for the backward).
+extern "C" int mtus_groupnorm_act_fused_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int B,
+                                            int HW, int C, int G, float eps, int act, int dtype, void* stream) {
+  MTUS_CHECK_ARG(x && gamma && beta && y && mean && rstd && (act == 0 || act == 1));
+  MTUS_CHECK_ARG(dtype == MTUS_F32 || dtype == MTUS_BF16);
+  if (B == 0 || HW == 0) return MTUS_OK;
+  static int use_fused = -1;
+  if (use_fused < 0) { const char* e = getenv("MTUS_GN_FUSED"); use_fused = e ? atoi(e) : 1; }
+  int ppc = 0; size_t smem = 0;
+  const int CL = use_fused ? gn_fused_plan(B, HW, C, G, dtype == MTUS_F32 ? 4 : 2, ppc, smem) : 0;
+  if (CL > 0) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MTUS_F32) return act == 0 ? gn_fused_launch<float, 0>(x, gamma, beta, y, mean, rstd, B, HW, C, G, eps, CL, ppc, smem, st)
+                                           : gn_fused_launch<float, 1>(x, gamma, beta, y, mean, rstd, B, HW, C, G, eps, CL, ppc, smem, st);
+    return act == 0 ? gn_fused_launch<bf16, 0>(x, gamma, beta, y, mean, rstd, B, HW, C, G, eps, CL, ppc, smem, st)
+                    : gn_fused_launch<bf16, 1>(x, gamma, beta, y, mean, rstd, B, HW, C, G, eps, CL, ppc, smem, st);
+  }
+  const int rc = mtus_groupnorm_stats(x, mean, rstd, B, HW, C, G, eps, dtype, stream);
+  if (rc) return rc;
+  return mtus_groupnorm_act_fwd(x, mean, rstd, gamma, beta, y, B, HW, C, G, act, dtype, stream);
+}
+
+// d act(z) / dz times dy.  ReLU: gate from the saved output y (USEY) or from z recomputed as x * a + s (the forward's own
+// expression, gn_affine: one read of the tensor less); SiLU: z recomputed (sigma(z) (1 + z (1 - sigma(z)))).
+template <int ACT, bool USEY>
+__device__ __forceinline__ float gn_act_grad(float dy, float yv, float xv, float ga, float gs) {
+  if (ACT == 0 && USEY) return yv > 0.f ? dy : 0.f;
+  const float z = fmaf(xv, ga, gs);
+  if (ACT == 0) return z > 0.f ? dy : 0.f;
+  const float sg = gn_sigmoid(z);
   return dy * sg * (1.0f + z * (1.0f - sg));
 }
 
 // backward pass 1: per (b,g) s1 = sum dyr*gamma, s2 = sum dyr*gamma*xhat (ws[0..BG), ws[BG..2BG));
 //                  per channel dgamma += sum dyr*xhat, dbeta += sum dyr     (dyr = dy * (y > 0))
-template <typename T, int ACT>
+template <typename T, int ACT, bool USEY>
 __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ ws,
@@ -226,11 +423,12 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict_
   const int v = threadIdx.x % C8, pl = threadIdx.x / C8, npl = 256 / C8;
   const int b = blockIdx.y;
   const int p0 = blockIdx.x * pix_per_chunk, p1 = min(HW, p0 + pix_per_chunk);
-  float mu[8], rs[8], gm[8], bt[8];
+  float mu[8], rs[8], gm[8], ga[8], gs[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int g = (v * 8 + k) / cpg;
-    mu[k] = mean[b * G + g]; rs[k] = rstd[b * G + g]; gm[k] = gamma[v * 8 + k]; bt[k] = ACT == 0 ? 0.f : beta[v * 8 + k];
+    mu[k] = mean[b * G + g]; rs[k] = rstd[b * G + g]; gm[k] = gamma[v * 8 + k];
+    gn_affine(mu[k], rs[k], gm[k], (ACT == 0 && USEY) ? 0.f : beta[v * 8 + k], ga[k], gs[k]);
   }
   float a1[8], a2[8], ag[8], ab[8];
 #pragma unroll
@@ -240,11 +438,11 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict_
       const int64_t off = ((int64_t)b * HW + p) * C + v * 8;
       float d[8], xv[8], yv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       IO<T>::load8(dy + off, d); IO<T>::load8(x + off, xv);
-      if (ACT == 0) IO<T>::load8(y + off, yv);
+      if (ACT == 0 && USEY) IO<T>::load8(y + off, yv);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float xh = (xv[k] - mu[k]) * rs[k];
-        const float dr = gn_act_grad<ACT>(d[k], yv[k], xh, gm[k], bt[k]);
+        const float dr = gn_act_grad<ACT, USEY>(d[k], yv[k], xv[k], ga[k], gs[k]);
         a1[k] += dr * gm[k]; a2[k] += dr * gm[k] * xh; ag[k] += dr * xh; ab[k] += dr;
       }
     }
@@ -268,7 +466,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const T* __restrict_
   for (int c = threadIdx.x; c < C; c += 256) { atomicAdd(dgamma + c, sred[2 * C + c]); atomicAdd(dbeta + c, sred[3 * C + c]); }
 }
 
-template <typename T, int ACT>
+template <typename T, int ACT, bool USEY>
 __global__ void gn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, const float* __restrict__ ws, T* __restrict__ dx, int64_t total, int B, int HW, int C8, int G,
@@ -280,7 +478,7 @@ __global__ void gn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
     const int64_t b = i / ((int64_t)C8 * HW);
     float d[8], xv[8], yv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gm[8], bt[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, o[8];
     IO<T>::load8(dy + i * 8, d); IO<T>::load8(x + i * 8, xv);
-    if (ACT == 0) IO<T>::load8(y + i * 8, yv); else IO<float>::load8(beta + v * 8, bt);
+    if (ACT == 0 && USEY) IO<T>::load8(y + i * 8, yv); else IO<float>::load8(beta + v * 8, bt);
     IO<float>::load8(gamma + v * 8, gm);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -288,7 +486,9 @@ __global__ void gn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
       const float m = __ldg(mean + b * G + g), r = __ldg(rstd + b * G + g);
       const float s1 = __ldg(ws + b * G + g) * inv_n, s2 = __ldg(ws + (int64_t)B * G + b * G + g) * inv_n;
       const float xh = (xv[k] - m) * r;
-      const float dr = gn_act_grad<ACT>(d[k], yv[k], xh, gm[k], bt[k]);
+      float ga, gs;
+      gn_affine(m, r, gm[k], bt[k], ga, gs);
+      const float dr = gn_act_grad<ACT, USEY>(d[k], yv[k], xv[k], ga, gs);
       o[k] = r * (dr * gm[k] - s1 - xh * s2);
     }
     IO<T>::store8(dx + i * 8, o);
@@ -299,9 +499,10 @@ extern "C" int mtus_groupnorm_act_bwd(const void* dy, const void* x, const void*
                                       const float* gamma, const float* beta, void* dx, float* dgamma, float* dbeta, float* ws,
                                       int B, int HW, int C, int G, int act, int dtype, void* stream) {
   MTUS_CHECK_ARG(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && ws && (act == 0 || act == 1));
-  MTUS_CHECK_ARG(act == 0 ? y != nullptr : beta != nullptr);
+  MTUS_CHECK_ARG(act == 0 ? (y != nullptr || beta != nullptr) : beta != nullptr);   // ReLU: gate from y, or recomputed when beta is given
   MTUS_CHECK_ARG(C % 8 == 0 && C / 8 <= 256 && G > 0 && C % G == 0 && B <= 65535);
   if (B == 0) return MTUS_OK;
+  const bool usey = act == 0 && beta == nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(float) * 2 * B * G, st);
   if (e != cudaSuccess) return (int)e;
@@ -309,13 +510,13 @@ extern "C" int mtus_groupnorm_act_bwd(const void* dy, const void* x, const void*
   dim3 grid(chunks, B);
   const size_t sm = sizeof(float) * 4 * C;
   const int64_t total = (int64_t)B * HW * (C / 8);
-#define GN_BWD(T_, ACT_)                                                                                                                  \
+#define GN_BWD(T_, ACT_, UY_)                                                                                                             \
   {                                                                                                                                       \
-    gn_bwd_reduce_kernel<T_, ACT_><<<grid, 256, sm, st>>>((const T_*)dy, (const T_*)x, (const T_*)y, mean, rstd, gamma, beta, ws, dgamma, dbeta, B, HW, C, G, ppc); \
-    gn_bwd_apply_kernel<T_, ACT_><<<grid_for(total, 256), 256, 0, st>>>((const T_*)dy, (const T_*)x, (const T_*)y, mean, rstd, gamma, beta, ws, (T_*)dx, total, B, HW, C / 8, G, C / G); \
+    gn_bwd_reduce_kernel<T_, ACT_, UY_><<<grid, 256, sm, st>>>((const T_*)dy, (const T_*)x, (const T_*)y, mean, rstd, gamma, beta, ws, dgamma, dbeta, B, HW, C, G, ppc); \
+    gn_bwd_apply_kernel<T_, ACT_, UY_><<<grid_for(total, 256), 256, 0, st>>>((const T_*)dy, (const T_*)x, (const T_*)y, mean, rstd, gamma, beta, ws, (T_*)dx, total, B, HW, C / 8, G, C / G); \
   }
-  if (dtype == MTUS_F32) { if (act == 0) GN_BWD(float, 0) else GN_BWD(float, 1) }
-  else if (dtype == MTUS_BF16) { if (act == 0) GN_BWD(bf16, 0) else GN_BWD(bf16, 1) }
+  if (dtype == MTUS_F32) { if (act == 1) GN_BWD(float, 1, false) else if (usey) GN_BWD(float, 0, true) else GN_BWD(float, 0, false) }
+  else if (dtype == MTUS_BF16) { if (act == 1) GN_BWD(bf16, 1, false) else if (usey) GN_BWD(bf16, 0, true) else GN_BWD(bf16, 0, false) }
   else return MTUS_ERR_UNSUPPORTED;
 #undef GN_BWD
   MTUS_LAUNCH_STATUS_N(2);
@@ -354,14 +555,14 @@ extern "C" int mtus_batchnorm_act_bwd(const void* dy, const void* x, const void*
   dim3 grid(chunks, B);
   const size_t sm = sizeof(float) * 4 * C;
   const int64_t total = (int64_t)HW * (C / 8);
-#define BN_BWD(T_, ACT_)                                                                                                                  \
+#define BN_BWD(T_, ACT_, UY_)                                                                                                             \
   {                                                                                                                                       \
-    gn_bwd_reduce_kernel<T_, ACT_><<<grid, 256, sm, st>>>((const T_*)dy, (const T_*)x, (const T_*)y, mean, rstd, gamma, beta, ws, dgamma, dbeta, B, HW, C, G, ppc); \
+    gn_bwd_reduce_kernel<T_, ACT_, UY_><<<grid, 256, sm, st>>>((const T_*)dy, (const T_*)x, (const T_*)y, mean, rstd, gamma, beta, ws, dgamma, dbeta, B, HW, C, G, ppc); \
     if (!training) { e = cudaMemsetAsync(ws, 0, sizeof(float) * 2 * B * G, st); if (e != cudaSuccess) return (int)e; }                   \
-    gn_bwd_apply_kernel<T_, ACT_><<<grid_for(total, 256), 256, 0, st>>>((const T_*)dy, (const T_*)x, (const T_*)y, mean, rstd, gamma, beta, ws, (T_*)dx, total, B, HW, C / 8, G, C / G); \
+    gn_bwd_apply_kernel<T_, ACT_, UY_><<<grid_for(total, 256), 256, 0, st>>>((const T_*)dy, (const T_*)x, (const T_*)y, mean, rstd, gamma, beta, ws, (T_*)dx, total, B, HW, C / 8, G, C / G); \
   }
-  if (dtype == MTUS_F32) { if (act == 0) BN_BWD(float, 0) else BN_BWD(float, 1) }
-  else if (dtype == MTUS_BF16) { if (act == 0) BN_BWD(bf16, 0) else BN_BWD(bf16, 1) }
+  if (dtype == MTUS_F32) { if (act == 0) BN_BWD(float, 0, true) else BN_BWD(float, 1, false) }
+  else if (dtype == MTUS_BF16) { if (act == 0) BN_BWD(bf16, 0, true) else BN_BWD(bf16, 1, false) }
   else return MTUS_ERR_UNSUPPORTED;
 #undef BN_BWD
   MTUS_LAUNCH_STATUS_N(2);
@@ -384,64 +585,85 @@ __device__ __forceinline__ void bil_src(int o, float scale, int in_size, int& i0
   l0 = 1.0f - l1;
 }
 
+// grid (ceil(Wo * C8 / 256), ceil(Ho / 4), B): a thread produces the same (ox, channel vector) of FOUR consecutive output rows;
+// all their taps (at most 3 input rows x 2 columns are distinct) are requested before the first is used, 32-bit index math only
+#define BIL_ROWS 4
 template <typename T>
-__global__ void bilinear_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C8, float sy, float sx) {
-  const int Ho = 2 * H, Wo = 2 * W;
-  const int64_t total = (int64_t)B * Ho * Wo * C8, stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int c = (int)(i % C8); int64_t p = i / C8;
-    const int ox = (int)(p % Wo); p /= Wo; const int oy = (int)(p % Ho); const int64_t b = p / Ho;
-    int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
-    bil_src(oy, sy, H, y0, y1, ly0, ly1);
-    bil_src(ox, sx, W, x0, x1, lx0, lx1);
-    const T* base = x + b * H * (int64_t)W * C8 * 8 + c * 8;
-    float a[8], bq[8], cc[8], d[8], o[8];
-    IO<T>::load8(base + ((int64_t)y0 * W + x0) * C8 * 8, a);
-    IO<T>::load8(base + ((int64_t)y0 * W + x1) * C8 * 8, bq);
-    IO<T>::load8(base + ((int64_t)y1 * W + x0) * C8 * 8, cc);
-    IO<T>::load8(base + ((int64_t)y1 * W + x1) * C8 * 8, d);
+__global__ void __launch_bounds__(256) bilinear_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, int C8, float sy, float sx) {
+  const int Wo = 2 * W, Ho = 2 * H, oy0 = blockIdx.y * BIL_ROWS, b = blockIdx.z;
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= Wo * C8) return;
+  const int c = j % C8, ox = j / C8;
+  int x0, x1; float lx0, lx1;
+  bil_src(ox, sx, W, x0, x1, lx0, lx1);
+  const T* base = x + ((int64_t)b * H * W * C8 + c) * 8;
+  float a[BIL_ROWS][8], bq[BIL_ROWS][8], cc[BIL_ROWS][8], d[BIL_ROWS][8], ly0[BIL_ROWS], ly1[BIL_ROWS];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = ly0 * (lx0 * a[k] + lx1 * bq[k]) + ly1 * (lx0 * cc[k] + lx1 * d[k]);
-    IO<T>::store8(y + i * 8, o);
+  for (int r = 0; r < BIL_ROWS; ++r) {
+    const int oy = min(oy0 + r, Ho - 1);
+    int y0, y1;
+    bil_src(oy, sy, H, y0, y1, ly0[r], ly1[r]);
+    IO<T>::load8(base + (int64_t)(y0 * W + x0) * C8 * 8, a[r]);
+    IO<T>::load8(base + (int64_t)(y0 * W + x1) * C8 * 8, bq[r]);
+    IO<T>::load8(base + (int64_t)(y1 * W + x0) * C8 * 8, cc[r]);
+    IO<T>::load8(base + (int64_t)(y1 * W + x1) * C8 * 8, d[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < BIL_ROWS; ++r) {
+    if (oy0 + r >= Ho) break;
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = ly0[r] * (lx0 * a[r][k] + lx1 * bq[r][k]) + ly1[r] * (lx0 * cc[r][k] + lx1 * d[r][k]);
+    IO<T>::store8(y + ((((int64_t)b * Ho + oy0 + r) * Wo + ox) * C8 + c) * 8, o);
   }
 }
 
-// gather-form backward: each input pixel collects from the output pixels whose 4 taps touch it
-template <typename T>
-__global__ void bilinear_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int H, int W, int C8, float sy, float sx) {
-  const int Ho = 2 * H, Wo = 2 * W;
-  const int64_t total = (int64_t)B * H * W * C8, stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int c = (int)(i % C8); int64_t p = i / C8;
-    const int ix = (int)(p % W); p /= W; const int iy = (int)(p % H); const int64_t b = p / H;
-    // candidate output range: r = s*o in (i-1, i+1)  =>  o in ((i-1)/s, (i+1)/s); widened by 1 for rounding
-    int oy_lo = (sy > 0.f) ? (int)floorf((float)(iy - 1) / sy) - 1 : 0, oy_hi = (sy > 0.f) ? (int)ceilf((float)(iy + 1) / sy) + 1 : Ho - 1;
-    int ox_lo = (sx > 0.f) ? (int)floorf((float)(ix - 1) / sx) - 1 : 0, ox_hi = (sx > 0.f) ? (int)ceilf((float)(ix + 1) / sx) + 1 : Wo - 1;
-    oy_lo = max(oy_lo, 0); oy_hi = min(oy_hi, Ho - 1); ox_lo = max(ox_lo, 0); ox_hi = min(ox_hi, Wo - 1);
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
-      int y0, y1; float ly0, ly1;
-      bil_src(oy, sy, H, y0, y1, ly0, ly1);
-      float wy = 0.f;
-      if (y0 == iy) wy += ly0;
-      if (y1 == iy) wy += ly1;
-      if (wy == 0.f) continue;
-      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-        int x0, x1; float lx0, lx1;
-        bil_src(ox, sx, W, x0, x1, lx0, lx1);
-        float wx = 0.f;
-        if (x0 == ix) wx += lx0;
-        if (x1 == ix) wx += lx1;
-        if (wx == 0.f) continue;
-        float v[8];
-        IO<T>::load8(dy + (((b * Ho + oy) * (int64_t)Wo + ox) * C8 + c) * 8, v);
-        const float wgt = wy * wx;
+// Weights with which input index i receives from the (at most 8) output indices o_lo .. o_lo + 7 along one axis: output o
+// touches i through its tap y0 (weight l0) and / or y1 (weight l1).  r = s * o lies in (i - 1, i + 1) for every contributor,
+// so o_lo = floor((i - 1) / s) - 1 (clamped) starts early enough and 2 / s <= 6 candidates plus the rounding margin fit in 8.
+__device__ __forceinline__ int bil_gather_weights(int i, float s, int in_size, int out_size, float (&w)[8]) {
+  int o_lo = (s > 0.f) ? (int)floorf((float)(i - 1) / s) - 1 : 0;
+  o_lo = max(o_lo, 0);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += wgt * v[k];
-      }
-    }
-    IO<T>::store8(dx + i * 8, acc);
+  for (int t = 0; t < 8; ++t) {
+    const int o = o_lo + t;
+    int i0, i1; float l0, l1;
+    bil_src(o, s, in_size, i0, i1, l0, l1);
+    float wt = 0.f;
+    if (i0 == i) wt += l0;
+    if (i1 == i) wt += l1;
+    w[t] = (o < out_size) ? wt : 0.f;
   }
+  return o_lo;
+}
+
+// gather-form backward (atomic-free): each input pixel collects from the output pixels whose taps touch it.
+// grid (ceil(W * C8 / 256), H, B)
+template <typename T>
+__global__ void __launch_bounds__(256) bilinear_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int H, int W, int C8, float sy, float sx) {
+  const int Wo = 2 * W, Ho = 2 * H, iy = blockIdx.y, b = blockIdx.z;
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= W * C8) return;
+  const int c = j % C8, ix = j / C8;
+  float wy[8], wx[8];
+  const int oy_lo = bil_gather_weights(iy, sy, H, Ho, wy);
+  const int ox_lo = bil_gather_weights(ix, sx, W, Wo, wx);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const T* base = dy + ((int64_t)b * Ho * Wo * C8 + c) * 8;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    if (wy[t] == 0.f) continue;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float wgt = wy[t] * wx[u];
+      if (wgt == 0.f) continue;
+      float v[8];
+      IO<T>::load8(base + (int64_t)((oy_lo + t) * Wo + ox_lo + u) * C8 * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, v[k], acc[k]);
+    }
+  }
+  IO<T>::store8(dx + ((((int64_t)b * H + iy) * W + ix) * C8 + c) * 8, acc);
 }
 
 static inline float ac_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
@@ -452,8 +674,10 @@ extern "C" int mtus_bilinear2x_fwd(const void* x, void* y, int B, int H, int W, 
   if (n == 0) return MTUS_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const float sy = ac_scale(H, 2 * H), sx = ac_scale(W, 2 * W);
-  if (dtype == MTUS_F32) bilinear_fwd_kernel<float><<<grid_for(n, 256), 256, 0, st>>>((const float*)x, (float*)y, B, H, W, C / 8, sy, sx);
-  else if (dtype == MTUS_BF16) bilinear_fwd_kernel<bf16><<<grid_for(n, 256), 256, 0, st>>>((const bf16*)x, (bf16*)y, B, H, W, C / 8, sy, sx);
+  MTUS_CHECK_ARG(2 * H <= 65535 && B <= 65535);
+  const dim3 grid(ceil_div(2 * W * (C / 8), 256), ceil_div(2 * H, BIL_ROWS), B);
+  if (dtype == MTUS_F32) bilinear_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, H, W, C / 8, sy, sx);
+  else if (dtype == MTUS_BF16) bilinear_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)y, H, W, C / 8, sy, sx);
   else return MTUS_ERR_UNSUPPORTED;
   MTUS_LAUNCH_STATUS();
   return MTUS_OK;
@@ -465,8 +689,10 @@ extern "C" int mtus_bilinear2x_bwd(const void* dy, void* dx, int B, int H, int W
   if (n == 0) return MTUS_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const float sy = ac_scale(H, 2 * H), sx = ac_scale(W, 2 * W);
-  if (dtype == MTUS_F32) bilinear_bwd_kernel<float><<<grid_for(n, 256), 256, 0, st>>>((const float*)dy, (float*)dx, B, H, W, C / 8, sy, sx);
-  else if (dtype == MTUS_BF16) bilinear_bwd_kernel<bf16><<<grid_for(n, 256), 256, 0, st>>>((const bf16*)dy, (bf16*)dx, B, H, W, C / 8, sy, sx);
+  MTUS_CHECK_ARG(H <= 65535 && B <= 65535);
+  const dim3 grid(ceil_div(W * (C / 8), 256), H, B);
+  if (dtype == MTUS_F32) bilinear_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, (float*)dx, H, W, C / 8, sy, sx);
+  else if (dtype == MTUS_BF16) bilinear_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dy, (bf16*)dx, H, W, C / 8, sy, sx);
   else return MTUS_ERR_UNSUPPORTED;
   MTUS_LAUNCH_STATUS();
   return MTUS_OK;

@@ -240,8 +240,8 @@ static int fpn_forward_body(const mtus_fpn_config* cfg, const void* const* feats
     for (const ConvL& L : p.tower[i]) {
       RUN(mtus_conv3x3_repack(F(L.w), A(L.wf), p.training ? A(L.wd) : nullptr, p.S, L.cin, dt, stream));
       RUN(mtus_conv3x3_fwd(x, A(L.wf), A(L.t), p.B, L.size, L.size, L.cin, p.S, dt, be, stream));
-      RUN(mtus_groupnorm_stats(A(L.t), FA(L.mean), FA(L.rstd), p.B, L.size * L.size, p.S, 32, 1e-5f, dt, stream));
-      RUN(mtus_groupnorm_relu_fwd(A(L.t), FA(L.mean), FA(L.rstd), F(L.gnw), F(L.gnb), A(L.u), p.B, L.size * L.size, p.S, 32, dt, stream));
+      // statistics + normalise + ReLU in one cluster kernel (one read, one write of the map) where a sample fits in shared memory
+      RUN(mtus_groupnorm_act_fused_fwd(A(L.t), F(L.gnw), F(L.gnb), A(L.u), FA(L.mean), FA(L.rstd), p.B, L.size * L.size, p.S, 32, 1e-5f, 0, dt, stream));
       if (L.up) RUN(mtus_bilinear2x_fwd(A(L.u), A(L.v), p.B, L.size, L.size, p.S, dt, stream));
       x = A(L.v);
     }
@@ -318,8 +318,9 @@ static int fpn_backward_body(const mtus_fpn_config* cfg, const void* const* feat
         RUN(mtus_bilinear2x_bwd(g, A(p.s1), p.B, L.size, L.size, p.S, dt, stream));
         du = A(p.s1); dtp = A(p.s2);
       }
-      RUN(mtus_groupnorm_relu_bwd(du, A(L.t), A(L.u), FA(L.mean), FA(L.rstd), F(L.gnw), dtp, GR(L.gnw), GR(L.gnb), FA(p.gnws), p.B, px,
-                                  p.S, 32, dt, stream));
+      // ReLU gate recomputed from x (beta given, y = nullptr): one read of the map less than gating on the saved output
+      RUN(mtus_groupnorm_act_bwd(du, A(L.t), nullptr, FA(L.mean), FA(L.rstd), F(L.gnw), F(L.gnb), dtp, GR(L.gnw), GR(L.gnb), FA(p.gnws), p.B, px,
+                                 p.S, 32, 0, dt, stream));
       cudaError_t e = cudaMemsetAsync(A(p.dwp), 0, (size_t)p.S * 9 * L.cin * 4, st);
       if (e != cudaSuccess) return (int)e;
       RUN(mtus_conv3x3_wgrad(dtp, xin, FA(p.dwp), p.B, L.size, L.size, L.cin, p.S, dt, be, stream));

@@ -279,9 +279,10 @@ def time_fpn_merge(B, H, Cc, nsrc, device):
     return graph_time(_ring(make, by), run), by
 
 
-def time_groupnorm_relu(B, H, Cc, device):
-    """GroupNorm(32) statistics + normalise + ReLU (two kernels, timed as the pair): the statistics pass reads x, the apply
-    pass reads x and writes y: SURVEY counts 2 B H^2 C s (one read + one write); the pair moves 3 B H^2 C s -- both reported."""
+def time_groupnorm_relu(B, H, Cc, device, fused=True):
+    """GroupNorm(32) statistics + normalise + ReLU.  fused: ONE cluster kernel (a sample is read once into shared memory, group
+    sums cross CTAs through distributed shared memory) = the 2 B H^2 C s of SURVEY 8d (one read + one write).  fused=False: the
+    two-pass statistics kernels + the normalise kernel (3 reads + 1 write), the fallback for maps that do not fit."""
     L = _lib.lib()
     bf = torch.bfloat16
     g, b = torch.ones(Cc, device=device), torch.zeros(Cc, device=device)
@@ -292,6 +293,9 @@ def time_groupnorm_relu(B, H, Cc, device):
 
     def run(s):
         x, mean, rstd, y = s
+        if fused:
+            _lib.check(L.mtus_groupnorm_act_fused_fwd(ptr(x), ptr(g), ptr(b), ptr(y), ptr(mean), ptr(rstd), B, H * H, Cc, 32, 1e-5, 0, BF16, _sp()), "gn_fused")
+            return
         _lib.check(L.mtus_groupnorm_stats(ptr(x), ptr(mean), ptr(rstd), B, H * H, Cc, 32, 1e-5, BF16, _sp()), "gn_stats")
         _lib.check(L.mtus_groupnorm_relu_fwd(ptr(x), ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(y), B, H * H, Cc, 32, BF16, _sp()), "gn_relu")
     by = 2.0 * B * H * H * Cc * 2

@@ -224,19 +224,33 @@ def groupnorm_relu_fwd(x, gamma, beta, groups=32, eps=1e-5):
     B, H, W, Cc = x.shape
     mean = torch.empty(B * groups, dtype=torch.float32, device=x.device)
     rstd = torch.empty_like(mean)
+    y = torch.empty_like(x)
+    check(lib().mtus_groupnorm_act_fused_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), B, H * W, Cc, groups, eps, 0, _dt(x), stream_ptr()), "groupnorm_act_fused_fwd")
+    return y, mean, rstd
+
+
+def groupnorm_relu_fwd_two_pass(x, gamma, beta, groups=32, eps=1e-5):
+    """The separate statistics + normalise kernels (what the fused call falls back to for maps that do not fit in shared memory)."""
+    B, H, W, Cc = x.shape
+    mean = torch.empty(B * groups, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
     check(lib().mtus_groupnorm_stats(ptr(x), ptr(mean), ptr(rstd), B, H * W, Cc, groups, eps, _dt(x), stream_ptr()), "groupnorm_stats")
     y = torch.empty_like(x)
     check(lib().mtus_groupnorm_relu_fwd(ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(y), B, H * W, Cc, groups, _dt(x), stream_ptr()), "groupnorm_relu_fwd")
     return y, mean, rstd
 
 
-def groupnorm_relu_bwd(dy, x, y, mean, rstd, gamma, groups=32):
+def groupnorm_relu_bwd(dy, x, y, mean, rstd, gamma, groups=32, beta=None):
+    """beta given: the ReLU gate is recomputed from x (y is not read); beta None: the gate comes from the saved output y."""
     B, H, W, Cc = x.shape
     dx = torch.empty_like(x)
     dg = torch.zeros(Cc, dtype=torch.float32, device=x.device)
     db = torch.zeros_like(dg)
     ws = torch.empty(2 * B * groups, dtype=torch.float32, device=x.device)
-    check(lib().mtus_groupnorm_relu_bwd(ptr(dy), ptr(x), ptr(y), ptr(mean), ptr(rstd), ptr(gamma), ptr(dx), ptr(dg), ptr(db), ptr(ws), B, H * W, Cc, groups, _dt(x), stream_ptr()), "groupnorm_relu_bwd")
+    if beta is not None:
+        check(lib().mtus_groupnorm_act_bwd(ptr(dy), ptr(x), None, ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(dx), ptr(dg), ptr(db), ptr(ws), B, H * W, Cc, groups, 0, _dt(x), stream_ptr()), "groupnorm_act_bwd")
+    else:
+        check(lib().mtus_groupnorm_relu_bwd(ptr(dy), ptr(x), ptr(y), ptr(mean), ptr(rstd), ptr(gamma), ptr(dx), ptr(dg), ptr(db), ptr(ws), B, H * W, Cc, groups, _dt(x), stream_ptr()), "groupnorm_relu_bwd")
     return dx, dg, db
 
 
@@ -245,9 +259,8 @@ def groupnorm_silu_fwd(x, gamma, beta, groups=32, eps=1e-5):
     B, H, W, Cc = x.shape
     mean = torch.empty(B * groups, dtype=torch.float32, device=x.device)
     rstd = torch.empty_like(mean)
-    check(lib().mtus_groupnorm_stats(ptr(x), ptr(mean), ptr(rstd), B, H * W, Cc, groups, eps, _dt(x), stream_ptr()), "groupnorm_stats")
     y = torch.empty_like(x)
-    check(lib().mtus_groupnorm_act_fwd(ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(y), B, H * W, Cc, groups, 1, _dt(x), stream_ptr()), "groupnorm_act_fwd")
+    check(lib().mtus_groupnorm_act_fused_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), B, H * W, Cc, groups, eps, 1, _dt(x), stream_ptr()), "groupnorm_act_fused_fwd")
     return y, mean, rstd
 
 

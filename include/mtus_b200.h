@@ -187,6 +187,13 @@ int mtus_groupnorm_act_fwd(const void* x, const float* mean, const float* rstd, 
 int mtus_groupnorm_act_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* rstd,
                            const float* gamma, const float* beta, void* dx, float* dgamma, float* dbeta, float* ws,
                            int B, int HW, int C, int G, int act, int dtype, void* stream);
+/* Statistics + normalise + activation in ONE call (outputs y and the saved mean / rstd [B, G]): a thread-block-cluster
+ * kernel that reads each sample once into shared memory, exchanges the group sums through distributed shared memory and
+ * writes y once, when a sample's slice fits; otherwise mtus_groupnorm_stats + mtus_groupnorm_act_fwd.  Replaces
+ * native_group_norm + relu / silu of smp Conv3x3GNReLU and of the reference's segmentation head (code/models/heads.py:16-42).
+ * mtus_groupnorm_act_bwd with act = 0: y may be NULL when beta is given (the ReLU gate is recomputed from x). */
+int mtus_groupnorm_act_fused_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                                 int B, int HW, int C, int G, float eps, int act, int dtype, void* stream);
 /* BatchNorm2d + activation over NHWC rows [M = B*H*W, C] (act 0 = ReLU: the reference's baseline detection head,
  * code/models/heads.py:404-428).  stats: per-channel batch mean and 1/sqrt(biased var + eps).  bwd:
  * training = 1 differentiates through the batch statistics, training = 0 treats mean / rstd as constants (running

@@ -292,12 +292,16 @@ def g_fpn_ops():
             x = (torch.randn(B, H, W, Cc, device=dev) * 2 + 0.3).to(dt)
             g = torch.randn(Cc, device=dev) * 0.5 + 1
             b = torch.randn(Cc, device=dev) * 0.1
-            y, mean, rstd = ops.groupnorm_relu_fwd(x, g, b)
+            y, mean, rstd = ops.groupnorm_relu_fwd(x, g, b)                       # fused cluster kernel where a sample fits
+            y2, mean2, rstd2 = ops.groupnorm_relu_fwd_two_pass(x, g, b)           # separate statistics / normalise kernels
             xr = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
             gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
             pre = F.group_norm(xr, 32, gr, br, 1e-5)
             yr = F.relu(pre)
             ok &= report(f"gn_relu_fwd {dt} {B,H,W,Cc}", y, yr.permute(0, 2, 3, 1), tol)
+            ok &= report(f"gn_relu_fwd two-pass", y2, yr.permute(0, 2, 3, 1), tol)
+            ok &= report(f"gn fused mean == two-pass mean", mean, mean2, 1e-5)
+            ok &= report(f"gn fused rstd == two-pass rstd", rstd, rstd2, 1e-5)
             dy = torch.randn(B, H, W, Cc, device=dev).to(dt)
             # the ReLU gate is taken from the kernel's own output: an element whose pre-activation rounds to
             # +-1e-8 may land on either side of 0 and would flip a whole dy term (seen once per ~1e6 elements);
@@ -312,6 +316,12 @@ def g_fpn_ops():
             ok &= report(f"gn_relu_bwd dx", dx, xr.grad.permute(0, 2, 3, 1), max(tol, 1e-4))
             ok &= report(f"gn_relu_bwd dgamma", dg, gr.grad, max(tol, 3e-4))
             ok &= report(f"gn_relu_bwd dbeta", db, br.grad, max(tol, 3e-4))
+            # gate recomputed from x (beta given, y not read): the same expression as the forward, so the same gate
+            dx_r, dg_r, db_r = ops.groupnorm_relu_bwd(dy, x, None, mean, rstd, g, beta=b)
+            # (the group sums are accumulated with atomics: two runs differ in the last bits)
+            ok &= report(f"gn_relu_bwd (recomputed gate) dx", dx_r, dx, 1e-4)
+            ok &= report(f"gn_relu_bwd (recomputed gate) dgamma", dg_r, dg, 1e-4)
+            ok &= report(f"gn_relu_bwd (recomputed gate) dbeta", db_r, db, 1e-4)
             xr2 = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
             ur = F.interpolate(xr2, scale_factor=2.0, mode="bilinear", align_corners=True)
             ok &= report(f"bilinear2x_fwd", ops.bilinear2x_fwd(x), ur.permute(0, 2, 3, 1), tol)
