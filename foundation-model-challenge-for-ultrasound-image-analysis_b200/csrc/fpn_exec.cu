@@ -33,7 +33,7 @@ struct Plan {
   size_t lp;              // bf16 shadow of the flat params (bf16 mode)
   size_t cin_nhwc[4];     // NHWC copies of the inputs when the caller passes NCHW
   size_t pl[4];           // p2..p5
-  size_t gM[4], s1, s2, gP[4], tmpL, dwp, gnws;   // backward scratch
+  size_t gM[4], s1[4], s2[4], gP[4], tmpL, dwp[4], gnws[4];   // backward scratch (s1 / s2 / dwp / gnws per tower: the towers run concurrently)
   size_t cs_slot;         // Dropout2d channel scales copied by forward (the caller's tensor is new every step)
   size_t ws_bytes;
   int out_channels;
@@ -110,14 +110,17 @@ bool build_plan(const mtus_fpn_config* c, Plan& p) {
   if (p.training) {
     const size_t slice = (size_t)p.B * p.size[0] * p.size[0] * p.S * es;
     for (int i = 0; i < 4; ++i) p.gM[i] = a.take(slice);
-    p.s1 = a.take(slice); p.s2 = a.take(slice);
+    for (int i = 0; i < 4; ++i) {
+      // tower i works on maps of at most size[0]^2 pixels; tower 3 (on p2) never upsamples and needs s1 only
+      p.s1[i] = a.take(slice); p.s2[i] = i < 3 ? a.take(slice) : p.s1[i];
+      p.dwp[i] = a.take((size_t)p.S * 9 * (p.P > p.S ? p.P : p.S) * 4);
+      p.gnws[i] = a.take((size_t)2 * p.B * 32 * 4);
+    }
     for (int k = 0; k < 4; ++k) p.gP[k] = a.take((size_t)p.B * p.size[k] * p.size[k] * p.P * es);
     size_t mx = 0;
     for (int k = 0; k < 4; ++k) { const size_t v = (size_t)p.B * p.size[k] * p.size[k] * p.cin[k] * es; if (v > mx) mx = v; }
     p.tmpL = a.take(mx);
-    p.dwp = a.take((size_t)p.S * 9 * (p.P > p.S ? p.P : p.S) * 4);
-    p.gnws = a.take((size_t)2 * p.B * 32 * 4);
-  } else { p.s1 = p.s2 = p.tmpL = p.dwp = p.gnws = 0; for (int k = 0; k < 4; ++k) p.gP[k] = p.gM[k] = 0; }
+  } else { p.tmpL = 0; for (int k = 0; k < 4; ++k) p.gP[k] = p.gM[k] = p.s1[k] = p.s2[k] = p.dwp[k] = p.gnws[k] = 0; }
   p.ws_bytes = a.off;
   return true;
 }
@@ -198,6 +201,35 @@ extern "C" int mtus_fpn_forward_film(const mtus_fpn_config* cfg, const void* con
   return MTUS_OK;
 }
 
+// The four Conv3x3-GN-ReLU(-bilinear) towers are independent of each other and most of their kernels under-fill the machine
+// (a 7x7 map is 13 GEMM tiles, a 14x14 map 49): towers 0-2 run on three side streams, tower 3 (the 56x56 map) on the caller's
+// stream.  Fork / join with events only, so the executor's CUDA-graph capture records the parallel branches.
+// MTUS_FPN_STREAMS=0 keeps everything on the caller's stream.
+struct TowerStreams {
+  cudaStream_t s[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, done[3] = {nullptr, nullptr, nullptr};
+  int state = 0;   // 0 unknown, 1 ready, -1 disabled
+};
+static TowerStreams g_tower_streams[16];
+
+static TowerStreams* tower_streams() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  TowerStreams& ts = g_tower_streams[dev];
+  if (ts.state == 0) {
+    const char* e = getenv("MTUS_FPN_STREAMS");
+    if (e && atoi(e) == 0) { ts.state = -1; return nullptr; }
+    bool ok = cudaEventCreateWithFlags(&ts.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 3; ++i) {
+      ok = ok && cudaStreamCreateWithFlags(&ts.s[i], cudaStreamNonBlocking) == cudaSuccess;
+      ok = ok && cudaEventCreateWithFlags(&ts.done[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    ts.state = ok ? 1 : -1;
+  }
+  return ts.state == 1 ? &ts : nullptr;
+}
+#define CUF(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return (int)e__; } while (0)
+
 static int fpn_forward_body(const mtus_fpn_config* cfg, const void* const* feats, int feats_layout, int feats_f32,
                             const float* params, void* workspace, const void** merged_out, void* stream) {
   Plan p;
@@ -233,20 +265,27 @@ static int fpn_forward_body(const mtus_fpn_config* cfg, const void* const* feats
     RUN(mtus_gemm(&d, stream));
     if (split_add) RUN(mtus_upsample_add_fwd(A(p.pl[k]), A(p.pl[k + 1]), A(p.pl[k]), p.B, p.size[k], p.size[k], p.P, dt, stream));
   }
-  // towers
+  // towers (concurrent: see TowerStreams)
+  TowerStreams* ts = tower_streams();
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ts) CUF(cudaEventRecord(ts->fork, st));
   const void* merged[4];
   for (int i = 0; i < 4; ++i) {
+    void* tstream = (ts && i < 3) ? (void*)ts->s[i] : stream;
+    if (ts && i < 3) CUF(cudaStreamWaitEvent(ts->s[i], ts->fork, 0));
     const void* x = A(p.pl[3 - i]);
     for (const ConvL& L : p.tower[i]) {
-      RUN(mtus_conv3x3_repack(F(L.w), A(L.wf), p.training ? A(L.wd) : nullptr, p.S, L.cin, dt, stream));
-      RUN(mtus_conv3x3_fwd(x, A(L.wf), A(L.t), p.B, L.size, L.size, L.cin, p.S, dt, be, stream));
+      RUN(mtus_conv3x3_repack(F(L.w), A(L.wf), p.training ? A(L.wd) : nullptr, p.S, L.cin, dt, tstream));
+      RUN(mtus_conv3x3_fwd(x, A(L.wf), A(L.t), p.B, L.size, L.size, L.cin, p.S, dt, be, tstream));
       // statistics + normalise + ReLU in one cluster kernel (one read, one write of the map) where a sample fits in shared memory
-      RUN(mtus_groupnorm_act_fused_fwd(A(L.t), F(L.gnw), F(L.gnb), A(L.u), FA(L.mean), FA(L.rstd), p.B, L.size * L.size, p.S, 32, 1e-5f, 0, dt, stream));
-      if (L.up) RUN(mtus_bilinear2x_fwd(A(L.u), A(L.v), p.B, L.size, L.size, p.S, dt, stream));
+      RUN(mtus_groupnorm_act_fused_fwd(A(L.t), F(L.gnw), F(L.gnb), A(L.u), FA(L.mean), FA(L.rstd), p.B, L.size * L.size, p.S, 32, 1e-5f, 0, dt, tstream));
+      if (L.up) RUN(mtus_bilinear2x_fwd(A(L.u), A(L.v), p.B, L.size, L.size, p.S, dt, tstream));
       x = A(L.v);
     }
     merged[i] = x;
+    if (ts && i < 3) CUF(cudaEventRecord(ts->done[i], ts->s[i]));
   }
+  if (ts) for (int i = 0; i < 3; ++i) CUF(cudaStreamWaitEvent(st, ts->done[i], 0));
   for (int i = 0; i < 4; ++i) merged_out[i] = merged[i];
   return MTUS_OK;
 }
@@ -305,31 +344,39 @@ static int fpn_backward_body(const mtus_fpn_config* cfg, const void* const* feat
 
   // towers backward: leaves the gradient w.r.t. p_k in gP[k].  Buffer discipline per layer:
   //   g --bilinear'--> s1 (if upsampling) --GN/ReLU'--> dt (s2 | s1) --dgrad--> old g buffer (dead by then)
+  // (the towers are independent: towers 0-2 on the side streams, each with its own scratch; see TowerStreams)
+  TowerStreams* ts = tower_streams();
+  if (ts) CUF(cudaEventRecord(ts->fork, st));
   for (int i = 0; i < 4; ++i) {
     const int k = 3 - i;
+    void* tstream = (ts && i < 3) ? (void*)ts->s[i] : stream;
+    cudaStream_t tst = (cudaStream_t)tstream;
+    if (ts && i < 3) CUF(cudaStreamWaitEvent(ts->s[i], ts->fork, 0));
     void* g = dm[i];
     for (int l = (int)p.tower[i].size() - 1; l >= 0; --l) {
       const ConvL& L = p.tower[i][l];
       const int px = L.size * L.size;
       const void* xin = l == 0 ? A(p.pl[k]) : A(p.tower[i][l - 1].v);
       const void* du = g;
-      void* dtp = A(p.s1);
+      void* dtp = A(p.s1[i]);
       if (L.up) {
-        RUN(mtus_bilinear2x_bwd(g, A(p.s1), p.B, L.size, L.size, p.S, dt, stream));
-        du = A(p.s1); dtp = A(p.s2);
+        RUN(mtus_bilinear2x_bwd(g, A(p.s1[i]), p.B, L.size, L.size, p.S, dt, tstream));
+        du = A(p.s1[i]); dtp = A(p.s2[i]);
       }
       // ReLU gate recomputed from x (beta given, y = nullptr): one read of the map less than gating on the saved output
-      RUN(mtus_groupnorm_act_bwd(du, A(L.t), nullptr, FA(L.mean), FA(L.rstd), F(L.gnw), F(L.gnb), dtp, GR(L.gnw), GR(L.gnb), FA(p.gnws), p.B, px,
-                                 p.S, 32, 0, dt, stream));
-      cudaError_t e = cudaMemsetAsync(A(p.dwp), 0, (size_t)p.S * 9 * L.cin * 4, st);
+      RUN(mtus_groupnorm_act_bwd(du, A(L.t), nullptr, FA(L.mean), FA(L.rstd), F(L.gnw), F(L.gnb), dtp, GR(L.gnw), GR(L.gnb), FA(p.gnws[i]), p.B, px,
+                                 p.S, 32, 0, dt, tstream));
+      cudaError_t e = cudaMemsetAsync(A(p.dwp[i]), 0, (size_t)p.S * 9 * L.cin * 4, tst);
       if (e != cudaSuccess) return (int)e;
-      RUN(mtus_conv3x3_wgrad(dtp, xin, FA(p.dwp), p.B, L.size, L.size, L.cin, p.S, dt, be, stream));
-      RUN(mtus_conv3x3_unpack_grad(FA(p.dwp), GR(L.w), p.S, L.cin, stream));
+      RUN(mtus_conv3x3_wgrad(dtp, xin, FA(p.dwp[i]), p.B, L.size, L.size, L.cin, p.S, dt, be, tstream));
+      RUN(mtus_conv3x3_unpack_grad(FA(p.dwp[i]), GR(L.w), p.S, L.cin, tstream));
       void* dxin = l == 0 ? A(p.gP[k]) : g;
-      RUN(mtus_conv3x3_dgrad(dtp, A(L.wd), dxin, p.B, L.size, L.size, L.cin, p.S, dt, be, stream));
+      RUN(mtus_conv3x3_dgrad(dtp, A(L.wd), dxin, p.B, L.size, L.size, L.cin, p.S, dt, be, tstream));
       g = dxin;
     }
+    if (ts && i < 3) CUF(cudaEventRecord(ts->done[i], ts->s[i]));
   }
+  if (ts) for (int i = 0; i < 3; ++i) CUF(cudaStreamWaitEvent(st, ts->done[i], 0));
   // top-down chain: Dp_{k+1} += 2x2-sum(Dp_k), k = 0..2 (p2 -> p5)
   for (int k = 0; k < 3; ++k)
     RUN(mtus_upsample_add_bwd(A(p.gP[k]), A(p.gP[k + 1]), 1, p.B, p.size[k], p.size[k], p.P, dt, stream));

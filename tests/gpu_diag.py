@@ -318,8 +318,9 @@ def g_fpn_ops():
             ok &= report(f"gn_relu_bwd dbeta", db, br.grad, max(tol, 3e-4))
             # gate recomputed from x (beta given, y not read): the same expression as the forward, so the same gate
             dx_r, dg_r, db_r = ops.groupnorm_relu_bwd(dy, x, None, mean, rstd, g, beta=b)
-            # (the group sums are accumulated with atomics: two runs differ in the last bits)
-            ok &= report(f"gn_relu_bwd (recomputed gate) dx", dx_r, dx, 1e-4)
+            # (the group sums are accumulated with atomics: two runs differ in the last bits, i.e. by one bf16 ulp of dx in bf16 mode)
+            rt = 1e-4 if dt == torch.float32 else 5e-3
+            ok &= report(f"gn_relu_bwd (recomputed gate) dx", dx_r, dx, rt)
             ok &= report(f"gn_relu_bwd (recomputed gate) dgamma", dg_r, dg, 1e-4)
             ok &= report(f"gn_relu_bwd (recomputed gate) dbeta", db_r, db, 1e-4)
             xr2 = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
