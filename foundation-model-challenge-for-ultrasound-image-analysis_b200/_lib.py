@@ -65,6 +65,8 @@ SIGNATURES = {
     "mtus_linear_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, vp]),
     "mtus_linear_fwd_stream": (i32, [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, vp]),
     "mtus_linear_dgrad": (i32, [vp, vp, vp, vp, vp, i32, vp, i64, i32, i32, i32, i32, vp]),
+    "mtus_linear_fwd_gelu_dact": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
+    "mtus_linear_dgrad_dact": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
     "mtus_layernorm_fwd_mixed": (i32, [vp, i32, vp, vp, vp, i32, vp, vp, i64, i32, f32, i32, vp]),
     "mtus_layernorm_bwd_mixed": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i64, i32, i32, vp]),
     "mtus_patch_merge_ln_fwd_mixed": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp]),

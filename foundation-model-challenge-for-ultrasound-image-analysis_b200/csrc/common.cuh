@@ -156,6 +156,16 @@ __device__ __forceinline__ float gelu_fast_f(float x) {
   float x2, xc, t;
   return x * gelu_sigmoid_core(x, x2, xc, t);
 }
+// value and derivative from ONE evaluation of the sigmoid core (the forward epilogue that stores GELU' for the backward)
+__device__ __forceinline__ float gelu_both_fast_f(float x, float& dgelu) {
+  float x2, xc, t;
+  const float s = gelu_sigmoid_core(x, x2, xc, t);
+  float dq = fmaf(x2, 5.0f * MTUS_GELU_C2, 3.0f * MTUS_GELU_C1);
+  dq = fmaf(dq, x2, MTUS_GELU_C0);
+  const float w = fmaf(-0.25f * t, t, 0.25f);
+  dgelu = fmaf(xc * w, dq, s);
+  return x * s;
+}
 __device__ __forceinline__ float gelu_grad_fast_f(float x) {
   float x2, xc, t;
   const float s = gelu_sigmoid_core(x, x2, xc, t);
@@ -169,6 +179,7 @@ __device__ __forceinline__ float gelu_grad_fast_f(float x) {
 struct EpiParams {
   const float* bias;       // [N] fp32 or null
   int act;                 // 0 none | 1 GELU fwd (pre-activation also written to aux) | 2 GELU bwd (acc *= gelu'(aux))
+                           // 3 GELU fwd (GELU'(pre-activation) written to aux) | 4 acc *= aux (the derivative stored by 3)
   void* aux;               // [M, ld_aux] in the activation dtype
   int64_t ld_aux;
   const void* res;         // residual in the activation dtype, or null
@@ -191,17 +202,20 @@ __device__ __forceinline__ void epilogue4(const EpiParams& ep, int64_t m, int n0
 #pragma unroll
     for (int j = 0; j < 4; ++j) if (j < nvalid) v[j] += __ldg(ep.bias + n0 + j);
   }
-  if (ep.act == 1) {
+  if (ep.act == 1 || ep.act == 3) {
     T* a = reinterpret_cast<T*>(ep.aux) + m * ep.ld_aux + n0;
-    if (nvalid == 4) IO<T>::store4(a, v); else for (int j = 0; j < nvalid; ++j) IO<T>::st(a + j, v[j]);
+    float sv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sv[j] = ep.act == 1 ? v[j] : gelu_grad_f(v[j]);
+    if (nvalid == 4) IO<T>::store4(a, sv); else for (int j = 0; j < nvalid; ++j) IO<T>::st(a + j, sv[j]);
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = gelu_f(v[j]);
-  } else if (ep.act == 2) {
+  } else if (ep.act == 2 || ep.act == 4) {
     const T* a = reinterpret_cast<const T*>(ep.aux) + m * ep.ld_aux + n0;
     float h[4] = {0.f, 0.f, 0.f, 0.f};
     if (nvalid == 4) IO<T>::load4(a, h); else for (int j = 0; j < nvalid; ++j) h[j] = IO<T>::ld(a + j);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] *= gelu_grad_f(h[j]);
+    for (int j = 0; j < 4; ++j) v[j] *= ep.act == 2 ? gelu_grad_f(h[j]) : h[j];
   }
   if (ep.rowscale) {
     const float s = __ldg(ep.rowscale + m / ep.rows_per_sample);

@@ -82,6 +82,37 @@ extern "C" int mtus_linear_fwd(const void* x, const void* w, const float* bias, 
 }
 
 // y (fp32) = res (fp32, optional) + rowscale * (x w^T + bias): Linear layers that write the fp32 residual stream
+// The MLP pair of the bf16 training path.  Forward: y = GELU(x w^T + bias) and dact = GELU'(x w^T + bias) (stored INSTEAD of the
+// pre-activation: it shares the sigmoid / erf of the forward, and the backward's epilogue shrinks to one multiply).
+extern "C" int mtus_linear_fwd_gelu_dact(const void* x, const void* w, const float* bias, void* y, void* dact, int64_t M, int N, int K,
+                                         int dtype, int backend, void* stream) {
+  MTUS_CHECK_ARG(x && w && y && dact && M >= 0 && M < (1ll << 31));
+  mtus_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.a = x; d.lda = K; d.b = w; d.ldb = K;
+  d.M = (int)M; d.N = N; d.K = K;
+  d.bias = bias;
+  d.act = 3; d.aux = dact; d.ld_aux = N;
+  d.out = y; d.ld_out = N;
+  d.dtype = dtype; d.backend = backend;
+  return mtus_gemm(&d, stream);
+}
+
+// dx[M,K] = (dy[M,N] w[N,K]) * dact[M,K] (+ column sums of dx): the data gradient through fc2 and the stored GELU'.
+extern "C" int mtus_linear_dgrad_dact(const void* dy, const void* w, void* dx, const void* dact, float* dx_colsum, int64_t M, int N,
+                                      int K, int dtype, int backend, void* stream) {
+  MTUS_CHECK_ARG(dy && w && dx && dact && M >= 0 && M < (1ll << 31));
+  mtus_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.a = dy; d.lda = N; d.b = w; d.ldb = K; d.b_mn_major = 1;
+  d.M = (int)M; d.N = K; d.K = N;
+  d.act = 4; d.aux = const_cast<void*>(dact); d.ld_aux = K;
+  d.out = dx; d.ld_out = K;
+  d.out_colsum = dx_colsum;
+  d.dtype = dtype; d.backend = backend;
+  return mtus_gemm(&d, stream);
+}
+
 extern "C" int mtus_linear_fwd_stream(const void* x, const void* w, const float* bias, float* y, const float* res,
                                       const float* rowscale, int rows_per_sample, int64_t M, int N, int K, int dtype,
                                       int backend, void* stream) {

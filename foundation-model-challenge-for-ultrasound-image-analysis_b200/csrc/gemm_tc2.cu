@@ -45,7 +45,7 @@ struct T2Epi {
   const float* bias;      // [N] or null
   const float* rowscale;  // per-sample scale or null
   int rows_per_sample;
-  int act;                // 0 none | 1 GELU (pre-activation -> X out) | 2 multiply by GELU'(X in)
+  int act;                // 0 none | 1 GELU (pre-activation -> X out) | 2 multiply by GELU'(X in) | 3 GELU (GELU' -> X out) | 4 multiply by X in
   int x_mode;             // 0 none | 1 residual in (out += X) | 2 aux in (act 2) | 3 aux out (act 1)
   int reduce;             // fp32 output: 1 = TMA reduce-add into the destination (split-K weight gradients), 0 = store
   float* colsum;          // bf16 output only: colsum[n] += sum over rows of the fp32 (un-rounded) output values (bias gradients)
@@ -327,6 +327,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               pre[j] = pack2_bf16(f[2 * j], f[2 * j + 1]);
               f[2 * j] = gelu_fast_f(f[2 * j]); f[2 * j + 1] = gelu_fast_f(f[2 * j + 1]);
             }
+          } else if (ep.act == 3) {         // the MLP pair of the bf16 training path: the backward's GELU' is computed here, next to
+#pragma unroll                             // the sigmoid it shares, and stored instead of the pre-activation
+            for (int j = 0; j < CH / 2; ++j) {
+              float d0, d1;
+              f[2 * j] = gelu_both_fast_f(f[2 * j], d0); f[2 * j + 1] = gelu_both_fast_f(f[2 * j + 1], d1);
+              pre[j] = pack2_bf16(d0, d1);
+            }
+          } else if (ep.act == 4) {
+#pragma unroll
+            for (int j = 0; j < CH / 2; ++j) {
+              const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xr[j]));
+              f[2 * j] *= h.x; f[2 * j + 1] *= h.y;
+            }
           } else if (ep.act == 2) {
 #pragma unroll
             for (int j = 0; j < CH / 2; ++j) {
@@ -350,7 +363,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t off = (((hf * CPT + c) ^ (row & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sd + off), "r"(pack2_bf16(f[8 * c], f[8 * c + 1])), "r"(pack2_bf16(f[8 * c + 2], f[8 * c + 3])),
                          "r"(pack2_bf16(f[8 * c + 4], f[8 * c + 5])), "r"(pack2_bf16(f[8 * c + 6], f[8 * c + 7])) : "memory");
-            if (ep.act == 1)
+            if (ep.act == 1 || ep.act == 3)
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sx + off), "r"(pre[4 * c]), "r"(pre[4 * c + 1]), "r"(pre[4 * c + 2]), "r"(pre[4 * c + 3]) : "memory");
           }
           if (ep.colsum) {
@@ -398,7 +411,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tma_reduce_add_2d(&tmD, smem_d + b * S::SUB_BYTES, n_sub, m_blk * T2_BM);
           } else {
             tma_store_2d(&tmD, smem_d + b * S::SUB_BYTES, n_sub, m_blk * T2_BM);
-            if (ep.act == 1) tma_store_2d(&tmX, smem_x + b * S::SUB_BYTES, n_sub, m_blk * T2_BM);
+            if (ep.act == 1 || ep.act == 3) tma_store_2d(&tmX, smem_x + b * S::SUB_BYTES, n_sub, m_blk * T2_BM);
           }
           bulk_commit();
         }
@@ -530,8 +543,8 @@ bool mtus_gemm_tc2_supported(const mtus_gemm_desc* d) {
     if (d->ld_out % 8) return false;
     if (d->res && (d->res_mode != 1 || d->ld_res % 8 || !al16(d->res))) return false;
     if (d->act && (!d->aux || d->ld_aux % 8 || !al16(d->aux))) return false;
-    if (d->act == 2 && d->res) return false;        // one epilogue operand tile
-    if (d->act == 1 && d->res) return false;
+    if (d->act && d->res) return false;             // one epilogue operand tile
+    if (d->act < 0 || d->act > 4) return false;
     if (d->a_conv && (d->bias || d->act || d->res || d->rowscale)) return false;
     if (d->a_conv && (d->N % 64 || d->ld_out != d->N)) return false;
     if (wgrad_conv) return false;
@@ -598,7 +611,7 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
   T2Epi ep{};
   ep.bias = d->bias; ep.rowscale = d->rowscale; ep.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1;
   ep.act = d->act;
-  ep.x_mode = d->res ? 1 : (d->act == 2 ? 2 : (d->act == 1 ? 3 : 0));
+  ep.x_mode = d->res ? 1 : ((d->act == 2 || d->act == 4) ? 2 : ((d->act == 1 || d->act == 3) ? 3 : 0));
   ep.reduce = d->atomic ? 1 : 0;
   ep.colsum = d->out_colsum;
   if (d->out_f32) rc = make_map_2d_f32(&td, d->out, N, M, d->ld_out, 32, T2_BM);

@@ -431,8 +431,8 @@ static int swin_forward_impl(const mtus_swin_config* cfg, const void* x, int x_i
                                shift, shift, dt, stream));
       RUN(mtus_linear_fwd_stream(A(ba.attn), W(bp.projw), F(bp.projb), FA(ba.xmid), FA(xin), dp1, rps, M, Cc, Cc, dt, be, stream));
       RUN(mtus_layernorm_fwd_mixed(A(ba.xmid), 1, F(bp.n2w), F(bp.n2b), A(ba.ln2), 0, FA(ba.mean2), FA(ba.rstd2), M, Cc, p.eps, dt, stream));
-      // fc1 + GELU: pre-activation -> h (saved for backward), activation -> a
-      RUN(mtus_linear_fwd(A(ba.ln2), W(bp.fc1w), F(bp.fc1b), A(ba.a), A(ba.h), nullptr, nullptr, 1, M, 4 * Cc, Cc, dt, be, stream));
+      // fc1 + GELU: activation -> a, GELU'(pre-activation) -> h (saved for the backward's mtus_linear_dgrad_dact)
+      RUN(mtus_linear_fwd_gelu_dact(A(ba.ln2), W(bp.fc1w), F(bp.fc1b), A(ba.a), A(ba.h), M, 4 * Cc, Cc, dt, be, stream));
       RUN(mtus_linear_fwd_stream(A(ba.a), W(bp.fc2w), F(bp.fc2b), FA(ba.xout), FA(ba.xmid), dp2, rps, M, Cc, 4 * Cc, dt, be, stream));
     }
     // stage output (fp32 stream) -> in-workspace NHWC copy in the operand dtype for zero-copy consumers; features the
@@ -565,7 +565,7 @@ static int swin_backward_impl(const mtus_swin_config* cfg, const float* params, 
       const int shift = (j % 2) ? p.shift[i] : 0;
       const float* dp1 = droppath ? droppath + (size_t)(2 * gblk) * p.B : nullptr;
       // ---- MLP branch (Gb = dp2 * G; fc2.bias gradient already accumulated by the producer of Gb) ----
-      RUN(mtus_linear_dgrad(Gb, W(bp.fc2w), dH, A(ba.h), nullptr, 1, GR(bp.fc1b), M, Cc, 4 * Cc, dt, be, stream));
+      RUN(mtus_linear_dgrad_dact(Gb, W(bp.fc2w), dH, A(ba.h), GR(bp.fc1b), M, Cc, 4 * Cc, dt, be, stream));
       if (ss) { CU(cudaEventRecord(ss->e1, st)); CU(cudaStreamWaitEvent(ss->s, ss->e1, 0)); }
       RUN_STREAM(mtus_linear_wgrad(Gb, A(ba.a), GR(bp.fc2w), nullptr, M, Cc, 4 * Cc, dt, be, wst), wst);
       RUN_STREAM(mtus_linear_wgrad(dH, A(ba.ln2), GR(bp.fc1w), nullptr, M, 4 * Cc, Cc, dt, be, wst), wst);

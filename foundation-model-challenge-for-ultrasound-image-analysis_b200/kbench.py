@@ -72,9 +72,10 @@ def time_linear(M, N, K, kind, direction, device):
     """Returns (seconds per launch, algorithmic flops, algorithmic bytes).
 
     forward  bias:   y[M,N] bf16 = x w^T + b                      bytes (M K + N K + M N) 2
-             gelu:   a, h[M,N] bf16 = gelu(x w^T + b), pre-act    bytes (M K + N K + 2 M N) 2
+             gelu:   a, h[M,N] bf16 = gelu, gelu'(x w^T + b)      bytes (M K + N K + 2 M N) 2   (the executor's MLP pair: the
+                     derivative is saved instead of the pre-activation, mtus_linear_fwd_gelu_dact / mtus_linear_dgrad_dact)
              stream: y[M,N] fp32 = res fp32 + x w^T + b           bytes (M K + N K) 2 + 2 M N 4
-    dgrad    dx[M,K] bf16 = dy w (x gelu'(h) for fc1's producer)  bytes (M N + N K + M K) 2 (+ M K 2 for h)
+    dgrad    dx[M,K] bf16 = dy w (x h for fc1's producer)         bytes (M N + N K + M K) 2 (+ M K 2 for h)
     wgrad    dw[N,K] fp32 += dy^T x (split-K, TMA reduce-add)     bytes (M N + M K) 2 + N K 4
     """
     L = _lib.lib()
@@ -98,7 +99,7 @@ def time_linear(M, N, K, kind, direction, device):
             if kind == "stream":
                 _lib.check(L.mtus_linear_fwd_stream(ptr(x), ptr(w), ptr(b), ptr(y), ptr(aux), None, 1, M, N, K, BF16, be, _sp()), "fwd_stream")
             elif kind == "gelu":
-                _lib.check(L.mtus_linear_fwd(ptr(x), ptr(w), ptr(b), ptr(y), ptr(aux), None, None, 1, M, N, K, BF16, be, _sp()), "fwd_gelu")
+                _lib.check(L.mtus_linear_fwd_gelu_dact(ptr(x), ptr(w), ptr(b), ptr(y), ptr(aux), M, N, K, BF16, be, _sp()), "fwd_gelu")
             else:
                 _lib.check(L.mtus_linear_fwd(ptr(x), ptr(w), ptr(b), ptr(y), None, None, None, 1, M, N, K, BF16, be, _sp()), "fwd")
     elif direction == "dgrad":
@@ -115,7 +116,10 @@ def time_linear(M, N, K, kind, direction, device):
 
         def run(s):
             dy, w, h, cs, dx = s
-            _lib.check(L.mtus_linear_dgrad(ptr(dy), ptr(w), ptr(dx), ptr(h), None, 1, ptr(cs), M, N, K, BF16, be, _sp()), "dgrad")
+            if with_gelu:
+                _lib.check(L.mtus_linear_dgrad_dact(ptr(dy), ptr(w), ptr(dx), ptr(h), ptr(cs), M, N, K, BF16, be, _sp()), "dgrad_dact")
+            else:
+                _lib.check(L.mtus_linear_dgrad(ptr(dy), ptr(w), ptr(dx), None, None, 1, None, M, N, K, BF16, be, _sp()), "dgrad")
     else:
         def make():
             dy = (torch.randn(M, N, device=device) * 0.5).to(bf)

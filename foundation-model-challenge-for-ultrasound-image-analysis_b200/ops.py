@@ -75,6 +75,26 @@ def linear_dgrad(dy, w, gelu_pre=None, rowscale=None, rows_per_sample=1, backend
     return (dx, colsum) if with_colsum else dx
 
 
+def linear_fwd_gelu_dact(x, w, bias=None, backend=0):
+    """(gelu(x w^T + bias), gelu'(x w^T + bias)): the forward of the MLP pair that saves the derivative for the backward."""
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty(M, N, dtype=x.dtype, device=x.device)
+    dact = torch.empty_like(y)
+    check(lib().mtus_linear_fwd_gelu_dact(ptr(x), ptr(w), ptr(bias), ptr(y), ptr(dact), M, N, K, _dt(x), backend, stream_ptr()), "linear_fwd_gelu_dact")
+    return y, dact
+
+
+def linear_dgrad_dact(dy, w, dact, backend=0, with_colsum=False):
+    """dx = (dy w) * dact (+ column sums of dx)."""
+    M, N = dy.shape
+    K = w.shape[1]
+    dx = torch.empty(M, K, dtype=dy.dtype, device=dy.device)
+    colsum = torch.zeros(K, dtype=torch.float32, device=dy.device) if with_colsum else None
+    check(lib().mtus_linear_dgrad_dact(ptr(dy), ptr(w), ptr(dx), ptr(dact), ptr(colsum), M, N, K, _dt(dy), backend, stream_ptr()), "linear_dgrad_dact")
+    return (dx, colsum) if with_colsum else dx
+
+
 def linear_fwd_stream(x, w, bias=None, res=None, rowscale=None, rows_per_sample=1, backend=0):
     """y (fp32) = res (fp32) + rowscale * (x w^T + bias): the Linear layers that write the fp32 residual stream."""
     M, K = x.shape

@@ -109,6 +109,13 @@ int mtus_linear_fwd_stream(const void* x, const void* w, const float* bias, floa
  * dx_colsum [K] (may be NULL) += column sums of dx = the bias gradient of the Linear that produced gelu_pre */
 int mtus_linear_dgrad(const void* dy, const void* w, void* dx, const void* gelu_pre, const float* rowscale,
                       int rows_per_sample, float* dx_colsum, int64_t M, int N, int K, int dtype, int backend, void* stream);
+/* The MLP pair of the training path (timm Mlp: fc1 -> GELU -> fc2, autograd of the same).  Forward: y = GELU(x w^T + bias) and
+ * dact = GELU'(x w^T + bias), saved INSTEAD of the pre-activation (it shares the forward's sigmoid / erf evaluation).  Backward:
+ * dx = (dy w) * dact, dx_colsum [K] (may be NULL) += column sums of dx = fc1's bias gradient. */
+int mtus_linear_fwd_gelu_dact(const void* x, const void* w, const float* bias, void* y, void* dact, int64_t M, int N, int K,
+                              int dtype, int backend, void* stream);
+int mtus_linear_dgrad_dact(const void* dy, const void* w, void* dx, const void* dact, float* dx_colsum, int64_t M, int N, int K,
+                           int dtype, int backend, void* stream);
 /* dw[N,K] += dy[M,N]^T x[M,K] (fp32, accumulated); db[N] += colsum(dy) when db != NULL */
 int mtus_linear_wgrad(const void* dy, const void* x, float* dw, float* db, int64_t M, int N, int K, int dtype,
                       int backend, void* stream);

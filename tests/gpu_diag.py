@@ -184,6 +184,17 @@ def _gemm_group(backend, dts):
             # (tcgen05 engine: fp32 sums, limited by the bf16 inputs of the reference product; SIMT engine in bf16: a column-sum
             # pass over the STORED values, i.e. sqrt(M) accumulated roundings of 2^-9 against a sum that is itself ~sqrt(M) terms)
             ok &= report(f"linear_dgrad*gelu' + colsum", cs3, hpf.grad.sum(0), 2e-4 if dt == torch.float32 else (2e-3 if backend == 2 else 1e-2))
+            # the MLP pair that stores GELU' instead of the pre-activation (the executor's training path)
+            a2, dact = ops.linear_fwd_gelu_dact(x, w, bias, backend=backend)
+            yrg = yr.clone().requires_grad_(True)
+            F.gelu(yrg).sum().backward()
+            ok &= report(f"linear_fwd_gelu_dact (act)", a2, F.gelu(yr), tol)
+            ok &= report(f"linear_fwd_gelu_dact (gelu')", dact, yrg.grad, tol)
+            dmul = (torch.rand(M, K, device=dev) * 1.2 - 0.1).to(dt)
+            dx4, cs4 = ops.linear_dgrad_dact(dy, w, dmul, backend=backend, with_colsum=True)
+            ref4 = (dy.float() @ w.float()) * dmul.float()
+            ok &= report(f"linear_dgrad_dact", dx4, ref4, tol)
+            ok &= report(f"linear_dgrad_dact + colsum", cs4, ref4.sum(0), 2e-4 if dt == torch.float32 else (2e-3 if backend == 2 else 1e-2))
             dw, db = ops.linear_wgrad(dy, x, backend=backend)
             ok &= report(f"linear_wgrad dw", dw, dy.float().t() @ x.float(), max(tol, 1e-4))
             ok &= report(f"linear_wgrad db", db, dy.float().sum(0), max(tol, 1e-4))
