@@ -11,7 +11,8 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libmtus_b200.so")
+# MTUS_B200_SO: developer knob -- load another build of the SAME library (e.g. the -DMTUS_DIAG_NOATOM diagnostic build)
+_SO = os.environ.get("MTUS_B200_SO") or os.path.join(_HERE, "libmtus_b200.so")
 _lock = threading.Lock()
 _lib = None
 

@@ -48,6 +48,14 @@ static inline cudaError_t mtus_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim
 }
 
 // ---- 8-wide vector load/store, fp32 compute -------------------------------------------------
+// Diagnostic build (-DMTUS_DIAG_NOATOM, never shipped): the hot reduction kernels skip their global atomics (behind a
+// predicate the compiler cannot fold) so the cost of the atomic tail can be read off a timing difference.
+#ifdef MTUS_DIAG_NOATOM
+#define MTUS_ATOMIC_ADD(p_, v_) do { const float mtus_v_ = (v_); if (mtus_v_ == 1.2345e-30f) atomicAdd((p_), mtus_v_); } while (0)
+#else
+#define MTUS_ATOMIC_ADD(p_, v_) atomicAdd((p_), (v_))
+#endif
+
 template <typename T> struct IO;
 
 template <> struct IO<float> {

@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(128) lnv2_bwd_kernel(LnxBwdArgs a, MergeGeom g
     float* out = qn == 0 ? a.dgamma : (qn == 1 ? a.dbeta : a.lp_colsum);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       const float v = acc_smem[c] + acc_smem[C + c] + acc_smem[2 * C + c] + acc_smem[3 * C + c];
-      atomicAdd(out + (qn == 2 ? (c % Cc) : c), v);
+      MTUS_ATOMIC_ADD(out + (qn == 2 ? (c % Cc) : c), v);
     }
   }
 }
@@ -764,7 +764,14 @@ static int lnv2_bwd_launch(const LnxBwdArgs& a, MergeGeom g, cudaStream_t st) {
   else if (nvec <= 8) V2B(8, 1, 2, 6)
   else if (nvec <= 16) V2B(16, 1, 2, 6)
   else if (nvec <= 32) V2B(32, 1, 2, 6)
-  else if (nvec <= 64) V2B(32, 2, 2, 2)      // 2 CTAs per SM fit (registers): one resident wave
+  else if (nvec <= 64) {
+    // one row per warp iteration, 162 registers, 3 CTAs per SM: 13.1 us at [6272, 512] against 15.5 us for the two-row form
+    // (214 registers, 2 CTAs per SM), which stays selectable with MTUS_LN_BWD_U=2
+    static int u2 = -1;
+    if (u2 < 0) { const char* e = getenv("MTUS_LN_BWD_U"); u2 = (e && atoi(e) == 2) ? 1 : 0; }
+    if (u2) V2B(32, 2, 2, 2)
+    else V2B(32, 2, 1, 3)
+  }
   else if (nvec <= 96) V2B(32, 3, 1, 3)
   else V2B(32, 4, 1, 3)
 #undef V2B

@@ -320,3 +320,39 @@ def time_bilinear(B, H, Cc, device):
         _lib.check(L.mtus_bilinear2x_fwd(ptr(x), ptr(y), B, H, H, Cc, BF16, _sp()), "bilinear")
     by = 1.25 * B * 4 * H * H * Cc * 2
     return graph_time(_ring(make, by), run), by
+
+
+def time_colsum(rows, Cc, device):
+    """out[c] += sum_r x[r, c] (bias gradient of the FPN lateral convolutions): bytes rows C s."""
+    L = _lib.lib()
+
+    def make():
+        return torch.randn(rows, Cc, device=device).to(torch.bfloat16), torch.zeros(Cc, device=device)
+
+    def run(s):
+        x, out = s
+        _lib.check(L.mtus_colsum(ptr(x), ptr(out), rows, Cc, BF16, _sp()), "colsum")
+    by = rows * Cc * 2.0
+    return graph_time(_ring(make, by), run), by
+
+
+def time_groupnorm_bwd(B, H, Cc, device, act=0):
+    """GroupNorm(32) + activation backward (gate recomputed from x): reads dy and x, writes dx: bytes 3 B H^2 C s."""
+    L = _lib.lib()
+    bf = torch.bfloat16
+    g, b = torch.ones(Cc, device=device), torch.zeros(Cc, device=device)
+
+    def make():
+        x = torch.randn(B, H, H, Cc, device=device)
+        xg = x.reshape(B, H * H, 32, Cc // 32)
+        mean = xg.mean((1, 3)).contiguous()
+        rstd = (xg.var((1, 3), unbiased=False) + 1e-5).rsqrt().contiguous()
+        return (torch.randn(B, H, H, Cc, device=device).to(bf), x.to(bf), mean, rstd, torch.empty(B, H, H, Cc, device=device, dtype=bf),
+                torch.zeros(Cc, device=device), torch.zeros(Cc, device=device), torch.zeros(2 * B * 32, device=device))
+
+    def run(s):
+        dy, x, mean, rstd, dx, dg, db, ws = s
+        _lib.check(L.mtus_groupnorm_act_bwd(ptr(dy), ptr(x), None, ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(dx), ptr(dg), ptr(db), ptr(ws),
+                                            B, H * H, Cc, 32, act, BF16, _sp()), "gn_bwd")
+    by = 3.0 * B * H * H * Cc * 2
+    return graph_time(_ring(make, by), run), by

@@ -165,6 +165,15 @@ def scale_cast_colsum(g, out_dtype, rowscale=None, rows_per_sample=1):
     return y, cs
 
 
+def colsum(x, out=None):
+    """out[c] += sum_r x[r, c] for x [rows, C] (fp32 or bf16); out fp32 [C] (zeros when not given)."""
+    rows, Cc = x.shape
+    if out is None:
+        out = torch.zeros(Cc, dtype=torch.float32, device=x.device)
+    check(lib().mtus_colsum(ptr(x), ptr(out), rows, Cc, _dt(x), stream_ptr()), "colsum")
+    return out
+
+
 def convert(x, out_dtype, transpose=False):
     """[B,R,C] -> [B,R,C] or [B,C,R] with a dtype change (fp32 <-> bf16)."""
     B, R, Cc = x.shape

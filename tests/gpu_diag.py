@@ -128,6 +128,13 @@ def g_elementwise():
         yq, cs = ops.scale_cast_colsum(gs, dt, rs, 111)
         ok &= report(f"scale_cast_colsum {dt}", yq, gs * rs[torch.arange(777, device=dev) // 111][:, None], tol)
         ok &= report(f"scale_cast_colsum sums", cs, yq.float().sum(0), 2e-4)
+        for (rows, Cc) in ((777, 256), (5000, 128), (33, 8), (100352 // 4, 264), (130, 520)):
+            xs_ = torch.randn(rows, Cc, device=dev).to(dt)
+            ok &= report(f"colsum {dt} {rows, Cc}", ops.colsum(xs_), xs_.double().sum(0).float(), 2e-4 if dt == torch.float32 else 1e-3)
+        acc_ = torch.ones(136, device=dev)[4:]                  # 16-byte aligned but not 32: vector reductions; then a misaligned view
+        ok &= report(f"colsum accumulates (offset view)", ops.colsum(torch.ones(300, 128, device=dev).to(dt), acc_[:128]), torch.full((128,), 301.0, device=dev), 1e-6)
+        acc2_ = torch.zeros(137, device=dev)[1:]
+        ok &= report(f"colsum scalar-atomic path (4-byte aligned out)", ops.colsum(torch.ones(300, 136, device=dev).to(dt), acc2_), torch.full((136,), 300.0, device=dev), 1e-6)
         xc = torch.randn(3, 50, 40, device=dev)
         ok &= report(f"convert f32->{dt} transpose", ops.convert(xc, dt, True), xc.transpose(1, 2), tol)
         ok &= report(f"convert {dt}->f32", ops.convert(xc.to(dt), torch.float32), xc.to(dt).float(), 0)
