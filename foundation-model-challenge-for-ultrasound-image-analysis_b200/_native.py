@@ -106,6 +106,13 @@ class FlatParamModule(nn.Module):
             self._split_sizes, self._split_pick = sizes, pick
         return e
 
+    def params_version_key(self):
+        """Changes whenever torch writes the parameters in place: the flat block's own version counter (writes through the
+        block, e.g. a broadcast) plus the counters of the parameter views (``set_data`` gave each its own; ``load_state_dict``,
+        ``param.mul_`` and torch optimizers bump those).  Writes through ``param.data`` or raw pointers are invisible to it."""
+        flat = self.flat_params()
+        return (flat.data_ptr(), flat._version, sum(p._version for p in self.ordered_params()))
+
     def ordered_params(self):
         self._entries()
         return self._ordered_cache

@@ -11,6 +11,8 @@
 // Algorithmic bytes: fwd 2*rows*C*s (+8 B/row stats), bwd 3*rows*C*s (+ dres: 4*rows*C*s).
 #include "common.cuh"
 #include <stdlib.h>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 struct MergeGeom { int B, H, W, C, Ho, Wo; };  // input [B,H,W,C] -> rows (b,i,j) of 4C columns
 
@@ -472,22 +474,58 @@ __global__ void __launch_bounds__(128) lnx_bwd_kernel(LnxBwdArgs a, MergeGeom g)
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      atomicAdd(a.dgamma + c, sg[c] + sg[C + c] + sg[2 * C + c] + sg[3 * C + c]);
-      atomicAdd(a.dbeta + c, sb[c] + sb[C + c] + sb[2 * C + c] + sb[3 * C + c]);
-      if (want_cs) atomicAdd(a.lp_colsum + (c % Cc), sc[c] + sc[C + c] + sc[2 * C + c] + sc[3 * C + c]);
+      MTUS_ATOMIC_ADD(a.dgamma + c, sg[c] + sg[C + c] + sg[2 * C + c] + sg[3 * C + c]);
+      MTUS_ATOMIC_ADD(a.dbeta + c, sb[c] + sb[C + c] + sb[2 * C + c] + sb[3 * C + c]);
+      if (want_cs) MTUS_ATOMIC_ADD(a.lp_colsum + (c % Cc), sc[c] + sc[C + c] + sc[2 * C + c] + sc[3 * C + c]);
     }
   } else {
+    // Wide rows (C > 1024, four warps per row): every thread owns its columns, so the CTA's partials go to shared memory
+    // as they are ([3][C]); the CTAs of a CLUSTER then add their partials through distributed shared memory -- rank r
+    // takes the column slice r -- and issue one coalesced vector reduction per four columns.  The first version issued
+    // 48 scalar atomics per thread with a 32-byte lane stride (one L2 sector per lane): 60 us of a 114 us launch at
+    // [1568, 2048] with 148 CTAs, and worse with more CTAs (MTUS_DIAG_NOATOM build: 51.7 us -> 19.6 us from 1 to 4 CTAs per SM).
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    float* sg = acc_smem; float* sb = acc_smem + C; float* sc = acc_smem + 2 * C;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int col = ((sub * NV + i) * 32 + lane) * 8;
       if (col < C) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          atomicAdd(a.dgamma + col + k, adg[i][k]); atomicAdd(a.dbeta + col + k, adb[i][k]);
-          if (want_cs) atomicAdd(a.lp_colsum + ((col + k) % Cc), acs[i][k]);
+        *reinterpret_cast<float4*>(sg + col) = make_float4(adg[i][0], adg[i][1], adg[i][2], adg[i][3]);
+        *reinterpret_cast<float4*>(sg + col + 4) = make_float4(adg[i][4], adg[i][5], adg[i][6], adg[i][7]);
+        *reinterpret_cast<float4*>(sb + col) = make_float4(adb[i][0], adb[i][1], adb[i][2], adb[i][3]);
+        *reinterpret_cast<float4*>(sb + col + 4) = make_float4(adb[i][4], adb[i][5], adb[i][6], adb[i][7]);
+        *reinterpret_cast<float4*>(sc + col) = make_float4(acs[i][0], acs[i][1], acs[i][2], acs[i][3]);
+        *reinterpret_cast<float4*>(sc + col + 4) = make_float4(acs[i][4], acs[i][5], acs[i][6], acs[i][7]);
+      }
+    }
+    cluster.sync();
+    const int nq = want_cs ? 3 : 2, C4 = C / 4;
+    const int per = (C4 + CL - 1) / CL, v0 = rank * per, v1 = min(C4, v0 + per);
+    const bool vec_ok = ((((uintptr_t)a.dgamma | (uintptr_t)a.dbeta | (uintptr_t)a.lp_colsum) & 15) == 0) && (Cc % 4 == 0);
+    for (int q = 0; q < nq; ++q) {
+      float* out = q == 0 ? a.dgamma : (q == 1 ? a.dbeta : a.lp_colsum);
+      for (int v = v0 + (int)threadIdx.x; v < v1; v += blockDim.x) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < CL; ++r) {
+          const float4 p = *reinterpret_cast<const float4*>(cluster.map_shared_rank(acc_smem, r) + q * C + v * 4);
+          t.x += p.x; t.y += p.y; t.z += p.z; t.w += p.w;
+        }
+        const int c = q == 2 ? (v * 4) % Cc : v * 4;
+        if (vec_ok) {
+#ifdef MTUS_DIAG_NOATOM
+          if (t.x == 1.2345e-30f)
+#endif
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+        } else {
+          MTUS_ATOMIC_ADD(out + (q == 2 ? (v * 4) % Cc : v * 4), t.x);
+          MTUS_ATOMIC_ADD(out + (q == 2 ? (v * 4 + 1) % Cc : v * 4 + 1), t.y);
+          MTUS_ATOMIC_ADD(out + (q == 2 ? (v * 4 + 2) % Cc : v * 4 + 2), t.z);
+          MTUS_ATOMIC_ADD(out + (q == 2 ? (v * 4 + 3) % Cc : v * 4 + 3), t.w);
         }
       }
     }
+    cluster.sync();                                       // no CTA leaves while a peer still reads its partials
   }
 }
 
@@ -772,8 +810,8 @@ static int lnv2_bwd_launch(const LnxBwdArgs& a, MergeGeom g, cudaStream_t st) {
     if (u2) V2B(32, 2, 2, 2)
     else V2B(32, 2, 1, 3)
   }
-  else if (nvec <= 96) V2B(32, 3, 1, 3)
-  else V2B(32, 4, 1, 3)
+  else if (nvec <= 96) V2B(32, 3, 1, 2)      // 206-255 registers: two CTAs per SM are resident, a third would wait for a second wave
+  else V2B(32, 4, 1, 2)
 #undef V2B
   MTUS_LAUNCH_STATUS();
   return MTUS_OK;
@@ -805,6 +843,12 @@ static int lnx_fwd_launch(const void* x, const float* gamma, const float* beta, 
   return MTUS_OK;
 }
 
+static int lnx_bwd_wide_bps() {        // MTUS_LNX_BWD_BPS: CTAs per SM of the wide-row (C > 1024) LayerNorm backward
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTUS_LNX_BWD_BPS"); v = e ? atoi(e) : 4; if (v < 1) v = 1; }
+  return v;
+}
+
 template <typename T, typename TDY, typename TX, int MODE>
 static int lnx_bwd_launch(const LnxBwdArgs& a, MergeGeom g, cudaStream_t st) {
   if (a.rows == 0) return MTUS_OK;
@@ -816,14 +860,23 @@ static int lnx_bwd_launch(const LnxBwdArgs& a, MergeGeom g, cudaStream_t st) {
   {                                                                                                          \
     const int rpb = 4 / WPR_;                                                                                \
     int64_t blocks = (a.rows + rpb - 1) / rpb;                                                               \
-    if (blocks > (WPR_ == 1 ? 148 * 4 : 148)) blocks = (WPR_ == 1 ? 148 * 4 : 148);                          \
-    const size_t sm = (WPR_ == 1) ? (size_t)12 * C * sizeof(float) : 0;                                      \
+    if (blocks > (WPR_ == 1 ? 148 * 4 : 148 * lnx_bwd_wide_bps())) blocks = (WPR_ == 1 ? 148 * 4 : 148 * lnx_bwd_wide_bps()); \
+    const int cl = (WPR_ == 1) ? 1 : (blocks >= 8 ? 8 : 1);        /* wide rows: clusters of 8 CTAs add their partials */ \
+    blocks = (blocks + cl - 1) / cl * cl;                                                                    \
+    const size_t sm = (WPR_ == 1) ? (size_t)12 * C * sizeof(float) : (size_t)3 * C * sizeof(float);          \
     auto kern = lnx_bwd_kernel<T, TDY, TX, NV_, WPR_, MODE>;                                                 \
     if (sm > 48 * 1024) {                                                                                    \
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);      \
       if (e != cudaSuccess) return (int)e;                                                                   \
     }                                                                                                        \
-    kern<<<(int)blocks, 128, sm, st>>>(a, g);                                                                \
+    cudaLaunchConfig_t cfg = {};                                                                             \
+    cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = sm; cfg.stream = st; \
+    cudaLaunchAttribute attr[1];                                                                             \
+    attr[0].id = cudaLaunchAttributeClusterDimension;                                                        \
+    attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;               \
+    cfg.attrs = attr; cfg.numAttrs = 1;                                                                      \
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, a, g);                                                   \
+    if (le != cudaSuccess) return (int)le;                                                                   \
   }
   if (nvec <= 32) LNX_CASE(1, 1)
   else if (nvec <= 64) LNX_CASE(2, 1)

@@ -471,9 +471,11 @@ extern "C" int mtus_sumsq(const float* g, int64_t n, float* out, void* stream) {
   return MTUS_OK;
 }
 
+template <bool SHADOW>
 __global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                          float* __restrict__ v, int64_t n4, float lr, float beta1, float beta2, float eps,
-                                                         float wd, float bc1, float bc2_sqrt, const float* __restrict__ grad_scale) {
+                                                         float wd, float bc1, float bc2_sqrt, const float* __restrict__ grad_scale,
+                                                         bf16* __restrict__ shadow) {
   const float gs = grad_scale ? __ldg(grad_scale) : 1.0f;
   const float decay = 1.0f - lr * wd, step = lr / bc1, inv_bc2 = 1.0f / bc2_sqrt;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -494,6 +496,12 @@ __global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, 
     reinterpret_cast<float4*>(p)[i] = pp;
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
+    if (SHADOW) {                         // the bf16 operand copy the next forward reads (same rounding as cast_kernel)
+      uint2 r;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+      h[0] = __floats2bfloat162_rn(pp.x, pp.y); h[1] = __floats2bfloat162_rn(pp.z, pp.w);
+      reinterpret_cast<uint2*>(shadow)[i] = r;
+    }
   }
 }
 
@@ -503,8 +511,22 @@ extern "C" int mtus_adamw_flat(float* p, const float* g, float* m, float* v, int
   MTUS_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
   if (n == 0) return MTUS_OK;
   const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
-  adamw_flat_kernel<<<grid_for(n / 4, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n / 4, lr, beta1, beta2, eps, weight_decay,
-                                                                                   bc1, sqrtf(bc2), grad_scale);
+  adamw_flat_kernel<false><<<grid_for(n / 4, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n / 4, lr, beta1, beta2, eps, weight_decay,
+                                                                                          bc1, sqrtf(bc2), grad_scale, nullptr);
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}
+
+// Same update; additionally writes the bf16 copy of the updated parameters (the encoder's operand shadow), so the next forward
+// does not have to re-read the fp32 block to refresh it (0.35 GB per step for Swin-B).
+extern "C" int mtus_adamw_flat_shadow(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1,
+                                      float beta2, float eps, float weight_decay, int step, const float* grad_scale, void* stream) {
+  MTUS_CHECK_ARG(p && g && m && v && shadow_bf16 && n >= 0 && n % 4 == 0 && step >= 1);
+  MTUS_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0 && ((uintptr_t)shadow_bf16 & 7) == 0);
+  if (n == 0) return MTUS_OK;
+  const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+  adamw_flat_kernel<true><<<grid_for(n / 4, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n / 4, lr, beta1, beta2, eps, weight_decay,
+                                                                                         bc1, sqrtf(bc2), grad_scale, (bf16*)shadow_bf16);
   MTUS_LAUNCH_STATUS();
   return MTUS_OK;
 }

@@ -199,7 +199,13 @@ class SwinCore(FlatParamModule):
             lp = getattr(self, "_lp_buf", None)
             if lp is None or lp.device != x.device or lp.numel() != self._n_flat:
                 lp = self._lp_buf = torch.empty(self._n_flat, dtype=torch.bfloat16, device=x.device)
-            _lib.check(L.mtus_cast_f32_to_bf16(_lib.ptr(flat), _lib.ptr(lp), self._n_flat, _lib.stream_ptr()), "cast")
+            # FlatAdamW.step writes the shadow together with the update (mtus_adamw_flat_shadow) and records the parameter
+            # block it is valid for; any later in-place change of the parameters through torch (load_state_dict, broadcast,
+            # another optimizer) bumps the block's version counter and the cast below runs again.  Only trusted in training
+            # mode: writes through ``param.data`` bypass the counter, and those belong to evaluation-time weight swaps.
+            if not (self.training and getattr(self, "_lp_fresh_key", None) == self.params_version_key() + (lp.data_ptr(),)):
+                _lib.check(L.mtus_cast_f32_to_bf16(_lib.ptr(flat), _lib.ptr(lp), self._n_flat, _lib.stream_ptr()), "cast")
+                self._lp_fresh_key = None
         dp = self._droppath_scales(B, x.device)
         out_f32 = self.output_dtype in ("fp32", "float32") and dt != _lib.F32
         feats, feat_ptrs = [], [None] * 4

@@ -14,12 +14,17 @@ the group -- so the reference's schedulers (``CosineAnnealingLR`` / ``StepLR`` /
 """
 
 import contextlib
+import os
 from typing import Dict, List
 
 import torch
 
 from . import _lib
 from ._native import FlatParamModule
+
+
+# MTUS_OPT_SHADOW=0: the optimizer leaves the encoder's bf16 parameter shadow alone and every forward re-casts it
+_OPT_WRITES_SHADOW = os.environ.get("MTUS_OPT_SHADOW", "1") != "0"
 
 
 class FlatAdamW(torch.optim.Optimizer):
@@ -119,9 +124,18 @@ class FlatAdamW(torch.optim.Optimizer):
                                        "(load_state_dict moves the moments to the parameters' device; did the model move afterwards?)")
                 f["step"] += 1
                 b1, b2 = grp["betas"]
-                _lib.check(L.mtus_adamw_flat(_lib.ptr(p), _lib.ptr(g), _lib.ptr(f["m"]), _lib.ptr(f["v"]), p.numel(), float(grp["lr"]),
-                                             float(b1), float(b2), float(grp["eps"]), float(grp["weight_decay"]), f["step"],
-                                             _lib.ptr(scale), st), "adamw_flat")
+                lp = getattr(mod, "_lp_buf", None) if _OPT_WRITES_SHADOW else None
+                if lp is not None and lp.device == p.device and lp.numel() == p.numel() and lp.dtype == torch.bfloat16:
+                    # the encoder's bf16 operand shadow is refreshed by the update itself; the module skips its own cast
+                    # pass while the parameter block stays untouched (same tensor, same version counter)
+                    _lib.check(L.mtus_adamw_flat_shadow(_lib.ptr(p), _lib.ptr(g), _lib.ptr(f["m"]), _lib.ptr(f["v"]), _lib.ptr(lp), p.numel(),
+                                                        float(grp["lr"]), float(b1), float(b2), float(grp["eps"]), float(grp["weight_decay"]),
+                                                        f["step"], _lib.ptr(scale), st), "adamw_flat_shadow")
+                    mod._lp_fresh_key = mod.params_version_key() + (lp.data_ptr(),)
+                else:
+                    _lib.check(L.mtus_adamw_flat(_lib.ptr(p), _lib.ptr(g), _lib.ptr(f["m"]), _lib.ptr(f["v"]), p.numel(), float(grp["lr"]),
+                                                 float(b1), float(b2), float(grp["eps"]), float(grp["weight_decay"]), f["step"],
+                                                 _lib.ptr(scale), st), "adamw_flat")
             if self.torch_opt is not None:
                 for mine, theirs in zip(self.param_groups[self._n_flat_groups:], self.torch_opt.param_groups):
                     for k in ("lr", "betas", "eps", "weight_decay"):

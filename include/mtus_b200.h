@@ -141,6 +141,10 @@ int mtus_sumsq(const float* g, int64_t n, float* out, void* stream);
 /* p, m, v updated in place from g * (*grad_scale) (grad_scale: device scalar = clip coefficient, or NULL) */
 int mtus_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int step, const float* grad_scale, void* stream);
+/* same update, and shadow_bf16[i] = bf16(p[i]) of the UPDATED parameters (the operand copy the bf16 forward reads; saves
+ * the separate mtus_cast_f32_to_bf16 pass over the block before the next forward) */
+int mtus_adamw_flat_shadow(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1,
+                           float beta2, float eps, float weight_decay, int step, const float* grad_scale, void* stream);
 
 /* ---- PatchEmbed (timm PatchEmbed; 8a a3): 4x4/4 conv as im2col (K padded 48->64) + GEMM + LN -- */
 int mtus_patch_embed_im2col(const void* x_nchw, void* cols, int B, int H, int W, int x_is_f32, int dtype,

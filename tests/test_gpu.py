@@ -189,6 +189,42 @@ def test_flat_adamw_matches_torch_adamw_with_clipping():
         assert torch.allclose(pa[k], pb[k], rtol=2e-4, atol=2e-6), k
 
 
+def test_optimizer_written_bf16_shadow_is_the_cast_of_the_parameters_and_is_dropped_on_foreign_writes():
+    """FlatAdamW.step refreshes the encoder's bf16 operand shadow inside the update kernel (mtus_adamw_flat_shadow); the next
+    training forward skips its cast pass only while the parameter block is untouched, and the shadow is bit-identical to the
+    cast it replaces."""
+    import mtus_b200 as m
+    tasks = [t for t in m.tasks_27() if t["task_id"] in ("T1_fetal_planes",)]
+    cfg = m.make_config("swin_micro_patch4_window7_test", 64, 4, tasks=tasks, dropout=0.0, mixed_precision=True)
+    torch.manual_seed(0)
+    model = m.build_model(cfg, precision="bf16").cuda().train()
+    opt = m.build_flat_optimizer(model, cfg)
+    fns, w = m.build_all_losses(cfg)
+    tr = m.DataParallelTrainer(model, opt, fns, w, gradient_clip=1.0)
+    x, y = m.synthetic_batch(tasks[0], 4, 64, generator=torch.Generator().manual_seed(3), device="cuda")
+    core = model.encoder.model
+    tr.step(x, y, "T1_fetal_planes")
+    flat = core.flat_params()
+    assert core._lp_fresh_key == core.params_version_key() + (core._lp_buf.data_ptr(),)
+    assert torch.equal(core._lp_buf, flat.to(torch.bfloat16))                 # written by the optimizer kernel
+    tr.step(x, y, "T1_fetal_planes")                                          # forward trusted the shadow (no cast in between)
+    assert core._lp_fresh_key is not None and torch.equal(core._lp_buf, core.flat_params().to(torch.bfloat16))
+    with torch.no_grad():                                                     # a foreign in-place write: the shadow is stale now
+        next(iter(core.parameters())).mul_(0.5)
+    model(x, "T1_fetal_planes")
+    assert core._lp_fresh_key is None and torch.equal(core._lp_buf, core.flat_params().to(torch.bfloat16))
+    tr.step(x, y, "T1_fetal_planes")
+    assert core._lp_fresh_key is not None
+    with torch.no_grad():                                                     # ... also when it goes through the flat block itself
+        core.flat_params().mul_(1.0)
+    model(x, "T1_fetal_planes")
+    assert core._lp_fresh_key is None
+    model.eval()
+    tr2 = core._lp_buf.clone()
+    model(x, "T1_fetal_planes")                                               # evaluation always re-casts
+    assert torch.equal(core._lp_buf, tr2)
+
+
 def test_chunked_backward_equals_one_shot_backward(monkeypatch):
     """mtus_swin_backward_blocks over the data-parallel chunk plan produces the same flat gradient as one call over all
     blocks (fp32 accumulation order differs only through atomics: compared at 1e-5 of the tensor scale)."""

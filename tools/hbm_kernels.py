@@ -34,6 +34,8 @@ def main():
         ("merge_ln_fwd [32,56,56,128]", lambda: K.time_patch_merge_ln(32, 56, 128, dev)),
         ("merge_ln_bwd [32,56,56,128]", lambda: K.time_patch_merge_ln(32, 56, 128, dev, backward=True)),
         ("merge_ln_bwd [32,28,28,256]", lambda: K.time_patch_merge_ln(32, 28, 256, dev, backward=True)),
+        ("merge_ln_bwd [32,14,14,512]", lambda: K.time_patch_merge_ln(32, 14, 512, dev, backward=True)),
+        ("merge_ln_fwd [32,14,14,512]", lambda: K.time_patch_merge_ln(32, 14, 512, dev)),
         ("colsum [100352,256]", lambda: K.time_colsum(100352, 256, dev)),
         ("colsum [25088,256]", lambda: K.time_colsum(25088, 256, dev)),
         ("gn_fwd fused [32,56,56,128]", lambda: K.time_groupnorm_relu(32, 56, 128, dev, fused=True)),
