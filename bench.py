@@ -286,6 +286,15 @@ def _kernel_rooflines(peaks, device):
     t, by = kbench.time_groupnorm_relu(32, 56, 128, device, fused=False)
     hbm_entry("gn_stats x2 + gn_relu_fwd, the two-pass fallback of the same op (3 reads + 1 write)", t, by,
               pair_moves_bytes=2.0 * by, frac_of_bytes_moved=round(2.0 * by / t / 1e9 / hbm, 4))
+    t, by = kbench.time_groupnorm_bwd(32, 56, 128, device, act=0)
+    hbm_entry("gn_fused_bwd_kernel GroupNorm(32)+ReLU backward [32,56,56,128] bf16 (one cluster kernel: x and dy staged once in shared "
+              "memory, two reads + one write)", t, by)
+    t, by = kbench.time_groupnorm_bwd(32, 56, 128, device, act=1)
+    hbm_entry("gn_fused_bwd_kernel GroupNorm(32)+SiLU backward [32,56,56,128] bf16 (segmentation head)", t, by)
+    t, by = kbench.time_colsum(32 * 3136, 256, device)
+    hbm_entry("colsum_kernel [100352,256] bf16 (FPN lateral bias gradient; one wave, vector reductions)", t, by)
+    t, by = kbench.time_patch_merge_ln(32, 14, 512, device, backward=True)
+    hbm_entry("patch_merge_ln_bwd [32,14,14,512] (4C = 2048: wide-row kernel, partials reduced across a cluster)", t, by)
     t, by = kbench.time_bilinear(32, 28, 128, device)
     hbm_entry("bilinear2x_fwd [32,28,28,128] -> [32,56,56,128] bf16 (align_corners)", t, by)
     for (H, Cc_, heads, tag) in ((56, 128, 4, "stage 1"), (14, 512, 16, "stage 3")):

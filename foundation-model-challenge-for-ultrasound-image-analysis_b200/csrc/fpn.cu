@@ -510,7 +510,7 @@ __global__ void gn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
 // through distributed shared memory.  Pass 2 writes dx = rstd (dr gamma - s1/n - xhat s2/n) out of shared memory.  Replaces
 // memset + gn_bwd_reduce + gn_bwd_apply (2 x 2 reads + 1 write, and a reduce kernel that kept only 16 KB per SM in flight:
 // 80 us at bf16 [32,56,56,128] against 23 us of traffic).
-template <typename T, int ACT>
+template <typename T, int ACT, bool DY_SMEM>
 __global__ void __launch_bounds__(256) gn_fused_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, T* __restrict__ dx, float* __restrict__ dgamma,
@@ -522,8 +522,8 @@ __global__ void __launch_bounds__(256) gn_fused_bwd_kernel(const T* __restrict__
   const int p0 = min(HW, rank * ppc), p1 = min(HW, p0 + ppc), npix = p1 - p0, nvec = npix * C8;
   const size_t slice = (size_t)ppc * C * sizeof(T);
   uint8_t* sx = gf_smem;                                                      // [ppc][C] x
-  uint8_t* sdy = gf_smem + slice;                                             // [ppc][C] dy
-  float* sred = reinterpret_cast<float*>(gf_smem + 2 * slice);                // [2][C]: ag, ab per channel (this CTA)
+  uint8_t* sdy = gf_smem + slice;                                             // [ppc][C] dy (DY_SMEM only)
+  float* sred = reinterpret_cast<float*>(gf_smem + (DY_SMEM ? 2 : 1) * slice);   // [2][C]: ag, ab per channel (this CTA)
   float* sg1 = sred + 2 * C;    // [G] this CTA's partial of s1 (read by the peers)
   float* sg2 = sg1 + G;         // [G] this CTA's partial of s2
   float* st1 = sg2 + G;         // [G] s1 / n of the sample
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(256) gn_fused_bwd_kernel(const T* __restrict__
   for (int i = tid; i < nvec * PIECES; i += 256) {
     const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(sx + (size_t)i * 16), d1 = (uint32_t)__cvta_generic_to_shared(sdy + (size_t)i * 16);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(reinterpret_cast<const uint8_t*>(x) + goff + (size_t)i * 16) : "memory");
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d1), "l"(reinterpret_cast<const uint8_t*>(dy) + goff + (size_t)i * 16) : "memory");
+    if (DY_SMEM) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d1), "l"(reinterpret_cast<const uint8_t*>(dy) + goff + (size_t)i * 16) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   for (int c = tid; c < 2 * C; c += 256) sred[c] = 0.f;
@@ -574,16 +574,42 @@ __global__ void __launch_bounds__(256) gn_fused_bwd_kernel(const T* __restrict__
   float ag[8], ab[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) ag[k] = ab[k] = 0.f;
-  for (int i = tid; i < nvec; i += 256) {
-    float xv[8], d[8];
-    ld8(sx, i, xv); ld8(sdy, i, d);
+  const T* dyg = dy + ((int64_t)b * HW + p0) * C;      // this CTA's slice of dy in global memory (!DY_SMEM: read twice, 2nd time from L2)
+  if (DY_SMEM) {
+    for (int i = tid; i < nvec; i += 256) {
+      float xv[8], d[8];
+      ld8(sx, i, xv); ld8(sdy, i, d);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      d[k] = gn_act_grad<ACT, false>(d[k], 0.f, xv[k], ga[k], gs[k]);          // dr = dy act'(z)
-      ag[k] = fmaf(d[k], (xv[k] - mu[k]) * rs[k], ag[k]);
-      ab[k] += d[k];
+      for (int k = 0; k < 8; ++k) {
+        d[k] = gn_act_grad<ACT, false>(d[k], 0.f, xv[k], ga[k], gs[k]);          // dr = dy act'(z)
+        ag[k] = fmaf(d[k], (xv[k] - mu[k]) * rs[k], ag[k]);
+        ab[k] += d[k];
+      }
+      if (ACT != 0) st8(sdy, i, d);     // SiLU: park dr over dy (own vector only) so pass 2 does not evaluate the sigmoid again
     }
-    if (ACT != 0) st8(sdy, i, d);       // SiLU: park dr over dy (own vector only) so pass 2 does not evaluate the sigmoid again
+  } else {
+    for (int i0 = tid; i0 < nvec; i0 += 4 * 256) {      // four independent 16/32-byte global loads of dy in flight per thread
+      float d[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 256;
+        if (i < nvec) IO<T>::load8(dyg + (size_t)i * 8, d[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 256;
+        if (i < nvec) {
+          float xv[8];
+          ld8(sx, i, xv);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float dr = gn_act_grad<ACT, false>(d[u][k], 0.f, xv[k], ga[k], gs[k]);
+            ag[k] = fmaf(dr, (xv[k] - mu[k]) * rs[k], ag[k]);
+            ab[k] += dr;
+          }
+        }
+      }
+    }
   }
   for (int off = C8; off < 32; off <<= 1) {
 #pragma unroll
@@ -627,37 +653,70 @@ __global__ void __launch_bounds__(256) gn_fused_bwd_kernel(const T* __restrict__
 #pragma unroll
   for (int k = 0; k < 8; ++k) { const int g = (v * 8 + k) / cpg; s1[k] = st1[g]; s2[k] = st2[g]; }
   T* dstp = dx + ((int64_t)b * HW + p0) * C;
-  for (int i = tid; i < nvec; i += 256) {
-    float xv[8], d[8], o[8];
-    ld8(sx, i, xv); ld8(sdy, i, d);
+  if (DY_SMEM) {
+    for (int i = tid; i < nvec; i += 256) {
+      float xv[8], d[8], o[8];
+      ld8(sx, i, xv); ld8(sdy, i, d);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float dr = ACT != 0 ? d[k] : gn_act_grad<ACT, false>(d[k], 0.f, xv[k], ga[k], gs[k]);
-      const float xh = (xv[k] - mu[k]) * rs[k];
-      o[k] = rs[k] * (dr * gm[k] - s1[k] - xh * s2[k]);
+      for (int k = 0; k < 8; ++k) {
+        const float dr = ACT != 0 ? d[k] : gn_act_grad<ACT, false>(d[k], 0.f, xv[k], ga[k], gs[k]);
+        const float xh = (xv[k] - mu[k]) * rs[k];
+        o[k] = rs[k] * (dr * gm[k] - s1[k] - xh * s2[k]);
+      }
+      IO<T>::store8(dstp + (size_t)i * 8, o);
     }
-    IO<T>::store8(dstp + (size_t)i * 8, o);
+  } else {
+    for (int i0 = tid; i0 < nvec; i0 += 4 * 256) {
+      float d[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 256;
+        if (i < nvec) IO<T>::load8(dyg + (size_t)i * 8, d[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 256;
+        if (i < nvec) {
+          float xv[8], o[8];
+          ld8(sx, i, xv);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float dr = gn_act_grad<ACT, false>(d[u][k], 0.f, xv[k], ga[k], gs[k]);
+            const float xh = (xv[k] - mu[k]) * rs[k];
+            o[k] = rs[k] * (dr * gm[k] - s1[k] - xh * s2[k]);
+          }
+          IO<T>::store8(dstp + (size_t)i * 8, o);
+        }
+      }
+    }
   }
   cluster.barrier_wait();
 }
 
 #define GN_FUSED_BWD_MAX_SMEM (216 * 1024)
 // cluster size and pixels per CTA of the fused backward; 0 = not eligible (the two-kernel path below runs)
-static int gn_fused_bwd_plan(int B, int HW, int C, int G, int esize, int& ppc, size_t& smem) {
+// dy_smem: x AND dy staged (small maps: everything fits at two or more CTAs per SM); otherwise only x is staged and dy is read
+// from global memory in both passes (the second read hits the L2) -- 100 KB instead of 200 KB per CTA at bf16 [56,56,128], so
+// two CTAs per SM are resident and the 32 clusters of a batch run as ONE wave (with 200 KB: two waves, SMs idle 44 % of the time).
+static int gn_fused_bwd_plan(int B, int HW, int C, int G, int esize, int& ppc, size_t& smem, bool& dy_smem) {
   const int C8 = C / 8;
   if (C % 8 || C8 > 256 || 256 % C8 || G <= 0 || C % G || B > 65535 || HW <= 0) return 0;
   int CL = 8;
   while (CL > 1 && HW < 16 * CL) CL >>= 1;
   ppc = (HW + CL - 1) / CL;
-  smem = (size_t)2 * ppc * C * esize + sizeof(float) * (2 * C + 4 * G) + 16;
+  const size_t slice = (size_t)ppc * C * esize, tail = sizeof(float) * (2 * C + 4 * G) + 16;
+  static int force = -1;                 // MTUS_GN_BWD_DY_SMEM=1: always stage dy too when it fits (A/B)
+  if (force < 0) { const char* e = getenv("MTUS_GN_BWD_DY_SMEM"); force = e ? atoi(e) : 0; }
+  dy_smem = 2 * slice + tail <= (size_t)(force ? GN_FUSED_BWD_MAX_SMEM : 100 * 1024);
+  smem = (dy_smem ? 2 : 1) * slice + tail;
   if (smem > GN_FUSED_BWD_MAX_SMEM) return 0;
   return CL;
 }
 
-template <typename T, int ACT>
+template <typename T, int ACT, bool DY_SMEM>
 static int gn_fused_bwd_launch(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta, void* dx,
                                float* dgamma, float* dbeta, int B, int HW, int C, int G, int CL, int ppc, size_t smem, cudaStream_t st) {
-  auto kern = gn_fused_bwd_kernel<T, ACT>;
+  auto kern = gn_fused_bwd_kernel<T, ACT, DY_SMEM>;
   static mtus_per_device_flag configured;
   if (!configured.get()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GN_FUSED_BWD_MAX_SMEM);
@@ -692,13 +751,13 @@ extern "C" int mtus_groupnorm_act_bwd(const void* dy, const void* x, const void*
       const char* ev = getenv("MTUS_GN_FUSED"); use_fused = ev ? atoi(ev) : 1;
       const char* eb = getenv("MTUS_GN_FUSED_BWD"); if (eb) use_fused = atoi(eb);
     }
-    int ppc = 0; size_t smem = 0;
-    const int CL = use_fused ? gn_fused_bwd_plan(B, HW, C, G, dtype == MTUS_F32 ? 4 : 2, ppc, smem) : 0;
+    int ppc = 0; size_t smem = 0; bool dys = true;
+    const int CL = use_fused ? gn_fused_bwd_plan(B, HW, C, G, dtype == MTUS_F32 ? 4 : 2, ppc, smem, dys) : 0;
     if (CL > 0) {
-      if (dtype == MTUS_F32) return act == 0 ? gn_fused_bwd_launch<float, 0>(dy, x, mean, rstd, gamma, beta, dx, dgamma, dbeta, B, HW, C, G, CL, ppc, smem, st)
-                                             : gn_fused_bwd_launch<float, 1>(dy, x, mean, rstd, gamma, beta, dx, dgamma, dbeta, B, HW, C, G, CL, ppc, smem, st);
-      return act == 0 ? gn_fused_bwd_launch<bf16, 0>(dy, x, mean, rstd, gamma, beta, dx, dgamma, dbeta, B, HW, C, G, CL, ppc, smem, st)
-                      : gn_fused_bwd_launch<bf16, 1>(dy, x, mean, rstd, gamma, beta, dx, dgamma, dbeta, B, HW, C, G, CL, ppc, smem, st);
+#define GN_FB(T_, A_, D_) gn_fused_bwd_launch<T_, A_, D_>(dy, x, mean, rstd, gamma, beta, dx, dgamma, dbeta, B, HW, C, G, CL, ppc, smem, st)
+      if (dtype == MTUS_F32) return act == 0 ? (dys ? GN_FB(float, 0, true) : GN_FB(float, 0, false)) : (dys ? GN_FB(float, 1, true) : GN_FB(float, 1, false));
+      return act == 0 ? (dys ? GN_FB(bf16, 0, true) : GN_FB(bf16, 0, false)) : (dys ? GN_FB(bf16, 1, true) : GN_FB(bf16, 1, false));
+#undef GN_FB
     }
   }
   cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(float) * 2 * B * G, st);
