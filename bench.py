@@ -421,7 +421,9 @@ def run_native(args):
         loss = trainer.step(xd, yd, tid)
         if not last:
             prefetch.issue(*host[key[seq[i + 1]]])
-        v = loss.item()                          # device -> host read of the step's result
+        # device -> host read of the step's result, every step: through the trainer's side-stream read-back (the value leaves
+        # the device as soon as the forward + loss are done instead of behind the whole backward); plain .item() for inference
+        v = trainer.loss_item() if hasattr(trainer, "loss_item") else loss.item()
         h2d = x.numel() * x.element_size() + y.numel() * y.element_size()
         if i >= args.warmup:
             h2d_sum += h2d

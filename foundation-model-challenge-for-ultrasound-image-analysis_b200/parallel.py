@@ -263,6 +263,11 @@ class GradAllReducer:
                         dist.broadcast(b.data, src=0, group=self.group)
 
 
+class _DoneNow:
+    def synchronize(self):
+        pass
+
+
 class DataParallelTrainer:
     """One training step with the reference's semantics (train.py:326,440-455) on 1..N ranks.
 
@@ -278,6 +283,40 @@ class DataParallelTrainer:
             optimizer.max_norm = self.clip
         self.reducer = GradAllReducer(model, group=group)
         self.reducer.broadcast_parameters(0)
+        self._loss_reader = None
+
+    def loss_item(self) -> float:
+        """The last step's loss as a Python float (the reference's ``loss.item()`` per step, train.py:330-332).
+
+        ``tensor.item()`` on the returned loss is ordered behind EVERYTHING the step enqueued (backward, all-reduce,
+        optimizer), so the host would sit idle until the step ends and the device would then wait for the next step's first
+        launches.  Here the value is copied to pinned host memory on a side stream that only waits for the forward + loss
+        (an event recorded before ``backward``): the host gets the number while the backward is still running and enqueues
+        the next step behind it."""
+        if self._loss_reader is None or self._loss_reader[2] is None:
+            raise RuntimeError("loss_item(): no step has run yet")
+        host, _, done = self._loss_reader
+        done.synchronize()
+        return float(host[0])
+
+    def _post_loss_readback(self, total):
+        if not total.is_cuda:
+            self._loss_reader = (total.detach().reshape(1).float().clone(), None, _DoneNow())
+            return
+        if self._loss_reader is None or self._loss_reader[1] is None or self._loss_reader[1].device != total.device:
+            self._loss_reader = (torch.empty(1, dtype=torch.float32).pin_memory(), torch.cuda.Stream(device=total.device), None)
+        host, side, _ = self._loss_reader
+        cur = torch.cuda.current_stream(total.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        src = total.detach()
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            host.copy_(src.reshape(1).float(), non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(side)
+        src.record_stream(side)
+        self._loss_reader = (host, side, done)
 
     def step(self, images, labels, task_id):
         from .losses import compute_task_loss
@@ -285,6 +324,7 @@ class DataParallelTrainer:
         outputs = self.model(images, task_id=task_id)
         loss = compute_task_loss(self.loss_functions, task_name, outputs, labels)
         total = loss * self.loss_weights.get(task_name, 1.0)
+        self._post_loss_readback(total)
         self.optimizer.zero_grad()
         head = self.model.heads[task_id] if hasattr(self.model, "heads") else None
         if head is not None:

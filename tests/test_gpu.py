@@ -184,6 +184,7 @@ def test_flat_adamw_matches_torch_adamw_with_clipping():
         la = trainers[0].step(x, y, tcfg["task_id"])
         lb = trainers[1].step(x, y, tcfg["task_id"])
         assert abs(float(la) - float(lb)) <= 1e-5 * max(1.0, abs(float(la)))
+        assert trainers[1].loss_item() == float(lb)          # side-stream read-back of the same value
     pa, pb = dict(models[0].named_parameters()), dict(models[1].named_parameters())
     for k in pa:
         assert torch.allclose(pa[k], pb[k], rtol=2e-4, atol=2e-6), k
