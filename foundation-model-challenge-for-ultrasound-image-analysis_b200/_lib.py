@@ -79,6 +79,8 @@ SIGNATURES = {
     "mtus_add": (i32, [vp, vp, vp, i64, i32, vp]),
     "mtus_sumsq": (i32, [vp, i64, vp, vp]),
     "mtus_adamw_flat": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp, vp]),
+    "mtus_pointwise_conv_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "mtus_pointwise_conv_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_adamw_flat_shadow": (i32, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp, vp]),
     "mtus_scale_cast_colsum": (i32, [vp, vp, i32, vp, vp, i64, i32, i32, vp]),
     "mtus_convert": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),

@@ -1255,3 +1255,152 @@ extern "C" int mtus_conv3x3_unpack_grad(const float* dw_packed, float* dw, int C
   MTUS_LAUNCH_STATUS();
   return MTUS_OK;
 }
+
+// ---- pointwise (1x1) convolution with a handful of output channels: the tails of the task heads -----------------------------
+// SegmentationHead ends in Conv2d(128 -> num_classes, 1) (code/models/heads.py:16-42 via smp's SegmentationHead) and the baseline
+// detection head in Conv2d(128 -> 4 + num_classes, 1) (heads.py:404-428): N <= 8 outputs over [B*H*W, K] channels-last rows.  As
+// GEMMs they are degenerate (cuBLAS: 27 us forward, and 19 + 92 + 8 us of data / weight gradient GEMMs plus a 49 us two-block bias
+// reduction backward at [100352, 128]); as streaming kernels they are one read of x forward and one read + one write backward.
+// Layouts: x [B, HW, K] (T), w [N, K] fp32, y / dy [B, N, HW] fp32 (NCHW planes, what the upsampling / loss behind them reads).
+// LPR = K / 8 lanes share a pixel (8 channels each), so a warp covers 32 / LPR pixels per iteration; K / 8 must be a power of two <= 32.
+#define PW_MAXN 8
+template <typename T, int N>
+__global__ void __launch_bounds__(256) pointwise_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                            float* __restrict__ y, int64_t rows, int HW, int K) {
+  const int LPR = K / 8, sub = threadIdx.x % LPR, ppb = 256 / LPR;
+  float wr[N][8];
+#pragma unroll
+  for (int j = 0; j < N; ++j) IO<float>::load8(w + (size_t)j * K + sub * 8, wr[j]);
+  for (int64_t p0 = (int64_t)blockIdx.x * ppb * 2; p0 < rows; p0 += (int64_t)gridDim.x * ppb * 2) {
+    float xv[2][8];
+    int64_t p[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {                       // two pixels in flight per lane group
+      p[u] = p0 + u * ppb + threadIdx.x / LPR;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) xv[u][k] = 0.f;
+      if (p[u] < rows) IO<T>::load8(x + p[u] * K + sub * 8, xv[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {                       // no early exit: the shuffles below need every lane of the warp
+      float acc[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        acc[j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[j] = fmaf(xv[u][k], wr[j][k], acc[j]);
+      }
+      for (int off = 1; off < LPR; off <<= 1) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off, 32);
+      }
+      if (sub == 0 && p[u] < rows) {
+        const int64_t b = p[u] / HW, q = p[u] - b * HW;
+#pragma unroll
+        for (int j = 0; j < N; ++j) y[(b * N + j) * HW + q] = acc[j] + (bias ? __ldg(bias + j) : 0.f);
+      }
+    }
+  }
+}
+
+// dx[p, :] = sum_j dy[j, p] w[j, :];  dw[j, :] += sum_p dy[j, p] x[p, :];  dbias[j] += sum_p dy[j, p]
+template <typename T, int N>
+__global__ void __launch_bounds__(256) pointwise_bwd_kernel(const float* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ w,
+                                                            T* __restrict__ dx, float* __restrict__ dw, float* __restrict__ dbias, int64_t rows,
+                                                            int HW, int K) {
+  extern __shared__ float pw_red[];                     // [N][K] + [N]
+  const int LPR = K / 8, sub = threadIdx.x % LPR, ppb = 256 / LPR;
+  float wr[N][8], aw[N][8], ab[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    IO<float>::load8(w + (size_t)j * K + sub * 8, wr[j]);
+    ab[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) aw[j][k] = 0.f;
+  }
+  for (int i = threadIdx.x; i < N * K + N; i += 256) pw_red[i] = 0.f;
+  for (int64_t p0 = (int64_t)blockIdx.x * ppb * 2; p0 < rows; p0 += (int64_t)gridDim.x * ppb * 2) {
+    float xv[2][8], g[2][N];
+    int64_t p[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      p[u] = p0 + u * ppb + threadIdx.x / LPR;
+      if (p[u] < rows) {
+        IO<T>::load8(x + p[u] * K + sub * 8, xv[u]);
+        const int64_t b = p[u] / HW, q = p[u] - b * HW;
+#pragma unroll
+        for (int j = 0; j < N; ++j) g[u][j] = __ldg(dy + (b * N + j) * HW + q);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (p[u] >= rows) continue;
+      float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { o[k] = fmaf(g[u][j], wr[j][k], o[k]); aw[j][k] = fmaf(g[u][j], xv[u][k], aw[j][k]); }
+        if (sub == 0) ab[j] += g[u][j];
+      }
+      if (dx) IO<T>::store8(dx + p[u] * K + sub * 8, o);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v = aw[j][k];
+      for (int off = LPR; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off, 32);      // lanes of the warp with the same channels
+      if ((threadIdx.x & 31) < LPR || LPR >= 32) atomicAdd(&pw_red[j * K + sub * 8 + k], v);
+    }
+    if (sub == 0) atomicAdd(&pw_red[N * K + j], ab[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N * K; i += 256) MTUS_ATOMIC_ADD(dw + i, pw_red[i]);
+  if (threadIdx.x < N) MTUS_ATOMIC_ADD(dbias + threadIdx.x, pw_red[N * K + threadIdx.x]);
+}
+
+static bool pw_ok(int K, int N) {
+  const int l = K / 8;
+  return K % 8 == 0 && l >= 1 && l <= 32 && (l & (l - 1)) == 0 && N >= 1 && N <= PW_MAXN;
+}
+
+extern "C" int mtus_pointwise_conv_fwd(const void* x, const float* w, const float* bias, float* y, int B, int HW, int K, int N, int dtype,
+                                       void* stream) {
+  MTUS_CHECK_ARG(x && w && y && B >= 0 && HW > 0);
+  if (!pw_ok(K, N)) return MTUS_ERR_UNSUPPORTED;
+  MTUS_CHECK_ARG(dtype == MTUS_F32 || dtype == MTUS_BF16);
+  const int64_t rows = (int64_t)B * HW;
+  if (rows == 0) return MTUS_OK;
+  const int ppb = 256 / (K / 8);
+  const int grid = (int)std::min<int64_t>((rows + 2 * ppb - 1) / (2 * ppb), 148 * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+#define PW_F(T_, N_) case N_: pointwise_fwd_kernel<T_, N_><<<grid, 256, 0, st>>>((const T_*)x, w, bias, y, rows, HW, K); break;
+#define PW_FS(T_) switch (N) { PW_F(T_, 1) PW_F(T_, 2) PW_F(T_, 3) PW_F(T_, 4) PW_F(T_, 5) PW_F(T_, 6) PW_F(T_, 7) PW_F(T_, 8) }
+  if (dtype == MTUS_F32) PW_FS(float) else PW_FS(bf16)
+#undef PW_FS
+#undef PW_F
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}
+
+extern "C" int mtus_pointwise_conv_bwd(const float* dy, const void* x, const float* w, void* dx, float* dw, float* dbias, int B, int HW, int K,
+                                       int N, int dtype, void* stream) {
+  MTUS_CHECK_ARG(dy && x && w && dw && dbias && B >= 0 && HW > 0);
+  if (!pw_ok(K, N)) return MTUS_ERR_UNSUPPORTED;
+  MTUS_CHECK_ARG(dtype == MTUS_F32 || dtype == MTUS_BF16);
+  const int64_t rows = (int64_t)B * HW;
+  if (rows == 0) return MTUS_OK;
+  const int ppb = 256 / (K / 8);
+  const int grid = (int)std::min<int64_t>((rows + 2 * ppb - 1) / (2 * ppb), 148 * 4);
+  const size_t sm = sizeof(float) * ((size_t)N * K + N);
+  cudaStream_t st = (cudaStream_t)stream;
+#define PW_B(T_, N_) case N_: pointwise_bwd_kernel<T_, N_><<<grid, 256, sm, st>>>(dy, (const T_*)x, w, (T_*)dx, dw, dbias, rows, HW, K); break;
+#define PW_BS(T_) switch (N) { PW_B(T_, 1) PW_B(T_, 2) PW_B(T_, 3) PW_B(T_, 4) PW_B(T_, 5) PW_B(T_, 6) PW_B(T_, 7) PW_B(T_, 8) }
+  if (dtype == MTUS_F32) PW_BS(float) else PW_BS(bf16)
+#undef PW_BS
+#undef PW_B
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}

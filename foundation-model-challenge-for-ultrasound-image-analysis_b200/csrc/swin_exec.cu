@@ -565,8 +565,14 @@ static int swin_backward_impl(const mtus_swin_config* cfg, const float* params, 
       const int shift = (j % 2) ? p.shift[i] : 0;
       const float* dp1 = droppath ? droppath + (size_t)(2 * gblk) * p.B : nullptr;
       // ---- MLP branch (Gb = dp2 * G; fc2.bias gradient already accumulated by the producer of Gb) ----
-      RUN(mtus_linear_dgrad_dact(Gb, W(bp.fc2w), dH, A(ba.h), GR(bp.fc1b), M, Cc, 4 * Cc, dt, be, stream));
+      // fc1.bias gradient = column sums of dH: inside the GEMM epilogue (warp-shuffle reductions, 2.6 us of a 22.7 us launch at
+      // stage 3 and 9.5 of 60 us at stage 1), or -- MTUS_FC1B_SIDE=1 -- as a colsum pass over dH on the weight-gradient stream
+      static int fc1b_side = -1;
+      if (fc1b_side < 0) { const char* e = getenv("MTUS_FC1B_SIDE"); fc1b_side = e ? atoi(e) : 0; }
+      const bool side_cs = ss && fc1b_side && dt == MTUS_BF16;
+      RUN(mtus_linear_dgrad_dact(Gb, W(bp.fc2w), dH, A(ba.h), side_cs ? nullptr : GR(bp.fc1b), M, Cc, 4 * Cc, dt, be, stream));
       if (ss) { CU(cudaEventRecord(ss->e1, st)); CU(cudaStreamWaitEvent(ss->s, ss->e1, 0)); }
+      if (side_cs) RUN_STREAM(mtus_colsum(dH, GR(bp.fc1b), M, 4 * Cc, dt, wst), wst);
       RUN_STREAM(mtus_linear_wgrad(Gb, A(ba.a), GR(bp.fc2w), nullptr, M, Cc, 4 * Cc, dt, be, wst), wst);
       RUN_STREAM(mtus_linear_wgrad(dH, A(ba.ln2), GR(bp.fc1w), nullptr, M, 4 * Cc, Cc, dt, be, wst), wst);
       if (ss) CU(cudaEventRecord(ss->d1, ss->s));

@@ -123,6 +123,51 @@ def _conv3x3(x, conv):
     return conv(x)
 
 
+class _PointwiseConvFn(torch.autograd.Function):
+    """1x1 convolution with a handful of output channels (the Conv2d(128 -> num_classes, 1) tails of the segmentation and
+    detection heads) as streaming kernels over the channels-last rows: fp32 NCHW logits out; backward = one pass that writes
+    dx and accumulates dw / dbias (replaces three degenerate cuBLAS GEMMs and a two-block bias reduction)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        from . import ops
+        xn = x.permute(0, 2, 3, 1)
+        if not xn.is_contiguous():
+            xn = xn.contiguous()
+        w2 = weight.detach().float().reshape(weight.shape[0], -1).contiguous()
+        y = ops.pointwise_conv_fwd(xn, w2, None if bias is None else bias.detach().float().contiguous())
+        ctx.save_for_backward(xn, w2)
+        ctx.wshape, ctx.wdtype = weight.shape, weight.dtype
+        ctx.bdtype = None if bias is None else bias.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import ops
+        xn, w2 = ctx.saved_tensors
+        dx, dw, db = ops.pointwise_conv_bwd(dy.float().contiguous(), xn, w2, need_dx=ctx.needs_input_grad[0])
+        return (None if dx is None else dx.permute(0, 3, 1, 2), dw.reshape(ctx.wshape).to(ctx.wdtype),
+                None if ctx.bdtype is None else db.to(ctx.bdtype))
+
+
+def _pointwise_ok(x, conv):
+    if os.environ.get("MTUS_HEAD_CONV", "native") != "native" or os.environ.get("MTUS_HEAD_POINTWISE", "1") == "0":
+        return False
+    l = conv.in_channels // 8
+    return (isinstance(conv, nn.Conv2d) and x.is_cuda and x.dim() == 4 and x.dtype in (torch.bfloat16, torch.float32)
+            and conv.kernel_size == (1, 1) and conv.padding == (0, 0) and conv.stride == (1, 1) and conv.dilation == (1, 1)
+            and conv.groups == 1 and conv.in_channels % 8 == 0 and 1 <= l <= 32 and (l & (l - 1)) == 0 and conv.out_channels <= 8)
+
+
+def _conv1x1(x, conv):
+    """conv(x) through the pointwise kernels when the geometry allows it (fp32 logits), else the module itself."""
+    if _pointwise_ok(x, conv):
+        if torch.is_autocast_enabled() and x.dtype == torch.float32:
+            x = x.to(torch.get_autocast_gpu_dtype())
+        return _PointwiseConvFn.apply(x, conv.weight, conv.bias)
+    return conv(x)
+
+
 class _BatchNormReLUFn(torch.autograd.Function):
     """relu(batch_norm(x)) for a channels-last CUDA tensor through the library's normalisation kernels: per-channel batch
     statistics (training) or the running statistics (eval), one fused normalise + ReLU pass, two-kernel backward."""
@@ -211,8 +256,17 @@ class SegmentationHead(nn.Module):
                 else:
                     x = mods[i](x)
                     i += 1
-            return self.head(x)
+            return self._tail(x)
         return self.head(self.pre_head(x))
+
+    def _tail(self, x):
+        mods = list(self.head)                   # Conv2d -> upsampling -> Identity
+        if mods and isinstance(mods[0], nn.Conv2d) and _pointwise_ok(x, mods[0]):
+            x = _conv1x1(x, mods[0])
+            for m in mods[1:]:
+                x = m(x)
+            return x
+        return self.head(x)
 
 
 class BaselineSmpClassificationHead(nn.Module):
@@ -256,6 +310,9 @@ class BaselineFPNGridDetectionHead(nn.Module):
                         and isinstance(mods[i + 2], nn.ReLU)):
                     x = _bn_relu(_conv3x3(x, mods[i]), mods[i + 1])
                     i += 3
+                elif isinstance(mods[i], nn.Conv2d) and _pointwise_ok(x, mods[i]):
+                    x = _conv1x1(x, mods[i])
+                    i += 1
                 else:
                     x = mods[i](x)
                     i += 1

@@ -371,3 +371,23 @@ def batchnorm_relu_bwd(dy, x, y, mean, rstd, gamma, training=True):
     check(lib().mtus_batchnorm_act_bwd(ptr(dy), ptr(x), ptr(y), ptr(mean), ptr(rstd), ptr(gamma), None, ptr(dx), ptr(dg), ptr(db), ptr(ws),
                                        x.numel() // Cc, Cc, 0, int(training), _dt(x), stream_ptr()), "batchnorm_act_bwd")
     return dx, dg, db
+
+
+def pointwise_conv_fwd(x, w, bias=None):
+    """x [B,H,W,K] channels-last rows, w [N,K] fp32, bias [N] -> y [B,N,H,W] fp32 (N <= 8; the head tails)."""
+    B, H, W, K = x.shape
+    N = w.shape[0]
+    y = torch.empty(B, N, H, W, dtype=torch.float32, device=x.device)
+    check(lib().mtus_pointwise_conv_fwd(ptr(x), ptr(w), ptr(bias), ptr(y), B, H * W, K, N, _dt(x), stream_ptr()), "pointwise_conv_fwd")
+    return y
+
+
+def pointwise_conv_bwd(dy, x, w, need_dx=True):
+    """dy [B,N,H,W] fp32 contiguous -> (dx [B,H,W,K] | None, dw [N,K] fp32, dbias [N] fp32)."""
+    B, H, W, K = x.shape
+    N = w.shape[0]
+    dx = torch.empty_like(x) if need_dx else None
+    dw = torch.zeros(N, K, dtype=torch.float32, device=x.device)
+    db = torch.zeros(N, dtype=torch.float32, device=x.device)
+    check(lib().mtus_pointwise_conv_bwd(ptr(dy), ptr(x), ptr(w), ptr(dx), ptr(dw), ptr(db), B, H * W, K, N, _dt(x), stream_ptr()), "pointwise_conv_bwd")
+    return dx, dw, db

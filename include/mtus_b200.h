@@ -135,6 +135,15 @@ int mtus_convert(const void* x, void* y, int B, int R, int Cc, int transpose, in
 int mtus_nhwc_to_nchw(const void* x, void* y, int B, int HW, int C, int dtype, int out_f32, void* stream);
 int mtus_nchw_to_nhwc(const void* x, void* y, int B, int HW, int C, int dtype, int in_f32, void* stream);
 
+/* ---- pointwise (1x1) convolution with N <= 8 output channels: the Conv2d(128 -> num_classes, 1) tails of the segmentation
+ * and detection heads (code/models/heads.py:16-42, 404-428).  x: [B, HW, K] channels-last rows (dtype), w: [N, K] fp32,
+ * bias: [N] fp32 or NULL, y / dy: [B, N, HW] fp32 (NCHW planes).  K / 8 must be a power of two <= 32.
+ * bwd: dx (dtype, may be NULL) is written, dw [N, K] and dbias [N] are ACCUMULATED (+=). */
+int mtus_pointwise_conv_fwd(const void* x, const float* w, const float* bias, float* y, int B, int HW, int K, int N, int dtype,
+                            void* stream);
+int mtus_pointwise_conv_bwd(const float* dy, const void* x, const float* w, void* dx, float* dw, float* dbias, int B, int HW, int K,
+                            int N, int dtype, void* stream);
+
 /* ---- optimizer step over the flat parameter blocks (torch.optim.AdamW rule, code/train.py:208,455) ----------- */
 /* out += sum(g^2)  (global gradient norm for clip_grad_norm_, code/train.py:446) */
 int mtus_sumsq(const float* g, int64_t n, float* out, void* stream);

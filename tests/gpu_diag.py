@@ -370,6 +370,21 @@ def g_fpn_ops():
             refu = skip.float() + F.interpolate(top.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
             ok &= report(f"upsample_add_fwd", ops.upsample_add_fwd(skip, top), refu, tol)
             ok &= report(f"upsample_add_bwd", ops.upsample_add_bwd(du), F.avg_pool2d(du.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1) * 4, tol)
+        # pointwise (1x1) convolution with a few output channels: the head tails
+        for (B, H, W, K, N) in ((2, 56, 56, 128, 2), (3, 14, 14, 128, 5), (1, 7, 9, 64, 1), (2, 5, 5, 256, 8), (1, 3, 3, 8, 3)):
+            xs = torch.randn(B, H, W, K, device=dev).to(dt)
+            wq = torch.randn(N, K, device=dev) * 0.1
+            bq = torch.randn(N, device=dev)
+            xr3 = xs.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+            wr3, br3 = wq.clone().requires_grad_(True), bq.clone().requires_grad_(True)
+            yr3 = F.conv2d(xr3, wr3[:, :, None, None], br3)
+            ok &= report(f"pointwise_conv_fwd {dt} {B,H,W,K,N}", ops.pointwise_conv_fwd(xs, wq, bq), yr3, max(tol, 1e-5))
+            dy3 = torch.randn(B, N, H, W, device=dev)
+            yr3.backward(dy3)
+            dx3, dw3, db3 = ops.pointwise_conv_bwd(dy3, xs, wq)
+            ok &= report(f"pointwise_conv_bwd dx", dx3, xr3.grad.permute(0, 2, 3, 1), max(tol, 1e-5))
+            ok &= report(f"pointwise_conv_bwd dw", dw3, wr3.grad, 2e-4)
+            ok &= report(f"pointwise_conv_bwd dbias", db3, br3.grad, 2e-4)
     return ok
 
 
