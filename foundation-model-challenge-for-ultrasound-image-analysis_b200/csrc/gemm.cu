@@ -40,7 +40,7 @@ extern "C" int mtus_gemm(const mtus_gemm_desc* d, void* stream) {
     if (mtus_gemm_tc2_supported(d)) return mtus_gemm_tc2(d, st);   // persistent TMA-in / TMA-out tcgen05 engine
     if (d->backend == MTUS_BACKEND_TCGEN05 && !f) return MTUS_ERR_UNSUPPORTED;  // explicit request: fail loudly
   }
-  // shapes the tensor-core engine does not take (unaligned leading dimensions, conv weight gradients with Cin % 128 != 0,
+  // shapes the tensor-core engine does not take (unaligned leading dimensions, conv weight gradients with Cin % 64 != 0,
   // fp32 mode): the SIMT engine
   int rc = mtus_gemm_simt(d, ep, st);
   if (rc) return rc;

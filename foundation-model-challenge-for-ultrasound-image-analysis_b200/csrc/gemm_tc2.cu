@@ -537,7 +537,7 @@ bool mtus_gemm_tc2_supported(const mtus_gemm_desc* d) {
     if (d->atomic && (d->bias || d->res || d->rowscale)) return false;
     if (d->res && (!d->res_f32 || d->res_mode != 1 || d->ld_res % 4 || !al16(d->res))) return false;
     if (d->a_conv || d->out_colsum) return false;
-    if (wgrad_conv && (!d->atomic || d->lda % 64 || d->conv_c % 128 || d->M % 64)) return false;
+    if (wgrad_conv && (!d->atomic || d->lda % 64 || d->conv_c % 64 || d->M % 64)) return false;   // an n-tile must lie inside one tap: BN | Cin
   } else {
     if (d->atomic || d->res_f32) return false;
     if (d->ld_out % 8) return false;
@@ -569,6 +569,14 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
     static int wg_bn = -1;
     if (wg_bn < 0) { const char* e = getenv("MTUS_WGRAD_BN"); wg_bn = e ? atoi(e) : 128; }   // measured: 128x256 weight-gradient tiles are 5-20 % SLOWER (fewer, longer work items)
     BN = (N <= 64) ? 64 : ((wg_bn == 256 && N % 256 == 0) ? 256 : 128);
+  }
+  if (wgrad_conv) {
+    // conv weight gradient: N = 9 Cin with the tap in the high part of the index, so the tile width must divide Cin
+    // (64 for Cin % 128 != 0; 256 where Cin % 256 == 0: 48 KB per k-block for twice the MACs of the 128-wide tile's 32 KB --
+    // the segmentation step gains 80 us; MTUS_CONV_WGRAD_BN=128 restores the narrower tile)
+    static int cw_bn = -1;
+    if (cw_bn < 0) { const char* e = getenv("MTUS_CONV_WGRAD_BN"); cw_bn = e ? atoi(e) : 256; }
+    BN = (d->conv_c % 128) ? 64 : ((cw_bn == 256 && d->conv_c % 256 == 0) ? 256 : (cw_bn == 64 ? 64 : 128));
   }
   int m_tiles = ceil_div(M, T2_BM), n_tiles = ceil_div(N, BN), total_kb = ceil_div(K, T2_BK);
   if (d->a_conv || d->b_conv) {
@@ -635,6 +643,10 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
     if (want < 1) want = 1;
     splits = (int)want;
   }
+  if (wgrad_conv && d->atomic && BN != 128) {       // the caller sized split_k for 128-wide tiles: keep the number of work items
+    const int64_t want = BN == 256 ? 2ll * splits : (splits + 1) / 2;
+    splits = (int)(want < 1 ? 1 : want);
+  }
   if (splits > total_kb) splits = total_kb;
   const int kbps = ceil_div(total_kb, splits);
   splits = ceil_div(total_kb, kbps);
@@ -651,6 +663,7 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
     if (BN == 256) {
       if (am == 0 && bm == 0) T2_GO(256, 0, 0, true);
       if (am == 1 && bm == 1) T2_GO(256, 1, 1, true);
+      if (am == 3 && bm == 2) T2_GO(256, 3, 2, true);
     } else if (BN == 192) {
       if (am == 0 && bm == 0) T2_GO(192, 0, 0, true);
     } else if (BN == 128) {
@@ -660,6 +673,7 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
     } else {
       if (am == 0 && bm == 0) T2_GO(64, 0, 0, true);
       if (am == 1 && bm == 1) T2_GO(64, 1, 1, true);
+      if (am == 3 && bm == 2) T2_GO(64, 3, 2, true);
     }
   } else if (BN == 256) {
     if (am == 0 && bm == 0) T2_GO(256, 0, 0, false);
