@@ -570,6 +570,13 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
     if (wg_bn < 0) { const char* e = getenv("MTUS_WGRAD_BN"); wg_bn = e ? atoi(e) : 128; }   // measured: 128x256 weight-gradient tiles are 5-20 % SLOWER (fewer, longer work items)
     BN = (N <= 64) ? 64 : ((wg_bn == 256 && N % 256 == 0) ? 256 : 128);
   }
+  if (d->a_conv) {
+    // implicit-GEMM conv forward / data gradient: 256-wide tiles when the output channels allow (the data gradient of the
+    // segmentation head's Conv3x3(512 -> 128) has N = 512); MTUS_CONV_BN=128 restores the narrower tile
+    static int cv_bn = -1;
+    if (cv_bn < 0) { const char* e = getenv("MTUS_CONV_BN"); cv_bn = e ? atoi(e) : 256; }
+    if (cv_bn == 256 && N % 256 == 0) BN = 256;
+  }
   if (wgrad_conv) {
     // conv weight gradient: N = 9 Cin with the tap in the high part of the index, so the tile width must divide Cin
     // (64 for Cin % 128 != 0; 256 where Cin % 256 == 0: 48 KB per k-block for twice the MACs of the 128-wide tile's 32 KB --
@@ -678,6 +685,7 @@ int mtus_gemm_tc2(const mtus_gemm_desc* d, cudaStream_t st) {
   } else if (BN == 256) {
     if (am == 0 && bm == 0) T2_GO(256, 0, 0, false);
     if (am == 0 && bm == 1) T2_GO(256, 0, 1, false);
+    if (am == 2 && bm == 0) T2_GO(256, 2, 0, false);
   } else if (BN == 192) {
     if (am == 0 && bm == 0) T2_GO(192, 0, 0, false);
     if (am == 0 && bm == 1) T2_GO(192, 0, 1, false);
