@@ -209,6 +209,43 @@ def test_persistent_buffers_keep_autograd_semantics():
     assert core._take_workspace(8, 1024, dev).data_ptr() != w1.data_ptr()
 
 
+def test_parameter_version_key_sees_every_in_place_write_through_torch():
+    """FlatParamModule.params_version_key guards the optimizer-written bf16 shadow (encoders.py): it must change when a
+    parameter view or the flat block is written in place (load_state_dict, torch optimizers, broadcasts) and stay put
+    otherwise; a re-flatten (module move) changes it through the block's address."""
+    enc = m.SwinTransformerEncoder("swin_t", pretrained=False, img_size=224, precision="bf16")
+    core = enc.model
+    k0 = core.params_version_key()
+    assert core.params_version_key() == k0                       # reading it does not change it
+    with torch.no_grad():
+        core.ordered_params()[5].mul_(1.0)
+    k1 = core.params_version_key()
+    assert k1 != k0
+    with torch.no_grad():
+        core.flat_params().add_(0.0)
+    k2 = core.params_version_key()
+    assert k2 != k1
+    core.load_state_dict(core.state_dict())
+    k3 = core.params_version_key()
+    assert k3 != k2
+    core.to(torch.float32)                                       # _apply re-flattens: new block
+    assert core.params_version_key()[0] != k3[0] or core.params_version_key() != k3
+
+
+def test_trainer_loss_item_on_cpu_matches_the_returned_loss():
+    """DataParallelTrainer.loss_item(): the side-stream read-back degenerates to a plain copy on CPU tensors."""
+    import types
+    from mtus_b200.parallel import DataParallelTrainer
+    tr = DataParallelTrainer.__new__(DataParallelTrainer)
+    tr._loss_reader = None
+    with pytest.raises(RuntimeError):
+        tr.loss_item()
+    tr._post_loss_readback(torch.tensor(1.25))
+    assert tr.loss_item() == 1.25
+    tr._post_loss_readback(torch.tensor(-3.5, dtype=torch.float64))
+    assert tr.loss_item() == -3.5
+
+
 def test_flat_adamw_is_a_torch_optimizer_and_follows_lr_schedulers():
     """the reference's CosineAnnealingLR (code/train.py:222-253, stepped at :698-704) must be able to drive
     FlatAdamW.  CPU part: a model without flat blocks (everything goes through the mirrored torch groups)."""
