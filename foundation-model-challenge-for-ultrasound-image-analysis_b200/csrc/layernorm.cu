@@ -798,10 +798,12 @@ static int lnv2_bwd_launch(const LnxBwdArgs& a, MergeGeom g, cudaStream_t st) {
     cudaError_t le = mtus_launch_pdl(kern, dim3((int)blocks), dim3(128), sm, st, a, g);                      \
     if (le != cudaSuccess) return (int)le;                                                                   \
   }
-  if (nvec <= 4) V2B(4, 1, 2, 6)
-  else if (nvec <= 8) V2B(8, 1, 2, 6)
-  else if (nvec <= 16) V2B(16, 1, 2, 6)
-  else if (nvec <= 32) V2B(32, 1, 2, 6)
+  // 138 registers x 128 threads: three CTAs per SM are resident, so three per SM is exactly one wave (six left a second wave
+  // that pays the prologue / column-sum epilogue again: 41.8 -> 40.4 us at [100352, 128], 24.4 -> 23.2 us at [25088, 256])
+  if (nvec <= 4) V2B(4, 1, 2, 3)
+  else if (nvec <= 8) V2B(8, 1, 2, 3)
+  else if (nvec <= 16) V2B(16, 1, 2, 3)
+  else if (nvec <= 32) V2B(32, 1, 2, 3)
   else if (nvec <= 64) {
     // one row per warp iteration, 162 registers, 3 CTAs per SM: 13.1 us at [6272, 512] against 15.5 us for the two-row form
     // (214 registers, 2 CTAs per SM), which stays selectable with MTUS_LN_BWD_U=2
