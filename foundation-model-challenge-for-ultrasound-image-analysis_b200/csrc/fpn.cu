@@ -1393,10 +1393,12 @@ extern "C" int mtus_pointwise_conv_bwd(const float* dy, const void* x, const flo
   const int64_t rows = (int64_t)B * HW;
   if (rows == 0) return MTUS_OK;
   const int ppb = 256 / (K / 8);
-  const int grid = (int)std::min<int64_t>((rows + 2 * ppb - 1) / (2 * ppb), 148 * 4);
   const size_t sm = sizeof(float) * ((size_t)N * K + N);
   cudaStream_t st = (cudaStream_t)stream;
-#define PW_B(T_, N_) case N_: pointwise_bwd_kernel<T_, N_><<<grid, 256, sm, st>>>(dy, (const T_*)x, w, (T_*)dx, dw, dbias, rows, HW, K); break;
+  // one resident wave: the register count (63 .. 236 with N) decides how many 256-thread CTAs an SM holds
+#define PW_B(T_, N_) case N_: { int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pointwise_bwd_kernel<T_, N_>, 256, sm);           \
+    const int g2 = (int)std::min<int64_t>((rows + 2 * ppb - 1) / (2 * ppb), 148 * (occ > 0 ? occ : 1));                                       \
+    pointwise_bwd_kernel<T_, N_><<<g2, 256, sm, st>>>(dy, (const T_*)x, w, (T_*)dx, dw, dbias, rows, HW, K); } break;
 #define PW_BS(T_) switch (N) { PW_B(T_, 1) PW_B(T_, 2) PW_B(T_, 3) PW_B(T_, 4) PW_B(T_, 5) PW_B(T_, 6) PW_B(T_, 7) PW_B(T_, 8) }
   if (dtype == MTUS_F32) PW_BS(float) else PW_BS(bf16)
 #undef PW_BS
