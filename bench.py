@@ -112,6 +112,15 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _config_dict(wl, world, B, S):
+    """The `config` object of the JSON line; both arms print the same one for the same workload and world size."""
+    return {"workload": wl["name"], "global_batch": world * B, "image_size": S, "parallelism": f"dp{world}",
+            "task_sequence": "random.Random(42).choice over the 27 task ids per step (MultiTaskUniformSampler)",
+            "l2": "no explicit flush: each step streams a multi-GB activation workspace (workspace_gb) plus 0.35 GB of weights, "
+                  "far beyond the 126 MB L2",
+            "detection_loss": "Detection (SURVEY 8d caveat: shipped YAML pairs the baseline head with the CenterNet loss)"}
+
+
 def _task_sequence(task_ids, n, seed=42):
     rng = random.Random(seed)            # code/data/dataset.py:145,171 -- one task per step, uniform over ids
     return [rng.choice(task_ids) for _ in range(n)]
@@ -166,6 +175,7 @@ def _cpu_sample_text(n_steps, batch, threads):
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
     threads = _cpu_threads()
@@ -187,8 +197,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / len(timed), 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{batch} images per step (bounded sample of the 32-image step)",
-                   "device": "host CPU"},
+        # the SAME config object as our arm prints (the driver compares the two lines); what the CPU actually ran per step
+        # is the bounded sample described next to it
+        "config": _config_dict(WORKLOADS["swin_b_224"], world, WORKLOADS["swin_b_224"]["batch"], WORKLOADS["swin_b_224"]["image"]),
+        "sample": f"{batch} images per step on the host CPU (bounded sample of the 32-image step), rank 0 only",
         "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": _cpu_sample_text(len(timed), batch, threads)},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -452,11 +464,7 @@ def run_native(args):
         "metric": wl["metric"], "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": wl["name"], "global_batch": world * B, "image_size": S, "parallelism": f"dp{world}",
-                   "task_sequence": "random.Random(42).choice over the 27 task ids per step (MultiTaskUniformSampler)",
-                   "l2": f"no explicit flush: each step streams a {ws_gb} GB activation workspace plus 0.35 GB of weights, "
-                         "far beyond the 126 MB L2",
-                   "detection_loss": "Detection (SURVEY 8d caveat: shipped YAML pairs the baseline head with the CenterNet loss)"},
+        "config": _config_dict(wl, world, B, S), "workspace_gb": ws_gb,
         "e2e": {"value": round(e2e, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d_sum / max(h2d_n, 1)), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": int(launches),

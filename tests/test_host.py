@@ -284,3 +284,21 @@ def test_flat_adamw_is_a_torch_optimizer_and_follows_lr_schedulers():
     sd = oa.state_dict()
     oa.load_state_dict(sd)
     assert [g["lr"] for g in oa.param_groups] == [g["lr"] for g in ob.param_groups]
+
+
+def test_bench_arms_print_the_same_config_and_non_zero_ranks_of_the_reference_arm_do_no_work(monkeypatch):
+    """bench.py contract: the CPU reference arm reports on OUR arm's config / metric / unit (the driver compares the two
+    lines), the seeded task sequence is the sampler's, and under torchrun only rank 0 of the reference arm works."""
+    import argparse
+    import bench
+    wl = bench.WORKLOADS["swin_b_224"]
+    for world in (1, 2, 8):
+        c = bench._config_dict(wl, world, wl["batch"], wl["image"])
+        assert c["global_batch"] == 32 * world and c["parallelism"] == f"dp{world}" and c["workload"] == bench.WORKLOAD
+        assert "model" not in c
+    ids = [t["task_id"] for t in m.tasks_27()]
+    rng = random.Random(42)
+    assert bench._task_sequence(ids, 16) == [rng.choice(ids) for _ in range(16)]
+    monkeypatch.setenv("RANK", "1")
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    assert bench.run_reference(argparse.Namespace(gpus=2, steps=1, warmup=0)) == 0      # returns before building anything
