@@ -88,6 +88,7 @@ SIGNATURES = {
     "mtus_nchw_to_nhwc": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_patch_embed_im2col": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "mtus_patch_embed_im2col_u8": (i32, [vp, _P(f32), _P(f32), vp, i32, i32, i32, i32, vp]),
+    "mtus_patch_embed_col2im": (i32, [vp, i32, vp, i32, i32, i32, i32, vp]),
     "mtus_window_attn_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mtus_window_attn_tc_launch_count": (i64, []),
     "mtus_window_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
@@ -121,6 +122,7 @@ SIGNATURES = {
     "mtus_swin_forward": (i32, [_P(SwinConfig), vp, i32, vp, vp, vp, vp, _P(vp), i32, i32, vp]),
     "mtus_swin_forward_u8": (i32, [_P(SwinConfig), vp, _P(f32), _P(f32), vp, vp, vp, vp, _P(vp), i32, i32, vp]),
     "mtus_swin_backward": (i32, [_P(SwinConfig), vp, vp, vp, vp, _P(vp), i32, i32, vp, i32, i32, vp]),
+    "mtus_swin_input_grad": (i32, [_P(SwinConfig), vp, vp, vp, vp, vp]),
     "mtus_graph_cache_stats": (None, [vp, vp, vp]),
     "mtus_swin_backward_blocks": (i32, [_P(SwinConfig), vp, vp, vp, vp, _P(vp), i32, i32, vp, i32, i32, vp]),
     "mtus_fpn_param_count": (i64, [_P(FpnConfig)]),

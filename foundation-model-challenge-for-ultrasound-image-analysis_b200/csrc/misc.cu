@@ -271,6 +271,40 @@ extern "C" int mtus_patch_embed_im2col(const void* x, void* cols, int B, int H, 
   return MTUS_OK;
 }
 
+// ---- gradient w.r.t. the image: the inverse gather of patch_im2col_kernel ---------------------------------------------------------
+// dcols [B*(H/4)*(W/4), ld] holds d(loss)/d(im2col operand) (k = c*16 + ky*4 + kx, 48 valid columns); the 4x4/4 patches tile the
+// image, so every pixel of dx [B,3,H,W] (fp32 NCHW, what autograd hands to the module in front of the encoder) is written once.
+template <typename TI>
+__global__ void patch_col2im_kernel(const TI* __restrict__ dcols, int ld, float* __restrict__ dx, int B, int H, int W) {
+  const int Ho = H / 4, Wo = W / 4;
+  const int64_t total = (int64_t)B * Ho * Wo * 6;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int k8 = (int)(i % 6);
+    const int64_t m = i / 6;
+    const int ox = (int)(m % Wo); const int64_t t = m / Wo; const int oy = (int)(t % Ho); const int64_t b = t / Ho;
+    const int c = k8 >> 1, ky0 = (k8 & 1) * 2;
+    float v[8];
+    IO<TI>::load8(dcols + m * ld + k8 * 8, v);
+    float* p = dx + ((b * 3 + c) * H + (oy * 4 + ky0)) * (int64_t)W + ox * 4;
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + W) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+extern "C" int mtus_patch_embed_col2im(const void* dcols, int ld, float* dx, int B, int H, int W, int dtype, void* stream) {
+  MTUS_CHECK_ARG(dcols && dx && B >= 0 && H % 4 == 0 && W % 4 == 0 && ld >= 48 && ld % 8 == 0);
+  if (B == 0) return MTUS_OK;
+  const int64_t total = (int64_t)B * (H / 4) * (W / 4) * 6;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = grid_for(total, 256);
+  if (dtype == MTUS_F32) patch_col2im_kernel<float><<<g, 256, 0, st>>>((const float*)dcols, ld, dx, B, H, W);
+  else if (dtype == MTUS_BF16) patch_col2im_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)dcols, ld, dx, B, H, W);
+  else return MTUS_ERR_UNSUPPORTED;
+  MTUS_LAUNCH_STATUS();
+  return MTUS_OK;
+}
+
 // ---- input pipeline fused into PatchEmbed's im2col: uint8 HWC image -> normalise -> GEMM operand ----------
 // Replaces albumentations Normalize(mean, std, max_pixel_value=255) + ToTensorV2 on the host and the fp32 NCHW batch the
 // reference copies to the device (/root/reference/code/train.py:35-44, 305): the device receives the raw uint8 [B,H,W,3]

@@ -506,6 +506,24 @@ extern "C" void mtus_graph_cache_stats(int64_t* hits, int64_t* misses, int64_t* 
   if (entries) *entries = (int64_t)g_graphs.size();
 }
 
+// Gradient w.r.t. the input image, for a trainable module in FRONT of the encoder (the reference's input-level TaskPrompt2D,
+// code/models/task_prompt.py:132-143, applied at code/models/multitask_model.py:198-199).  Valid right after a backward that
+// ran down to block 0 on the same workspace: the patch-embed LayerNorm backward left d(loss)/d(conv output) in the dLN slot;
+// dcols = dLN x W_pe ([M0, C0] x [C0, 48]) goes into the (now free) im2col slot and is scattered back to [B,3,S,S] fp32.
+extern "C" int mtus_swin_input_grad(const mtus_swin_config* cfg, const float* params, const void* params_lp, void* workspace,
+                                    float* dx, void* stream) {
+  Plan p;
+  if (!build_plan(cfg, p)) return MTUS_ERR_BAD_ARG;
+  MTUS_CHECK_ARG(params && workspace && dx && p.training);
+  MTUS_CHECK_ARG(p.dtype == MTUS_F32 || params_lp);
+  if (p.B == 0) return MTUS_OK;
+  char* ws = reinterpret_cast<char*>(workspace);
+  const void* w = p.dtype == MTUS_BF16 ? (const void*)(reinterpret_cast<const bf16*>(params_lp) + p.pe_w) : (const void*)(params + p.pe_w);
+  RUN(mtus_linear_dgrad(ws + p.dLN, w, ws + p.cols, nullptr, nullptr, 0, nullptr, p.M[0], p.C0, 48, p.dtype, p.backend, stream));
+  RUN(mtus_patch_embed_col2im(ws + p.cols, 48, dx, p.B, p.S, p.S, p.dtype, stream));
+  return MTUS_OK;
+}
+
 static int swin_backward_impl(const mtus_swin_config* cfg, const float* params, const void* params_lp,
                               const float* droppath, void* workspace, const void* const* dfeats, int dfeats_layout,
                               int dfeats_f32, float* grads, int block_hi, int block_lo, void* stream) {

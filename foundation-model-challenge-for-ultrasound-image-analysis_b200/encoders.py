@@ -63,7 +63,8 @@ class _FeatureInfo:
 class _SwinFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, core, x, *params):
-        needs_grad = any(ctx.needs_input_grad[2:])
+        # a trainable module in front of the encoder (TaskPrompt2D) needs the backward plan even with a frozen encoder
+        needs_grad = any(ctx.needs_input_grad[1:])
         if not x.is_cuda:
             raise RuntimeError("mtus_b200: the Swin encoder runs only on CUDA (sm_100a); there is no CPU fallback")
         with _lib.device_guard(x):
@@ -78,9 +79,9 @@ class _SwinFn(torch.autograd.Function):
     def backward(ctx, *dfeats):
         core = ctx.core
         with _lib.device_guard(core._flat):          # autograd's backward thread may sit on another device
-            flat_grad = core._run_backward(ctx.saved, dfeats)
+            flat_grad, dx = core._run_backward(ctx.saved, dfeats, want_input_grad=ctx.needs_input_grad[1])
         ctx.saved = None
-        return (None, None) + tuple(core.grad_views(flat_grad, ctx.param_needs))
+        return (None, dx) + tuple(core.grad_views(flat_grad, ctx.param_needs))
 
 
 class SwinCore(FlatParamModule):
@@ -235,7 +236,7 @@ class SwinCore(FlatParamModule):
         saved = (cfg, ws, lp, dp, flat, out_f32) if training_plan else None
         return feats, saved
 
-    def _run_backward(self, saved, dfeats):
+    def _run_backward(self, saved, dfeats, want_input_grad=False):
         cfg, ws, lp, dp, flat, out_f32 = saved
         L = _lib.lib()
         dt, tdt = precision_to_dtype(self.precision)
@@ -257,8 +258,13 @@ class SwinCore(FlatParamModule):
             if hook is not None:
                 hook(flat_grad, s_lo, s_hi)
         self._last_flat_grad = flat_grad
+        dx = None
+        if want_input_grad:       # d(loss)/d(image) for the module in front of the encoder (mtus_swin_input_grad)
+            dx = torch.empty(cfg.batch, 3, self.img_size, self.img_size, dtype=torch.float32, device=flat.device)
+            _lib.check(L.mtus_swin_input_grad(C.byref(cfg), _lib.ptr(flat), _lib.ptr(lp), _lib.ptr(ws), _lib.ptr(dx),
+                                              _lib.stream_ptr()), "swin_input_grad")
         self._return_workspace(cfg.batch, ws)
-        return flat_grad
+        return flat_grad, dx
 
     def _backward_chunks(self, blocks_per_chunk: int = 0):
         """[(block_hi, block_lo, grad_lo, grad_hi)] in backward order: runs of ``blocks_per_chunk`` blocks that never

@@ -6,8 +6,9 @@ unknown id (:187-188), ``use_fpn_for_{cls,reg}`` (:45-46), decoder aliasing (:29
 ``get_trainable_parameters`` (:282), ``freeze_encoder/unfreeze_encoder`` (:333-343),
 ``get_moe_aux_loss/get_moe_stats`` (:310-331), attribute names (``encoder``, ``fpn_decoder_{seg,det,cls,reg}``,
 ``heads``) and therefore the checkpoint keys.  FiLM on the decoder output (``model.use_film``, :52-79, 214-216) is provided with the
-modulation fused into the decoder's merge kernel.  Not provided (outside the hot path, SURVEY §2 rows
-9-10): TaskPrompt2D, MoE -- requesting them raises.
+modulation fused into the decoder's merge kernel; the input-level TaskPrompt2D (``model.task_prompt``, :81-111,
+194-199) is a small PyTorch module in front of the encoder whose gradient the encoder returns (``mtus_swin_input_grad``, §8f N4).
+Not provided (outside the hot path): MoE -- requesting it raises.
 """
 
 import torch
@@ -23,9 +24,8 @@ class MultiTaskModel(nn.Module):
         super().__init__()
         self.config = config
         self.task_configs = config.get_task_configs()
-        for key in ("model.task_prompt.enabled", "model.moe.enabled"):
-            if config.get(key, False):
-                raise NotImplementedError(f"mtus_b200: {key} is outside the hot path and not provided")
+        if config.get("model.moe.enabled", False):
+            raise NotImplementedError("mtus_b200: model.moe.enabled is outside the hot path and not provided")
         task_ids = [c["task_id"] for c in self.task_configs]
         self.encoder = build_encoder(config, task_ids=task_ids, precision=precision, zero_copy_features=zero_copy_features)
         self.precision = self.encoder.model.precision
@@ -44,7 +44,22 @@ class MultiTaskModel(nn.Module):
         if self.use_film:
             from .film import build_film
             self.film_generator, self.film_layer = build_film(config, task_ids, self.fpn_out_channels)
-        self.use_task_prompt = False
+        # input-level task prompt (multitask_model.py:81-111): a small PyTorch module in front of the encoder; its gradient
+        # comes out of the encoder through mtus_swin_input_grad
+        tp_cfg = config.get("model.task_prompt", {}) or {}
+        self.use_task_prompt = bool(tp_cfg.get("enabled", False))
+        names = tp_cfg.get("apply_to_task_names", None)
+        self.task_prompt_apply_task_names = None if names is None else {str(n).lower() for n in names}
+        if self.use_task_prompt:
+            if hasattr(config, "tasks_from_dataset") and not config.tasks_from_dataset():
+                raise ValueError("TaskPrompt2D requires dataset-derived task configs. "
+                                 "Load dataset metadata and override config tasks before building the model.")
+            from .task_prompt import TaskPrompt2D
+            self.task_prompt = TaskPrompt2D(self.task_configs, out_channels=int(tp_cfg.get("channels", 1)),
+                                            prompt_size=int(tp_cfg.get("prompt_size", 32)),
+                                            inject_mode=str(tp_cfg.get("inject_mode", "add")).lower(),
+                                            init_scale=float(tp_cfg.get("init_scale", 0.1)),
+                                            use_tanh=bool(tp_cfg.get("use_tanh", True)))
         self.use_moe = False
         self.heads = build_all_heads(self.task_configs, self.fpn_out_channels, encoder_channels,
                                      config.config.get("model", {}) if hasattr(config, "config") else {})
@@ -63,6 +78,12 @@ class MultiTaskModel(nn.Module):
         if task_id not in self.heads:
             raise ValueError(f"Unknown task_id: {task_id}")
         task_name = self.task_id_to_name[task_id]
+        if self.use_task_prompt and (self.task_prompt_apply_task_names is None
+                                     or task_name.lower() in self.task_prompt_apply_task_names):
+            if x.dtype == torch.uint8:
+                raise TypeError("mtus_b200: TaskPrompt2D modulates the NORMALISED image; pass the float [B,3,H,W] batch, not "
+                                "the raw uint8 one")
+            x = self.task_prompt.apply(x, task_id)
         features = self.encoder(x, task_id) if getattr(self.encoder, "supports_task_id", False) else self.encoder(x)
         film = self.film_generator(task_id) if self.use_film else None
         if task_name == "segmentation":
@@ -88,6 +109,8 @@ class MultiTaskModel(nn.Module):
                                                                  self.fpn_decoder_cls):
             head_params += list(self.fpn_decoder_reg.parameters())
         head_params += list(self.heads.parameters())
+        if self.use_task_prompt:
+            head_params += list(self.task_prompt.parameters())
         # as in the reference (multitask_model.py:282-308) the FiLM generator's parameters are in NEITHER group: with
         # grouped learning rates (train.py:184-190) they keep their initial values; model.parameters() still lists them
         return encoder_params, head_params

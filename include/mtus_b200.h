@@ -289,6 +289,9 @@ int mtus_swin_forward(const mtus_swin_config* cfg, const void* x, int x_is_f32, 
  * HOST arrays (Normalize(mean, std, max_pixel_value=255)); cols = the [B*(H/4)*(W/4), 64] im2col operand. */
 int mtus_patch_embed_im2col_u8(const void* x_u8, const float* mean3, const float* std3, void* cols, int B, int H, int W,
                                int dtype, void* stream);
+/* Inverse of mtus_patch_embed_im2col for gradients: dcols [B*(H/4)*(W/4), ld] (dtype; 48 valid columns, ld % 8 == 0) is
+ * scattered to dx [B,3,H,W] fp32 NCHW; every pixel is written exactly once (no zero-fill needed). */
+int mtus_patch_embed_col2im(const void* dcols, int ld, float* dx, int B, int H, int W, int dtype, void* stream);
 /* mtus_swin_forward fed by the uint8 HWC batch (everything else identical). */
 int mtus_swin_forward_u8(const mtus_swin_config* cfg, const void* x_u8, const float* mean3, const float* std3,
                          const float* params, const void* params_lp, const float* droppath, void* workspace,
@@ -302,6 +305,12 @@ int mtus_swin_forward_u8(const mtus_swin_config* cfg, const void* x_u8, const fl
 int mtus_swin_backward(const mtus_swin_config* cfg, const float* params, const void* params_lp,
                        const float* droppath, void* workspace, const void* const* dfeats, int dfeats_layout,
                        int dfeats_f32, float* grads, int stage_hi, int stage_lo, void* stream);
+/* Gradient w.r.t. the input image: dx [B,3,S,S] fp32 NCHW.  For a trainable module in front of the encoder (the reference's
+ * input-level TaskPrompt2D, code/models/task_prompt.py:132-143, applied at code/models/multitask_model.py:198-199; timm's
+ * trunk gives it through autograd).  Call right after a backward that ran down to block 0 on the same workspace (it reads the
+ * patch-embed gradient that backward left there and overwrites the im2col slot). */
+int mtus_swin_input_grad(const mtus_swin_config* cfg, const float* params, const void* params_lp, void* workspace,
+                         float* dx, void* stream);
 /* Same, at block granularity: global block indices count the blocks of all stages in forward order
  * (Swin-B: 0..23); runs blocks block_hi-1 down to block_lo, plus the PatchMerging / patch-embed backward of every
  * stage whose first block is in the range.  Lets the data-parallel wrapper all-reduce finished slices of the flat

@@ -131,8 +131,46 @@ def build_head(task_cfg, fpn_out, enc_channels, cfg):
     raise ValueError(f"Unknown task type: {name}")
 
 
+class OracleTaskPrompt(nn.Module):
+    """task_prompt.py:28-143, literally: one multi-hot row per task ([task types | num_classes_<n> tags | id tokens without the
+    "T<k>" prefix], every vocabulary sorted), expanded to B rows -> Linear -> [B, channels, p, p] -> tanh -> bilinear
+    (align_corners=False) to the image size -> x + s * prompt ("add") or x * (1 + s * prompt) ("mul")."""
+
+    def __init__(self, task_configs, channels, prompt_size, mode, init_scale, use_tanh):
+        super().__init__()
+        import re
+        drop = re.compile(r"^t\d+[a-z]?$", re.IGNORECASE)
+        ids = [str(t["task_id"]) for t in task_configs]
+        kinds = [str(t.get("task_name", "unknown")).lower() for t in task_configs]
+        tags = [f"num_classes_{int(t.get('num_classes', -1))}" for t in task_configs]
+        toks = [[w for w in (q.strip().lower() for q in i.split("_")) if w and not drop.match(w)] for i in ids]
+        vk, vt, vw = sorted(set(kinds)), sorted(set(tags)), sorted(set(sum(toks, [])))
+        meta = torch.zeros(len(ids), len(vk) + len(vt) + len(vw))
+        for r in range(len(ids)):
+            meta[r, vk.index(kinds[r])] = 1.0
+            meta[r, len(vk) + vt.index(tags[r])] = 1.0
+            for w in toks[r]:
+                meta[r, len(vk) + len(vt) + vw.index(w)] = 1.0
+        self.rows = {t: r for r, t in enumerate(ids)}
+        self.channels, self.p, self.mode, self.use_tanh = channels, prompt_size, mode, use_tanh
+        self.register_buffer("task_metadata", meta)
+        self.prompt_proj = nn.Linear(meta.shape[1], channels * prompt_size * prompt_size)
+        self.prompt_scale = nn.Parameter(torch.tensor(float(init_scale)))
+
+    def inject(self, x, task_id):
+        B = x.shape[0]
+        vec = self.task_metadata[self.rows[task_id]].to(x.device).unsqueeze(0).expand(B, -1)
+        pr = self.prompt_proj(vec).view(B, self.channels, self.p, self.p)
+        if self.use_tanh:
+            pr = torch.tanh(pr)
+        if pr.shape[-2:] != x.shape[-2:]:
+            pr = F.interpolate(pr, size=x.shape[-2:], mode="bilinear", align_corners=False)
+        s, pr = self.prompt_scale.to(x.dtype), pr.to(x.dtype)
+        return x + s * pr if self.mode == "add" else x * (1.0 + s * pr)
+
+
 class OracleMultiTaskModel(nn.Module):
-    """multitask_model.py:13-250 for the swin_b.yaml family of configs (no FiLM / MoE / TaskPrompt)."""
+    """multitask_model.py:13-250 for the swin_b.yaml family of configs (FiLM and TaskPrompt2D optional; no MoE)."""
 
     def __init__(self, cfg, drop_path_rate=0.1):
         super().__init__()
@@ -177,6 +215,15 @@ class OracleMultiTaskModel(nn.Module):
                 if self.film_affine:
                     gen.task_betas = nn.ParameterDict({t: nn.Parameter(torch.zeros(C)) for t in ids})
             self.film_generator = gen
+        # input-level task prompt (multitask_model.py:81-111; task_prompt.py): built before the heads, like the reference
+        tp = cfg.get("model.task_prompt", {}) or {}
+        self.use_task_prompt = bool(tp.get("enabled", False))
+        names = tp.get("apply_to_task_names", None)
+        self.task_prompt_apply_task_names = None if names is None else {str(n).lower() for n in names}
+        if self.use_task_prompt:
+            self.task_prompt = OracleTaskPrompt(self.task_configs, int(tp.get("channels", 1)), int(tp.get("prompt_size", 32)),
+                                                str(tp.get("inject_mode", "add")).lower(), float(tp.get("init_scale", 0.1)),
+                                                bool(tp.get("use_tanh", True)))
         self.heads = nn.ModuleDict({t["task_id"]: build_head(t, self.fpn_out_channels, ch, cfg)
                                     for t in self.task_configs})
         self.task_id_to_name = {t["task_id"]: t["task_name"] for t in self.task_configs}
@@ -197,6 +244,9 @@ class OracleMultiTaskModel(nn.Module):
         if task_id not in self.heads:
             raise ValueError(f"Unknown task_id: {task_id}")
         name = self.task_id_to_name[task_id]
+        if self.use_task_prompt and (self.task_prompt_apply_task_names is None
+                                     or name.lower() in self.task_prompt_apply_task_names):   # multitask_model.py:194-199
+            x = self.task_prompt.inject(x, task_id)
         feats = self.encoder(x)
         if name == "segmentation":
             return self.heads[task_id](self._film(self.fpn_decoder_seg(feats), task_id))

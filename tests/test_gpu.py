@@ -633,6 +633,69 @@ def test_film_epilogue_fused_into_the_merge_kernel_matches_the_oracle(precision,
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_task_prompt_and_image_gradient_match_the_oracle(precision, tol):
+    """SURVEY 8f N4 (optional part): model.task_prompt (multitask_model.py:81-111, 194-199; task_prompt.py:132-143) in front of
+    the native encoder.  The prompt's parameters are trained through d(loss)/d(image), which the encoder returns
+    (mtus_swin_input_grad = patch-embed data gradient + col2im): outputs, EVERY parameter gradient (task_prompt.* included) and
+    the image gradient itself against the oracle, "add" with a 1-channel prompt on all task types and "mul" with a 3-channel
+    prompt restricted to segmentation; a frozen encoder must still hand the gradient through."""
+    import mtus_b200 as m
+    from oracle.model import OracleMultiTaskModel
+    ids = ("T2C_fetal_head", "T4A_fetal_femur", "T3A_breast_tumor", "T1_fetal_planes")
+    tasks = [t for t in m.tasks_27() if t["task_id"] in ids]
+    for mode, channels, names in (("add", 1, None), ("mul", 3, ["segmentation"])):
+        cfg = m.make_config("swin_micro_patch4_window7_test", 128, 2, tasks=tasks, dropout=0.0, mixed_precision=(precision == "bf16"))
+        cfg.set_task_configs_from_dataset(tasks)
+        cfg.config["model"]["task_prompt"] = {"enabled": True, "channels": channels, "prompt_size": 16, "inject_mode": mode,
+                                              "init_scale": 0.1, "use_tanh": True, "apply_to_task_names": names}
+        torch.manual_seed(0)
+        oracle = OracleMultiTaskModel(cfg, drop_path_rate=0.0).cuda().eval()
+        with torch.no_grad():
+            oracle.task_prompt.prompt_scale.fill_(0.6)       # a visible modulation (0.1 at init)
+        model = m.build_model(cfg, precision=precision).cuda().eval()
+        model.load_state_dict(oracle.state_dict())
+        x0 = torch.randn(2, 3, 128, 128, generator=torch.Generator().manual_seed(2)).cuda()
+        for t in tasks:
+            tid = t["task_id"]
+            oracle.zero_grad(set_to_none=True)
+            model.zero_grad(set_to_none=True)
+            xo, xm = x0.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+            yo, ym = oracle(xo, tid), model(xm, tid)
+            _elementwise(f"task_prompt({mode}) {precision} output[{tid}]", ym.detach(), yo.detach(), tol)
+            yo.square().mean().backward()
+            ym.float().square().mean().backward()
+            via_fpn = t["task_name"] in gpu_diag.FPN_TASK_TYPES
+            floor = 0.999 if (precision == "fp32" or not via_fpn) else 0.985      # see the FiLM test: ReLU gate flips in bf16
+            assert gpu_diag._compare_grads(f"task_prompt({mode}) {precision} grads[{tid}]", model, oracle, floor)
+            applies = names is None or t["task_name"].lower() in names
+            gs = [p.grad for p in model.task_prompt.parameters()]
+            assert all((g is not None and g.abs().sum() > 0) == applies for g in gs), (tid, applies)
+            assert xm.grad is not None and xm.grad.shape == x0.shape
+            c = torch.nn.functional.cosine_similarity(xm.grad.flatten().float(), xo.grad.flatten(), dim=0).item()
+            rn = (xm.grad.float().norm() / xo.grad.norm()).item()
+            print(f"  image gradient[{tid}] cosine {c:.6f} norm ratio {rn:.4f}", flush=True)
+            assert c >= floor and 0.9 < rn < 1.1, (tid, c, rn)
+            if precision == "fp32":
+                # relative L2 of the whole map: 5e-3 is the error a cosine of 0.9999875 allows, 80x tighter than the 0.999 bar
+                # (measured 2.5e-4 through the FPN, where the fp32 parameter gradients themselves sit at cosine 0.999998)
+                rl2 = ((xm.grad - xo.grad).norm() / xo.grad.norm()).item()
+                print(f"  image gradient[{tid}] fp32 rel-L2 {rl2:.3e}", flush=True)
+                assert rl2 <= 5e-3, (tid, rl2)
+        # frozen encoder (model.encoder.freeze_encoder): no parameter gradient inside the encoder, the prompt still trains
+        model.freeze_encoder()
+        model.zero_grad(set_to_none=True)
+        oracle.zero_grad(set_to_none=True)
+        tid = "T2C_fetal_head"
+        model(x0, tid).float().square().mean().backward()
+        oracle(x0, tid).square().mean().backward()
+        assert all(p.grad is None for p in model.encoder.parameters())
+        for (k, pm), (_, po) in zip(model.task_prompt.named_parameters(), oracle.task_prompt.named_parameters()):
+            c = torch.nn.functional.cosine_similarity(pm.grad.flatten().float(), po.grad.flatten(), dim=0).item()
+            assert c >= (0.999 if precision == "fp32" else 0.985), (k, c)
+        model.unfreeze_encoder()
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
 def test_uint8_input_pipeline_fused_into_patch_embed(precision, tol):
     """forward(uint8 [B,H,W,3]) == forward(Normalize(mean, std)(img) as fp32 NCHW) (code/train.py:35-44) --
     features vs the oracle fed the host-normalised batch, and the patch-embed gradients of both input forms agree."""

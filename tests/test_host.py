@@ -302,3 +302,30 @@ def test_bench_arms_print_the_same_config_and_non_zero_ranks_of_the_reference_ar
     monkeypatch.setenv("RANK", "1")
     monkeypatch.setenv("WORLD_SIZE", "2")
     assert bench.run_reference(argparse.Namespace(gpus=2, steps=1, warmup=0)) == 0      # returns before building anything
+
+
+def test_task_prompt_wiring_without_a_gpu():
+    """model.task_prompt (multitask_model.py:81-111): requires dataset-derived task configs, registers task_prompt.* with
+    the reference's names, joins the head parameter group (:305-306), refuses the raw uint8 batch, and keeps
+    nn.Module.apply(fn) working next to the reference's apply(x, task_id)."""
+    tasks = [t for t in m.tasks_27() if t["task_id"] in ("T2C_fetal_head", "T1_fetal_planes")]
+    cfg = m.make_config("swin_micro_patch4_window7_test", 64, 2, tasks=tasks, mixed_precision=False)
+    cfg.config["model"]["task_prompt"] = {"enabled": True, "channels": 1, "prompt_size": 8, "apply_to_task_names": ["Segmentation"]}
+    with pytest.raises(ValueError, match="dataset-derived"):
+        m.build_model(cfg, precision="fp32")
+    cfg.set_task_configs_from_dataset(tasks)
+    model = m.build_model(cfg, precision="fp32")
+    assert model.use_task_prompt and model.task_prompt_apply_task_names == {"segmentation"}
+    keys = [k for k in model.state_dict() if k.startswith("task_prompt.")]
+    assert keys == ["task_prompt.prompt_scale", "task_prompt.task_metadata", "task_prompt.prompt_proj.weight", "task_prompt.prompt_proj.bias"]
+    assert model.task_prompt.prompt_proj.weight.shape == (64, model.task_prompt.prompt_dim)
+    _, head = model.get_trainable_parameters()
+    assert all(any(p is q for q in head) for p in model.task_prompt.parameters())
+    with pytest.raises(TypeError, match="uint8"):
+        model(torch.zeros(2, 64, 64, 3, dtype=torch.uint8), "T2C_fetal_head")
+    seen = []
+    model.apply(lambda mod: seen.append(type(mod).__name__))
+    assert "TaskPrompt2D" in seen
+    x = torch.randn(2, 3, 64, 64)
+    y = model.task_prompt.apply(x, "T2C_fetal_head")
+    assert y.shape == x.shape and not torch.equal(y, x)

@@ -3,6 +3,7 @@ functional re-derivation, committed golden tensors (generated through the refere
 tests/golden/make_golden.py), structural invariants, and -- where /root/reference exists -- the
 reference's MultiTaskModel running on the shims."""
 import os
+import sys
 
 import pytest
 import torch
@@ -206,6 +207,70 @@ def test_film_reference_model_equals_oracle_and_native_key_layout(embedding):
     enc, head = native.get_trainable_parameters()
     ids = {id(p) for p in enc + head}
     assert not any(id(p) in ids for p in native.film_generator.parameters())     # as in the reference (:282-308)
+
+
+def _task_prompt_cfg(m, tasks, image, mode, channels, names=None, mixed=False):
+    cfg = m.make_config("swin_micro_patch4_window7_test", image, 2, tasks=tasks, dropout=0.0, mixed_precision=mixed)
+    cfg.set_task_configs_from_dataset(tasks)                 # the reference refuses TaskPrompt2D on YAML-only task lists
+    cfg.config["model"]["task_prompt"] = {"enabled": True, "channels": channels, "prompt_size": 8, "inject_mode": mode,
+                                          "init_scale": 0.1, "use_tanh": True, "apply_to_task_names": names}
+    return cfg
+
+
+@pytest.mark.skipif(not HAS_REFERENCE, reason="needs /root/reference (authoring container)")
+@pytest.mark.parametrize("mode,channels,names", [("add", 1, None), ("mul", 3, ["segmentation"])])
+def test_task_prompt_reference_model_equals_oracle_and_native_key_layout(mode, channels, names):
+    """model.task_prompt (multitask_model.py:81-111, 194-199; task_prompt.py): the reference's own MultiTaskModel +
+    TaskPrompt2D on the shims == the oracle's restatement bit for bit (forward and the prompt's gradients), the product's
+    TaskPrompt2D == the reference's class, and the native model has the same task_prompt.* keys and parameter groups."""
+    import mtus_b200 as m
+    from mtus_b200.task_prompt import TaskPrompt2D, build_task_prompt_metadata
+    from oracle import shims
+    from oracle.model import OracleMultiTaskModel
+    models, _, _ = shims.import_reference_models("/root/reference")
+    tasks = [t for t in m.tasks_27() if t["task_id"] in ("T2C_fetal_head", "T3A_breast_tumor", "T4A_fetal_femur")]
+    cfg = _task_prompt_cfg(m, tasks, 64, mode, channels, names)
+    torch.manual_seed(0)
+    oracle = OracleMultiTaskModel(cfg, drop_path_rate=0.0).eval()
+    with torch.no_grad():
+        oracle.task_prompt.prompt_scale.fill_(0.7)
+    ref = models.build_model(cfg).eval()
+    ref.load_state_dict(oracle.state_dict(), strict=True)
+    assert list(ref.state_dict().keys()) == list(oracle.state_dict().keys())
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(3))
+    for t in tasks:
+        ref.zero_grad(set_to_none=True)
+        oracle.zero_grad(set_to_none=True)
+        yr, yo = ref(x, t["task_id"]), oracle(x, t["task_id"])
+        assert torch.equal(yr, yo), t["task_id"]
+        yr.square().mean().backward()
+        yo.square().mean().backward()
+        applies = names is None or t["task_name"].lower() in names
+        for (k, pr), (_, po) in zip(ref.task_prompt.named_parameters(), oracle.task_prompt.named_parameters()):
+            assert (pr.grad is not None) == applies, (k, t["task_id"])
+            if applies:
+                assert torch.equal(pr.grad, po.grad), k
+    # the product's module against the reference's class (same seed -> same parameters -> same map, 1 ulp of the Linear)
+    ref_tp = models.TaskPrompt2D
+    meta_ref = sys.modules[ref_tp.__module__].build_task_prompt_metadata(m.tasks_27())
+    meta = build_task_prompt_metadata(m.tasks_27())
+    assert torch.equal(meta[0], meta_ref[0]) and meta[1] == meta_ref[1] and meta[2] == meta_ref[2]
+    torch.manual_seed(1)
+    a = TaskPrompt2D(m.tasks_27(), channels, 8, mode, 0.3, True)
+    torch.manual_seed(1)
+    b = ref_tp(m.tasks_27(), channels, 8, mode, 0.3, True)
+    assert all(torch.equal(a.state_dict()[k], v) for k, v in b.state_dict().items())
+    for tid in ("T1_fetal_planes", "T2A_fetal_abdomen"):
+        torch.testing.assert_close(a.apply(x, tid), b.apply(x, tid), rtol=1e-6, atol=1e-6)
+    with pytest.raises(ValueError):
+        a.apply(x, "no_such_task")
+    native = m.build_model(cfg, precision="fp32")
+    assert list(native.state_dict().keys()) == list(oracle.state_dict().keys())
+    native.load_state_dict(oracle.state_dict(), strict=True)
+    enc, head = native.get_trainable_parameters()
+    enc_r, head_r = ref.get_trainable_parameters()
+    assert len(enc) == len(enc_r) and len(head) == len(head_r)
+    assert all(any(p is q for q in head) for p in native.task_prompt.parameters())          # multitask_model.py:305-306
 
 
 # ---- second independent pin of the Swin restatement: Hugging Face transformers (SURVEY App. B) -------------------
