@@ -102,16 +102,16 @@ def test_routing_and_errors_without_a_gpu():
     assert not any(p.requires_grad for p in model.encoder.parameters())
     model.unfreeze_encoder()
     assert all(p.requires_grad for p in model.encoder.parameters())
-    # FiLM is provided (fused into the merge kernel); TaskPrompt / MoE are outside the hot path and must fail loudly
+    # FiLM is provided (fused into the merge kernel) and so is TaskPrompt2D (test_task_prompt_wiring_without_a_gpu); MoE is
+    # outside the hot path and must fail loudly
     c2 = _cfg()
     c2.config["model"]["use_film"] = True
     film_model = m.build_model(c2, precision="fp32")
     assert any(k.startswith("film_generator.task_gammas.") for k in film_model.state_dict())
-    for key in ("task_prompt", "moe"):
-        c3 = _cfg()
-        c3.config["model"][key] = {"enabled": True}
-        with pytest.raises(NotImplementedError):
-            m.build_model(c3)
+    c3 = _cfg()
+    c3.config["model"]["moe"] = {"enabled": True}
+    with pytest.raises(NotImplementedError):
+        m.build_model(c3)
 
 
 def test_sampler_is_task_synchronous_and_partitions_the_global_batch():
