@@ -21,7 +21,7 @@ from .losses import build_all_losses, compute_task_loss
 from .multitask_model import MultiTaskModel, build_model, build_optimizer, build_flat_optimizer
 from .optim import FlatAdamW
 from .checkpoint import load_pretrained, load_checkpoint, convert_swin_state_dict, resize_rel_pos_bias_table
-from .parallel import DistributedTaskSampler, GradAllReducer, DataParallelTrainer, DevicePrefetcher, synthetic_batch
+from .parallel import DistributedTaskSampler, DistributedEvalBatchSampler, gather_task_metrics, GradAllReducer, DataParallelTrainer, DevicePrefetcher, synthetic_batch
 
 __all__ = [
     "build_encoder", "SwinTransformerEncoder", "SwinCore", "SWIN_MODEL_MAPPING", "SWIN_ARCHS",
@@ -29,5 +29,5 @@ __all__ = [
     "build_all_losses", "compute_task_loss", "MultiTaskModel", "build_model", "build_optimizer", "build_flat_optimizer", "FlatAdamW",
     "load_pretrained", "load_checkpoint", "convert_swin_state_dict", "resize_rel_pos_bias_table",
     "Config", "make_config", "swin_b_27task", "tasks_27",
-    "DistributedTaskSampler", "GradAllReducer", "DataParallelTrainer", "DevicePrefetcher", "synthetic_batch",
+    "DistributedTaskSampler", "DistributedEvalBatchSampler", "gather_task_metrics", "GradAllReducer", "DataParallelTrainer", "DevicePrefetcher", "synthetic_batch",
 ]

@@ -13,6 +13,8 @@ preserving the single-process step semantics of ``/root/reference/code/train.py:
   grad is ``None`` (the 26 idle heads, idle decoders) are left untouched so AdamW keeps skipping them
   (train.py:440,455 semantics).
 * ``DataParallelTrainer`` -- zero_grad -> forward -> loss -> backward -> all-reduce -> clip -> step.
+* ``DistributedEvalBatchSampler`` + ``gather_task_metrics`` -- the validation split of ``evaluate()``: batches strided over
+  ranks, per-batch metric values gathered to rank 0 in single-process order.
 """
 
 import random
@@ -70,6 +72,67 @@ class DistributedTaskSampler(torch.utils.data.Sampler):
 
     def __len__(self) -> int:
         return self.steps_per_epoch
+
+
+class DistributedEvalBatchSampler(torch.utils.data.Sampler):
+    """Validation split for ``evaluate()`` (code/metrics/__init__.py:72-184) under data parallelism.
+
+    The reference's ``val_loader`` is a plain ``shuffle=False`` loader (code/train.py:164-171) and every metric is the mean of
+    PER-BATCH values (metrics/__init__.py:176-182), so the split is strided over BATCHES, not samples: global batch ``g`` =
+    indices ``[g * B, (g + 1) * B)`` goes to rank ``g % world``.  No padding and no repeated samples -- the union of the ranks'
+    batches is exactly the single-process batch list, and ``gather_task_metrics`` puts the per-batch values back in that order,
+    so rank 0 reports the numbers a single process would.  Use as ``DataLoader(val_dataset, batch_sampler=...)``."""
+
+    def __init__(self, dataset_len: int, batch_size: int, rank: int = 0, world_size: int = 1):
+        self.n, self.batch_size, self.rank, self.world_size = int(dataset_len), int(batch_size), int(rank), int(world_size)
+        if not (0 <= self.rank < self.world_size) or self.batch_size <= 0:
+            raise ValueError("rank must be in [0, world_size) and batch_size positive")
+        self.num_global_batches = (self.n + self.batch_size - 1) // self.batch_size
+
+    def global_batch_ids(self) -> List[int]:
+        return list(range(self.rank, self.num_global_batches, self.world_size))
+
+    def __iter__(self) -> Iterator[List[int]]:
+        for g in self.global_batch_ids():
+            yield list(range(g * self.batch_size, min((g + 1) * self.batch_size, self.n)))
+
+    def __len__(self) -> int:
+        return len(self.global_batch_ids())
+
+
+def gather_task_metrics(task_metrics: Dict[str, Dict[str, list]], batch_ids: Sequence[Sequence[int]], group=None, dst: int = 0):
+    """Merge the per-rank ``task_metrics[task_id][metric] -> [value per batch]`` dictionaries of ``evaluate()`` on rank ``dst``.
+
+    ``batch_ids[task_id]`` (or one list for all tasks) holds, for each appended value, the GLOBAL index of the batch it came from
+    (``DistributedEvalBatchSampler.global_batch_ids()``; a task absent from a batch appends nothing).  Returns, on ``dst``, the
+    merged dictionary with every list ordered by global batch index -- element for element the list a single process builds --
+    and ``None`` on the other ranks.  Host-side Python objects over the group's object collective (gloo or NCCL)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    per_task_ids = batch_ids if isinstance(batch_ids, dict) else {t: list(batch_ids) for t in task_metrics}
+    local = {t: {"ids": list(per_task_ids[t]), "metrics": {k: list(v) for k, v in mm.items()}} for t, mm in task_metrics.items()}
+    for t, e in local.items():
+        for k, v in e["metrics"].items():
+            if len(v) != len(e["ids"]):
+                raise ValueError(f"gather_task_metrics: {t}/{k} has {len(v)} values for {len(e['ids'])} batch ids")
+    if world == 1:
+        parts = [local]
+    else:
+        parts = [None] * world if rank == dst else None
+        dist.gather_object(local, parts, dst=dst, group=group)
+        if rank != dst:
+            return None
+    merged: Dict[str, Dict[str, list]] = {}
+    for t in sorted({t for part in parts for t in part}):
+        names = []
+        for part in parts:
+            names += [k for k in part.get(t, {"metrics": {}})["metrics"] if k not in names]
+        merged[t] = {}
+        for k in names:
+            rows = [(g, v) for part in parts if t in part and k in part[t]["metrics"]
+                    for g, v in zip(part[t]["ids"], part[t]["metrics"][k])]
+            merged[t][k] = [v for _, v in sorted(rows, key=lambda r: r[0])]
+    return merged
 
 
 class GradAllReducer:

@@ -147,3 +147,57 @@ def test_world_size_2_gloo():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+# ---- validation split (evaluate(), code/metrics/__init__.py:72-184): batches strided over ranks, metrics gathered ----------
+def _fake_evaluate(task_of_sample, batches, batch_ids):
+    """The bookkeeping of the reference's evaluate(): per batch, group samples by task id and append ONE value per
+    (task, metric) -- here a deterministic function of the sample indices, so any reordering or loss shows."""
+    metrics, ids = {}, {}
+    for g, batch in zip(batch_ids, batches):
+        for tid in sorted({task_of_sample[i] for i in batch}):
+            mine = [i for i in batch if task_of_sample[i] == tid]
+            mm = metrics.setdefault(tid, {})
+            mm.setdefault("Score", []).append(sum((i * 37) % 11 for i in mine) / len(mine))
+            if tid == "cls":
+                mm.setdefault("F1-Score", []).append(float(len(mine)))
+            ids.setdefault(tid, []).append(g)
+    return metrics, ids
+
+
+def _eval_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import mtus_b200 as m
+    n, B = 53, 4                                          # ragged: 14 batches, the last one short; rank 1 gets no "rare" sample
+    task_of_sample = ["seg" if i % 3 else "cls" for i in range(n)]
+    task_of_sample[8] = "rare"
+    single = m.DistributedEvalBatchSampler(n, B, 0, 1)
+    want, _ = _fake_evaluate(task_of_sample, list(single), single.global_batch_ids())
+    sampler = m.DistributedEvalBatchSampler(n, B, rank, world)
+    got, ids = _fake_evaluate(task_of_sample, list(sampler), sampler.global_batch_ids())
+    merged = m.gather_task_metrics(got, ids)
+    ok = (merged == want) if rank == 0 else (merged is None)
+    covered = [None] * world
+    dist.all_gather_object(covered, [i for b in sampler for i in b])
+    ok &= sorted(sum(covered, [])) == list(range(n))       # every sample exactly once, no padding
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_validation_split_reproduces_the_single_process_metric_lists():
+    import pytest
+    import mtus_b200 as m
+    s = m.DistributedEvalBatchSampler(10, 4, 0, 1)
+    assert list(s) == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]] and len(s) == 3
+    assert [len(m.DistributedEvalBatchSampler(10, 4, r, 2)) for r in (0, 1)] == [2, 1]
+    assert list(m.DistributedEvalBatchSampler(0, 4, 0, 2)) == []
+    with pytest.raises(ValueError):
+        m.DistributedEvalBatchSampler(10, 4, 2, 2)
+    with pytest.raises(ValueError):
+        m.gather_task_metrics({"a": {"Dice": [0.5, 0.6]}}, [0])          # one value per batch id
+    assert m.gather_task_metrics({"a": {"Dice": [0.5, 0.6]}}, [3, 1]) == {"a": {"Dice": [0.6, 0.5]}}    # world 1: sorted by batch
+    world = 2
+    out = mp.Manager().dict()
+    mp.spawn(_eval_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
