@@ -346,6 +346,45 @@ def test_swin_oracle_matches_huggingface_transformers(img):
         assert torch.allclose(a, b, rtol=1e-4, atol=2e-5), float((a - b).abs().max())
 
 
+def test_swin_oracle_padded_windows_match_huggingface_on_unshifted_blocks():
+    """Window PADDING pinned where the two orderings coincide: without a cyclic shift, pad-then-roll (HF, torchvision) and
+    roll-then-pad (timm) are the same computation, so a model whose blocks are all unshifted (one block per stage) must agree
+    with HF on maps that are not multiples of the window -- 256 px -> 64 / 32 / 16 / 8, padded to 70 / 35 / 21 / 14 (zero rows
+    after the norm, so padded tokens carry the qkv bias and ARE attended).  What stays unpinned against
+    an independent implementation is only the order of roll and pad inside SHIFTED blocks of padded maps
+    (test_swin_roll_then_pad_order pins that against a hand-built case)."""
+    transformers = pytest.importorskip("transformers")
+    from transformers import SwinConfig, SwinModel
+    from oracle import swin
+    name = "swin_unshifted_1_1_1_1_test"
+    ed, depths, heads, win = swin.SWIN_VARIANTS.setdefault(name, (32, (1, 1, 1, 1), (1, 2, 4, 8), 7))
+    img = 256
+    torch.manual_seed(0)
+    o = swin.create_model(name, features_only=True, img_size=img, drop_path_rate=0.0).eval()
+    with torch.no_grad():
+        for p in o.parameters():
+            p.add_(torch.randn_like(p) * 0.05)          # non-zero qkv biases: the padded tokens' keys / values matter
+    cfg = SwinConfig(image_size=img, patch_size=4, num_channels=3, embed_dim=ed, depths=list(depths), num_heads=list(heads),
+                     window_size=win, mlp_ratio=4.0, qkv_bias=True, hidden_dropout_prob=0.0,
+                     attention_probs_dropout_prob=0.0, drop_path_rate=0.0, hidden_act="gelu",
+                     use_absolute_embeddings=False, layer_norm_eps=1e-5)
+    hf = SwinModel(cfg, add_pooling_layer=False).eval()
+    res = hf.load_state_dict(_hf_state_dict_from_oracle(o.state_dict(), depths), strict=False)
+    assert not res.unexpected_keys
+    assert not [k for k in res.missing_keys if "relative_position_index" not in k and not k.startswith("layernorm.")], res
+    x = torch.randn(2, 3, img, img, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        fo = o(x)
+        emb, dims = hf.embeddings(x)
+        enc = hf.encoder(emb, dims, output_hidden_states=True, output_hidden_states_before_downsampling=True, return_dict=True)
+    hs = enc.reshaped_hidden_states[1:]
+    assert [tuple(f.shape[1:3]) for f in fo] == [(64, 64), (32, 32), (16, 16), (8, 8)]
+    for a, b in zip(fo, hs):
+        b = b.permute(0, 2, 3, 1)
+        assert a.shape == b.shape
+        assert torch.allclose(a, b, rtol=1e-4, atol=2e-5), float((a - b).abs().max())
+
+
 # ---- FPN lateral + top-down pathway vs torchvision.ops.FeaturePyramidNetwork ------------------------------------
 def test_fpn_lateral_topdown_matches_torchvision_feature_pyramid_network():
     """smp's p5 = 1x1(c5), p_k = nearest_up(p_{k+1}) + 1x1(c_k) is torchvision's FPN inner pathway.  torchvision then
