@@ -38,6 +38,13 @@ def test_null_arguments_are_rejected_without_touching_the_gpu(lib):
     assert lib.mtus_layernorm_fwd(None, None, None, None, None, None, 4, 32, 1e-5, 0, None) == -1
     assert lib.mtus_window_attn_fwd(None, None, None, None, None, 1, 7, 7, 32, 1, 7, 7, 0, 0, 0, None) == -1
     assert lib.mtus_swin_forward(None, None, 1, None, None, None, None, None, 0, 0, None) == -1
+    assert lib.mtus_swin_input_grad(None, None, None, None, None, None) == -1
+    assert lib.mtus_patch_embed_col2im(None, 48, None, 1, 8, 8, 0, None) == -1
+    import ctypes as C
+    buf = (C.c_float * 4)()
+    assert lib.mtus_patch_embed_col2im(buf, 40, buf, 1, 8, 8, 0, None) == -1        # fewer than 48 columns
+    assert lib.mtus_patch_embed_col2im(buf, 48, buf, 1, 6, 8, 0, None) == -1        # height not a multiple of the patch
+    assert lib.mtus_patch_embed_col2im(buf, 48, buf, 0, 8, 8, 0, None) == 0         # empty batch: nothing launched
 
 
 def test_swin_param_layout_matches_the_published_trunk_sizes(lib):
